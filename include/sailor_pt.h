@@ -1,0 +1,165 @@
+/*
+ * sailor_pt.h — C-ABI of the B200 path tracer that replaces Sailor's CPU path tracer (Runtime/Raytracing).
+ *
+ * The reference has no FFI for this path: its only surface is the C++ class
+ *     Sailor::Raytracing::PathTracer { struct Params; static ParseCommandLineArgs(...); void Run(const Params&); }
+ * (reference Runtime/Raytracing/PathTracer.h:17-36).  This header follows the reference's existing C export
+ * convention (reference Lib/DllMain.cpp:9-144: extern "C", POD arguments only, failures by return value, no
+ * exceptions across the boundary) and keeps Params field-for-field (PathTracer.h:21-32).
+ *
+ * Two libraries export exactly this set:
+ *   - sailor_b200/libsailor_pt_cuda.so : the product (CUDA, sm_100a).  No CPU fallback: every entry point that
+ *     computes returns SAILOR_PT_ERR_NO_DEVICE when no CUDA device is usable.
+ *   - oracle/_ref/libsailor_pt_ref.so  : the test oracle (the reference's own C++ compiled with g++), used only
+ *     by tests/, smoke() and the bench's CPU-baseline legs.
+ *
+ * All buffers are caller-allocated host memory unless a name ends in `Device`.
+ */
+#ifndef SAILOR_PT_H
+#define SAILOR_PT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define SAILOR_PT_API __declspec(dllexport)
+#else
+#define SAILOR_PT_API __attribute__((visibility("default")))
+#endif
+
+/* ---- error codes (negative = failure, like the reference's bool/count returns in Lib/DllMain.cpp:78-137) ---- */
+enum {
+	SAILOR_PT_OK = 0,
+	SAILOR_PT_ERR_ARG = -1,        /* null / inconsistent argument */
+	SAILOR_PT_ERR_IO = -2,         /* file missing / unreadable / unwritable */
+	SAILOR_PT_ERR_FORMAT = -3,     /* glTF / PNG content not understood */
+	SAILOR_PT_ERR_NO_DEVICE = -4,  /* product only: CUDA device or kernel image unavailable */
+	SAILOR_PT_ERR_CUDA = -5,       /* product only: a CUDA call failed (message via SailorPt_LastError) */
+	SAILOR_PT_ERR_LIMIT = -6,      /* > 256 materials / > 255 textures (reference u8 slots, MaterialUtils.h:157-174) */
+	SAILOR_PT_ERR_UNSUPPORTED = -7
+};
+
+/* Mirrors PathTracer::Params (reference PathTracer.h:21-32).  Fields after `ambient` are extensions the
+ * reference lacks; zero means "reference behaviour". */
+typedef struct SailorPtParams {
+	const char* pathToModel;      /* m_pathToModel */
+	const char* output;           /* m_output (PNG); NULL/"" = do not write a file */
+	const char* camera;           /* m_camera; NULL/"" = first camera */
+	uint32_t height;              /* m_height */
+	uint32_t numSamples;          /* m_numSamples        (S: importance samples at the first hit) */
+	uint32_t numAmbientSamples;   /* m_numAmbientSamples (A: hemisphere samples at the first hit) */
+	uint32_t maxBounces;          /* m_maxBounces */
+	uint32_t msaa;                /* m_msaa (primary samples per pixel) */
+	float ambient[3];             /* m_ambient */
+	/* extensions */
+	uint32_t widthOverride;       /* 0: width = uint(height * aspect) (PathTracer.cpp:137-142) */
+	uint64_t seed;                /* RNG stream key; the reference uses unseeded rand() */
+	uint32_t rowBegin, rowEnd;    /* render only image rows [rowBegin,rowEnd) of the task grid (multi-GPU shard); 0,0 = all */
+	uint32_t msaaBegin, msaaEnd;  /* render only primary-sample indices [msaaBegin,msaaEnd); 0,0 = all */
+} SailorPtParams;
+
+typedef struct SailorPtScene SailorPtScene; /* opaque */
+
+/* One flattened triangle in the reference's Math::Triangle field order (reference Math/Bounds.h:12-25):
+ * centroid(3) vertices(9) normals(9) tangent(9) bitangent(9) uvs(6) uvs2(6) = 51 floats, + material index. */
+#define SAILOR_PT_TRI_FLOATS 51
+
+/* The reference's BVH node (reference Raytracing/BVH.h:13-24), 32 bytes. */
+typedef struct SailorPtBvhNode {
+	float aabbMin[3];
+	uint32_t leftFirst;
+	float aabbMax[3];
+	uint32_t triCount;
+} SailorPtBvhNode;
+
+/* One closest-hit result (the fields of Math::RaycastHit the integrator consumes, Bounds.h:59-71). */
+typedef struct SailorPtHit {
+	float t;          /* m_rayLenght; +inf when no hit */
+	float baryU;      /* m_barycentricCoordinate.y */
+	float baryV;      /* m_barycentricCoordinate.z */
+	uint32_t triId;   /* m_triangleIndex (original, pre-BVH order); 0xFFFFFFFF when no hit */
+} SailorPtHit;
+
+typedef struct SailorPtStats {
+	uint64_t rays;            /* closest-hit queries (BVH::IntersectBVH calls) of the last call */
+	uint64_t primarySamples;  /* Raytrace() evaluations at depth 0 of the last call */
+	uint64_t boxTests;        /* oracle (counting build) only: IntersectRayAABB calls */
+	uint64_t triTests;        /* oracle (counting build) only: IntersectRayTriangle calls */
+	double secondsTotal;      /* wall time of the last call (host clock) */
+	double secondsFlatten;    /* device/CPU time per stage of the last call, seconds */
+	double secondsBvhBuild;
+	double secondsTraverse;   /* product: sum of traversal-kernel launches (CUDA events on the launch stream) */
+	double secondsShade;
+	double secondsOutput;
+	uint32_t traverseLaunches;
+	uint32_t kernelLaunches;  /* product: all kernel launches of the last call */
+	uint32_t threads;         /* oracle: worker threads used */
+	uint32_t reserved;
+} SailorPtStats;
+
+/* ---- the reference entry points (PathTracer.h:34-36) ---- */
+
+/* PathTracer::ParseCommandLineArgs (PathTracer.cpp:30-73): --in --out --height --samples --bounces --camera
+ * --ambient RRGGBB.  Strings stay owned by the library until the next call on the same thread. */
+SAILOR_PT_API int32_t SailorPt_ParseCommandLineArgs(SailorPtParams* params, const char** args, int32_t num);
+
+/* PathTracer::Run (PathTracer.cpp:75-575): glTF in, PNG out.  Blocking. */
+SAILOR_PT_API int32_t SailorPt_Run(const SailorPtParams* params);
+
+/* ---- staged entry points (the same pipeline, one stage per call; used by parity tests and the bench) ---- */
+
+/* Load + flatten (PathTracer.cpp:84-162, MaterialUtils.cpp:64-198) + materials/textures/lights (:164-381). */
+SAILOR_PT_API int32_t SailorPt_SceneLoad(const char* pathToModel, SailorPtScene** outScene);
+SAILOR_PT_API void SailorPt_SceneFree(SailorPtScene* scene);
+/* counts[0..5] = triangles, materials, textures, directional lights, cameras, BVH nodes used (0 before build) */
+SAILOR_PT_API int32_t SailorPt_SceneCounts(const SailorPtScene* scene, uint32_t counts[6]);
+/* triangles: numTriangles*SAILOR_PT_TRI_FLOATS floats; materialIndex: numTriangles bytes (either may be NULL). */
+SAILOR_PT_API int32_t SailorPt_SceneGetTriangles(const SailorPtScene* scene, float* triangles, uint8_t* materialIndex);
+
+/* BVH::BuildBVH (BVH.cpp:280-338).  Idempotent. */
+SAILOR_PT_API int32_t SailorPt_BuildBVH(SailorPtScene* scene);
+/* nodes: 2N-1 reference-layout nodes (only counts[5] are meaningful); triIdxMapping: N entries (reordered->original). */
+SAILOR_PT_API int32_t SailorPt_GetBVH(const SailorPtScene* scene, SailorPtBvhNode* nodes, uint32_t* triIdxMapping);
+
+/* Camera + image size for params (PathTracer.cpp:102-153,390-403).
+ * cam[0..2]=position, [3..5]=pixel00Dir, [6..8]=pixelDeltaU, [9..11]=pixelDeltaV. */
+SAILOR_PT_API int32_t SailorPt_GetCamera(const SailorPtScene* scene, const SailorPtParams* params,
+	uint32_t* width, uint32_t* height, float cam[12]);
+
+/* BVH::IntersectBVH (BVH.cpp:122-191) for `count` rays: origin/dir 3 floats each, ignoreTri may be NULL. */
+SAILOR_PT_API int32_t SailorPt_IntersectRays(SailorPtScene* scene, uint32_t count, const float* origins,
+	const float* directions, const uint32_t* ignoreTri, SailorPtHit* hits);
+
+/* Primary ray of sample 0 (offset .5,.5; PathTracer.cpp:458-466) for every pixel, in task order
+ * (index = y*width + x with y the task row, i.e. before the row flip of :449). */
+SAILOR_PT_API int32_t SailorPt_PrimaryHits(SailorPtScene* scene, const SailorPtParams* params, SailorPtHit* hits);
+
+/* Tile loop + Raytrace (PathTracer.cpp:418-487, 622-879): linear accumulator, width*height*3 floats, rows as the
+ * reference stores them (flipped, :449).  srgb8 (width*height*3 bytes, may be NULL) = output stage (:535-565). */
+SAILOR_PT_API int32_t SailorPt_Render(SailorPtScene* scene, const SailorPtParams* params, float* linearRGB,
+	uint8_t* srgb8);
+
+/* Output stage alone (PathTracer.cpp:535-565 + Core/Utils.cpp:48-57). */
+SAILOR_PT_API int32_t SailorPt_OutputStage(uint32_t width, uint32_t height, const float* linearRGB, uint8_t* srgb8);
+
+/* CombinedSampler2D::Sample (MaterialUtils.h:75-124) on texture `textureIndex`: uv 2 floats per sample, out 4
+ * floats per sample (vec3 textures leave .w = 0). */
+SAILOR_PT_API int32_t SailorPt_SampleTexture(SailorPtScene* scene, uint32_t textureIndex, uint32_t count,
+	const float* uv, float* out);
+
+/* LightingModel function table (LightingModel.cpp:28-386) on `count` inputs; see tests/test_lighting.py for the
+ * record layout (in: 24 floats, out: 28 floats). */
+SAILOR_PT_API int32_t SailorPt_EvalLighting(uint32_t count, const float* in, float* out);
+
+SAILOR_PT_API int32_t SailorPt_GetStats(SailorPtStats* stats);
+SAILOR_PT_API const char* SailorPt_LastError(void);
+/* "cuda sm_100a" for the product, "reference-cpu" for the oracle. */
+SAILOR_PT_API const char* SailorPt_Backend(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

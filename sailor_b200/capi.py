@@ -1,0 +1,274 @@
+"""ctypes binding of include/sailor_pt.h.
+
+The same C-ABI is exported by the product (`sailor_b200/libsailor_pt_cuda.so`) and by the test oracle
+(`oracle/_ref/libsailor_pt_ref.so`); `Library(path)` binds whichever file it is given.  The product package only
+ever binds its own CUDA library (see `sailor_b200/__init__.py`); the oracle is bound by tests/ and bench.py only.
+
+Host-side mirror of the reference interface (reference Runtime/Raytracing/PathTracer.h:17-36):
+`Params` keeps the reference's field names, `PathTracer.parse_command_line_args` / `PathTracer.run` keep the
+reference's method names and error behaviour (return value, no exception for a bad scene: the reference logs and
+returns, PathTracer.cpp:94-98).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+TRI_FLOATS = 51
+
+OK = 0
+ERR_ARG, ERR_IO, ERR_FORMAT, ERR_NO_DEVICE, ERR_CUDA, ERR_LIMIT, ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6, -7
+
+
+class SailorPtParams(C.Structure):
+    _fields_ = [
+        ("pathToModel", C.c_char_p), ("output", C.c_char_p), ("camera", C.c_char_p),
+        ("height", C.c_uint32), ("numSamples", C.c_uint32), ("numAmbientSamples", C.c_uint32),
+        ("maxBounces", C.c_uint32), ("msaa", C.c_uint32), ("ambient", C.c_float * 3),
+        ("widthOverride", C.c_uint32), ("seed", C.c_uint64),
+        ("rowBegin", C.c_uint32), ("rowEnd", C.c_uint32), ("msaaBegin", C.c_uint32), ("msaaEnd", C.c_uint32),
+    ]
+
+
+class SailorPtStats(C.Structure):
+    _fields_ = [
+        ("rays", C.c_uint64), ("primarySamples", C.c_uint64), ("boxTests", C.c_uint64), ("triTests", C.c_uint64),
+        ("secondsTotal", C.c_double), ("secondsFlatten", C.c_double), ("secondsBvhBuild", C.c_double),
+        ("secondsTraverse", C.c_double), ("secondsShade", C.c_double), ("secondsOutput", C.c_double),
+        ("traverseLaunches", C.c_uint32), ("kernelLaunches", C.c_uint32), ("threads", C.c_uint32),
+        ("reserved", C.c_uint32),
+    ]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+BVH_NODE_DTYPE = np.dtype([("aabbMin", "<f4", 3), ("leftFirst", "<u4"), ("aabbMax", "<f4", 3), ("triCount", "<u4")])
+HIT_DTYPE = np.dtype([("t", "<f4"), ("baryU", "<f4"), ("baryV", "<f4"), ("triId", "<u4")])
+
+# every symbol include/sailor_pt.h declares (tests check the built libraries export all of them)
+SYMBOLS = [
+    "SailorPt_ParseCommandLineArgs", "SailorPt_Run", "SailorPt_SceneLoad", "SailorPt_SceneFree",
+    "SailorPt_SceneCounts", "SailorPt_SceneGetTriangles", "SailorPt_BuildBVH", "SailorPt_GetBVH",
+    "SailorPt_GetCamera", "SailorPt_IntersectRays", "SailorPt_PrimaryHits", "SailorPt_Render",
+    "SailorPt_OutputStage", "SailorPt_SampleTexture", "SailorPt_EvalLighting", "SailorPt_GetStats",
+    "SailorPt_LastError", "SailorPt_Backend",
+]
+
+
+class SailorPtError(RuntimeError):
+    def __init__(self, code, what, detail=""):
+        super().__init__("%s failed with code %d%s" % (what, code, (": " + detail) if detail else ""))
+        self.code = code
+
+
+def _ptr(a, ctype):
+    return a.ctypes.data_as(C.POINTER(ctype)) if a is not None else None
+
+
+class Params:
+    """PathTracer::Params (reference PathTracer.h:21-32) + the documented extensions."""
+
+    def __init__(self, path_to_model="", output="", camera="", height=512, num_samples=1, num_ambient_samples=1,
+                 max_bounces=4, msaa=1, ambient=(0.0, 0.0, 0.0), width_override=0, seed=0,
+                 rows=(0, 0), msaa_range=(0, 0)):
+        self.m_pathToModel = path_to_model
+        self.m_output = output
+        self.m_camera = camera
+        self.m_height = height
+        self.m_numSamples = num_samples
+        self.m_numAmbientSamples = num_ambient_samples
+        self.m_maxBounces = max_bounces
+        self.m_msaa = msaa
+        self.m_ambient = tuple(ambient)
+        self.width_override = width_override
+        self.seed = seed
+        self.rows = tuple(rows)
+        self.msaa_range = tuple(msaa_range)
+
+    def to_c(self):
+        p = SailorPtParams()
+        self._keep = [os.fsencode(self.m_pathToModel), os.fsencode(self.m_output), self.m_camera.encode()]
+        p.pathToModel, p.output, p.camera = self._keep
+        p.height, p.numSamples, p.numAmbientSamples = self.m_height, self.m_numSamples, self.m_numAmbientSamples
+        p.maxBounces, p.msaa = self.m_maxBounces, self.m_msaa
+        p.ambient[0], p.ambient[1], p.ambient[2] = self.m_ambient
+        p.widthOverride, p.seed = self.width_override, self.seed
+        p.rowBegin, p.rowEnd = self.rows
+        p.msaaBegin, p.msaaEnd = self.msaa_range
+        return p
+
+    @staticmethod
+    def from_samples(samples, **kw):
+        """`--samples n` decoding of PathTracer.cpp:48-54 (msaa = n<=32 ? min(4,n) : 8; S = max(1, lround(n/msaa))).
+        numAmbientSamples := numSamples (the reference never sets it)."""
+        msaa = min(4, samples) if samples <= 32 else 8
+        s = max(1, int(np.float32(samples) / np.float32(msaa) + np.float32(0.5)))
+        return Params(num_samples=s, num_ambient_samples=s, msaa=msaa, **kw)
+
+
+class Library:
+    def __init__(self, path):
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.path = path
+        self.lib = lib = C.CDLL(path)
+        P = C.POINTER
+        lib.SailorPt_ParseCommandLineArgs.argtypes = [P(SailorPtParams), P(C.c_char_p), C.c_int32]
+        lib.SailorPt_Run.argtypes = [P(SailorPtParams)]
+        lib.SailorPt_SceneLoad.argtypes = [C.c_char_p, P(C.c_void_p)]
+        lib.SailorPt_SceneFree.argtypes = [C.c_void_p]
+        lib.SailorPt_SceneFree.restype = None
+        lib.SailorPt_SceneCounts.argtypes = [C.c_void_p, P(C.c_uint32)]
+        lib.SailorPt_SceneGetTriangles.argtypes = [C.c_void_p, P(C.c_float), P(C.c_uint8)]
+        lib.SailorPt_BuildBVH.argtypes = [C.c_void_p]
+        lib.SailorPt_GetBVH.argtypes = [C.c_void_p, C.c_void_p, P(C.c_uint32)]
+        lib.SailorPt_GetCamera.argtypes = [C.c_void_p, P(SailorPtParams), P(C.c_uint32), P(C.c_uint32), P(C.c_float)]
+        lib.SailorPt_IntersectRays.argtypes = [C.c_void_p, C.c_uint32, P(C.c_float), P(C.c_float), P(C.c_uint32), C.c_void_p]
+        lib.SailorPt_PrimaryHits.argtypes = [C.c_void_p, P(SailorPtParams), C.c_void_p]
+        lib.SailorPt_Render.argtypes = [C.c_void_p, P(SailorPtParams), P(C.c_float), P(C.c_uint8)]
+        lib.SailorPt_OutputStage.argtypes = [C.c_uint32, C.c_uint32, P(C.c_float), P(C.c_uint8)]
+        lib.SailorPt_SampleTexture.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, P(C.c_float), P(C.c_float)]
+        lib.SailorPt_EvalLighting.argtypes = [C.c_uint32, P(C.c_float), P(C.c_float)]
+        lib.SailorPt_GetStats.argtypes = [P(SailorPtStats)]
+        lib.SailorPt_LastError.restype = C.c_char_p
+        lib.SailorPt_Backend.restype = C.c_char_p
+        for s in SYMBOLS:
+            f = getattr(lib, s)
+            if s not in ("SailorPt_SceneFree", "SailorPt_LastError", "SailorPt_Backend"):
+                f.restype = C.c_int32
+
+    # -- helpers -------------------------------------------------------------------------------------------
+    def check(self, rc, what):
+        if rc != OK:
+            raise SailorPtError(rc, what, (self.lib.SailorPt_LastError() or b"").decode(errors="replace"))
+
+    def backend(self):
+        return self.lib.SailorPt_Backend().decode()
+
+    def stats(self):
+        s = SailorPtStats()
+        self.check(self.lib.SailorPt_GetStats(C.byref(s)), "SailorPt_GetStats")
+        return s.as_dict()
+
+    # -- the reference entry points ------------------------------------------------------------------------
+    def parse_command_line_args(self, params: Params, args):
+        """PathTracer::ParseCommandLineArgs (PathTracer.cpp:30-73); args[0] is skipped like argv[0]."""
+        cp = params.to_c()
+        arr = (C.c_char_p * len(args))(*[a.encode() for a in args])
+        self.check(self.lib.SailorPt_ParseCommandLineArgs(C.byref(cp), arr, len(args)), "SailorPt_ParseCommandLineArgs")
+        params.m_pathToModel = (cp.pathToModel or b"").decode()
+        params.m_output = (cp.output or b"").decode()
+        params.m_camera = (cp.camera or b"").decode()
+        params.m_height, params.m_numSamples, params.m_numAmbientSamples = cp.height, cp.numSamples, cp.numAmbientSamples
+        params.m_maxBounces, params.m_msaa = cp.maxBounces, cp.msaa
+        params.m_ambient = (cp.ambient[0], cp.ambient[1], cp.ambient[2])
+        return params
+
+    def run(self, params: Params):
+        """PathTracer::Run (PathTracer.cpp:75-575). Returns the C-ABI code (0 = ok) like the reference returns quietly."""
+        cp = params.to_c()
+        return self.lib.SailorPt_Run(C.byref(cp))
+
+    def load_scene(self, path):
+        return Scene(self, path)
+
+    def output_stage(self, linear):
+        linear = np.ascontiguousarray(linear, dtype=np.float32)
+        h, w, _ = linear.shape
+        out = np.empty((h, w, 3), np.uint8)
+        self.check(self.lib.SailorPt_OutputStage(w, h, _ptr(linear, C.c_float), _ptr(out, C.c_uint8)), "SailorPt_OutputStage")
+        return out
+
+    def eval_lighting(self, records):
+        records = np.ascontiguousarray(records, dtype=np.float32)
+        assert records.ndim == 2 and records.shape[1] == 24
+        out = np.empty((records.shape[0], 28), np.float32)
+        self.check(self.lib.SailorPt_EvalLighting(records.shape[0], _ptr(records, C.c_float), _ptr(out, C.c_float)), "SailorPt_EvalLighting")
+        return out
+
+
+class Scene:
+    def __init__(self, library: Library, path):
+        self.L = library
+        self.h = C.c_void_p()
+        library.check(library.lib.SailorPt_SceneLoad(os.fsencode(path), C.byref(self.h)), "SailorPt_SceneLoad")
+
+    def close(self):
+        if self.h:
+            self.L.lib.SailorPt_SceneFree(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def counts(self):
+        c = (C.c_uint32 * 6)()
+        self.L.check(self.L.lib.SailorPt_SceneCounts(self.h, c), "SailorPt_SceneCounts")
+        return dict(zip(("triangles", "materials", "textures", "lights", "cameras", "nodes"), list(c)))
+
+    def triangles(self):
+        n = self.counts()["triangles"]
+        tris = np.empty((n, TRI_FLOATS), np.float32)
+        mat = np.empty(n, np.uint8)
+        self.L.check(self.L.lib.SailorPt_SceneGetTriangles(self.h, _ptr(tris, C.c_float), _ptr(mat, C.c_uint8)), "SailorPt_SceneGetTriangles")
+        return tris, mat
+
+    def build_bvh(self):
+        self.L.check(self.L.lib.SailorPt_BuildBVH(self.h), "SailorPt_BuildBVH")
+
+    def bvh(self):
+        self.build_bvh()
+        c = self.counts()
+        n = c["triangles"]
+        nodes = np.zeros(2 * n - 1, BVH_NODE_DTYPE)
+        mapping = np.empty(n, np.uint32)
+        self.L.check(self.L.lib.SailorPt_GetBVH(self.h, nodes.ctypes.data, _ptr(mapping, C.c_uint32)), "SailorPt_GetBVH")
+        return nodes[:c["nodes"]], mapping
+
+    def camera(self, params: Params):
+        cp = params.to_c()
+        w, h = C.c_uint32(), C.c_uint32()
+        cam = (C.c_float * 12)()
+        self.L.check(self.L.lib.SailorPt_GetCamera(self.h, C.byref(cp), C.byref(w), C.byref(h), cam), "SailorPt_GetCamera")
+        return w.value, h.value, np.array(list(cam), np.float32)
+
+    def intersect_rays(self, origins, directions, ignore=None):
+        o = np.ascontiguousarray(origins, dtype=np.float32)
+        d = np.ascontiguousarray(directions, dtype=np.float32)
+        n = o.shape[0]
+        ig = np.ascontiguousarray(ignore, dtype=np.uint32) if ignore is not None else None
+        hits = np.empty(n, HIT_DTYPE)
+        self.L.check(self.L.lib.SailorPt_IntersectRays(self.h, n, _ptr(o, C.c_float), _ptr(d, C.c_float),
+                                                      _ptr(ig, C.c_uint32), hits.ctypes.data), "SailorPt_IntersectRays")
+        return hits
+
+    def primary_hits(self, params: Params):
+        w, h, _ = self.camera(params)
+        cp = params.to_c()
+        hits = np.empty(w * h, HIT_DTYPE)
+        self.L.check(self.L.lib.SailorPt_PrimaryHits(self.h, C.byref(cp), hits.ctypes.data), "SailorPt_PrimaryHits")
+        return hits.reshape(h, w)
+
+    def render(self, params: Params, want_srgb=True):
+        w, h, _ = self.camera(params)
+        cp = params.to_c()
+        lin = np.empty((h, w, 3), np.float32)
+        srgb = np.empty((h, w, 3), np.uint8) if want_srgb else None
+        self.L.check(self.L.lib.SailorPt_Render(self.h, C.byref(cp), _ptr(lin, C.c_float), _ptr(srgb, C.c_uint8)), "SailorPt_Render")
+        return lin, srgb
+
+    def sample_texture(self, index, uv):
+        uv = np.ascontiguousarray(uv, dtype=np.float32)
+        out = np.empty((uv.shape[0], 4), np.float32)
+        self.L.check(self.L.lib.SailorPt_SampleTexture(self.h, index, uv.shape[0], _ptr(uv, C.c_float), _ptr(out, C.c_float)), "SailorPt_SampleTexture")
+        return out
