@@ -1,0 +1,201 @@
+// backend.cu — implementation of backend.h (CUDA product build; SPT_EMU host build for tests/emu only).
+#include "backend.h"
+#include "../../include/sailor_pt.h"
+#include <chrono>
+#include <stdio.h>
+
+namespace spt
+{
+	bool Ctx::Fail(const char* what, int code)
+	{
+		if (ok)
+		{
+			ok = false;
+			char buf[512];
+#if !defined(SPT_EMU)
+			snprintf(buf, sizeof(buf), "%s -> %s (%d)", what, cudaGetErrorString((cudaError_t)code), code);
+#else
+			snprintf(buf, sizeof(buf), "%s -> %d", what, code);
+#endif
+			error = buf;
+		}
+		return false;
+	}
+
+#if !defined(SPT_EMU)
+	// ------------------------------------------------------------------------------------------------ CUDA
+	int Ctx::Init()
+	{
+		int count = 0;
+		if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0)
+		{
+			cudaGetLastError();
+			ok = false;
+			error = "no CUDA device: the sailor_b200 product library has no CPU path";
+			return SAILOR_PT_ERR_NO_DEVICE;
+		}
+		if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess ||
+			cudaEventCreate(&evA) != cudaSuccess || cudaEventCreate(&evB) != cudaSuccess ||
+			cudaEventCreate(&ev[0]) != cudaSuccess || cudaEventCreate(&ev[1]) != cudaSuccess || cudaEventCreate(&ev[2]) != cudaSuccess || cudaEventCreate(&ev[3]) != cudaSuccess)
+		{
+			Fail("cudaStreamCreate/cudaEventCreate", (int)cudaGetLastError());
+			return SAILOR_PT_ERR_CUDA;
+		}
+		ok = true;
+		return SAILOR_PT_OK;
+	}
+	void Ctx::Destroy()
+	{
+		if (evA) cudaEventDestroy(evA);
+		if (evB) cudaEventDestroy(evB);
+		for (int i = 0; i < 4; i++) { if (ev[i]) cudaEventDestroy(ev[i]); ev[i] = nullptr; }
+		if (stream) cudaStreamDestroy(stream);
+		evA = evB = nullptr; stream = nullptr;
+	}
+	void Ctx::Sync() { if (ok) SPT_CUDA_CHECK(*this, cudaStreamSynchronize(stream)); }
+	void Ctx::TimerStart() { if (ok) SPT_CUDA_CHECK(*this, cudaEventRecord(evA, stream)); }
+	double Ctx::TimerStop()
+	{
+		if (!ok) return 0.0;
+		SPT_CUDA_CHECK(*this, cudaEventRecord(evB, stream));
+		SPT_CUDA_CHECK(*this, cudaEventSynchronize(evB));
+		float ms = 0.0f;
+		if (ok) SPT_CUDA_CHECK(*this, cudaEventElapsedTime(&ms, evA, evB));
+		return (double)ms * 1e-3;
+	}
+
+	void Ctx::Mark(int i) { if (ok) SPT_CUDA_CHECK(*this, cudaEventRecord(ev[i], stream)); }
+	double Ctx::Between(int i, int j)
+	{
+		float ms = 0.0f;
+		if (ok) SPT_CUDA_CHECK(*this, cudaEventElapsedTime(&ms, ev[i], ev[j]));
+		return (double)ms * 1e-3;
+	}
+
+	void* DevAllocBytes(Ctx& ctx, size_t bytes)
+	{
+		void* p = nullptr;
+		if (!ctx.ok) return nullptr;
+		SPT_CUDA_CHECK(ctx, cudaMalloc(&p, bytes));
+		return ctx.ok ? p : nullptr;
+	}
+	void DevFreeBytes(void* p) { cudaFree(p); }
+	void DevUpload(Ctx& ctx, void* dst, const void* src, size_t bytes) { if (ctx.ok) SPT_CUDA_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx.stream)); }
+	void DevDownload(Ctx& ctx, void* dst, const void* src, size_t bytes)
+	{
+		if (!ctx.ok) return;
+		SPT_CUDA_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx.stream));
+		SPT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx.stream));
+	}
+	void DevMemset(Ctx& ctx, void* dst, int byte, size_t bytes) { if (ctx.ok) SPT_CUDA_CHECK(ctx, cudaMemsetAsync(dst, byte, bytes, ctx.stream)); }
+	void DevCopy(Ctx& ctx, void* dst, const void* src, size_t bytes) { if (ctx.ok) SPT_CUDA_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx.stream)); }
+
+	// ---- exclusive scan: reduce-then-scan, 2048 items per CTA, coalesced, warp shuffles -----------------
+	namespace
+	{
+		constexpr uint32_t kScanThreads = 256, kScanItems = 8, kScanTile = kScanThreads * kScanItems;
+
+		__device__ __forceinline__ uint32_t BlockExclusiveScan(uint32_t v, uint32_t& total)
+		{
+			__shared__ uint32_t warpSums[kScanThreads / 32];
+			const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+			uint32_t incl = v;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+			if (lane == 31) warpSums[warp] = incl;
+			__syncthreads();
+			if (warp == 0)
+			{
+				uint32_t w = lane < kScanThreads / 32 ? warpSums[lane] : 0;
+#pragma unroll
+				for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+				if (lane < kScanThreads / 32) warpSums[lane] = w;
+			}
+			__syncthreads();
+			total = warpSums[kScanThreads / 32 - 1];
+			const uint32_t base = warp ? warpSums[warp - 1] : 0;
+			__syncthreads();
+			return base + incl - v;
+		}
+
+		__global__ void __launch_bounds__(kScanThreads) k_scan_reduce(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ tileSums)
+		{
+			const uint32_t base = blockIdx.x * kScanTile;
+			uint32_t s = 0;
+#pragma unroll
+			for (uint32_t k = 0; k < kScanItems; k++) { const uint32_t i = base + k * kScanThreads + threadIdx.x; if (i < n) s += in[i]; }
+			uint32_t total;
+			BlockExclusiveScan(s, total);
+			if (threadIdx.x == 0) tileSums[blockIdx.x] = total;
+		}
+
+		__global__ void __launch_bounds__(kScanThreads) k_scan_tiles(uint32_t* tileSums, uint32_t numTiles)
+		{
+			uint32_t carry = 0;
+			for (uint32_t base = 0; base < numTiles; base += kScanThreads)
+			{
+				const uint32_t i = base + threadIdx.x;
+				const uint32_t v = i < numTiles ? tileSums[i] : 0;
+				uint32_t total;
+				const uint32_t ex = BlockExclusiveScan(v, total);
+				if (i < numTiles) tileSums[i] = carry + ex;
+				carry += total;
+			}
+			if (threadIdx.x == 0) tileSums[numTiles] = carry;
+		}
+
+		__global__ void __launch_bounds__(kScanThreads) k_scan_apply(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n, const uint32_t* __restrict__ tileOffsets, uint32_t numTiles)
+		{
+			// each thread owns kScanItems CONSECUTIVE items so the scan is a plain running sum per thread
+			const uint32_t base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+			uint32_t v[kScanItems];
+			uint32_t s = 0;
+#pragma unroll
+			for (uint32_t k = 0; k < kScanItems; k++) { v[k] = (base + k) < n ? in[base + k] : 0; s += v[k]; }
+			uint32_t total;
+			uint32_t run = tileOffsets[blockIdx.x] + BlockExclusiveScan(s, total);
+#pragma unroll
+			for (uint32_t k = 0; k < kScanItems; k++) { if ((base + k) < n) out[base + k] = run; run += v[k]; }
+			if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = tileOffsets[numTiles];
+		}
+	}
+
+	void ExclusiveScanU32(Ctx& ctx, const uint32_t* in, uint32_t* out, uint32_t n, DevBuf<uint32_t>& scratch)
+	{
+		if (!ctx.ok) return;
+		if (n == 0) { DevMemset(ctx, out, 0, sizeof(uint32_t)); return; }
+		const uint32_t numTiles = (n + kScanTile - 1) / kScanTile;
+		scratch.Ensure(ctx, numTiles + 1);
+		if (!ctx.ok) return;
+		k_scan_reduce<<<numTiles, kScanThreads, 0, ctx.stream>>>(in, n, scratch.p);
+		k_scan_tiles<<<1, kScanThreads, 0, ctx.stream>>>(scratch.p, numTiles);
+		k_scan_apply<<<numTiles, kScanThreads, 0, ctx.stream>>>(in, out, n, scratch.p, numTiles);
+		ctx.kernelLaunches += 3;
+		SPT_CUDA_CHECK(ctx, cudaGetLastError());
+	}
+
+#else
+	// ------------------------------------------------------------------------------------------------ EMU (tests only)
+	static std::chrono::steady_clock::time_point g_t0, g_marks[4];
+	void Ctx::Mark(int i) { g_marks[i] = std::chrono::steady_clock::now(); }
+	double Ctx::Between(int i, int j) { return std::chrono::duration<double>(g_marks[j] - g_marks[i]).count(); }
+	int Ctx::Init() { ok = true; return SAILOR_PT_OK; }
+	void Ctx::Destroy() {}
+	void Ctx::Sync() {}
+	void Ctx::TimerStart() { g_t0 = std::chrono::steady_clock::now(); }
+	double Ctx::TimerStop() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - g_t0).count(); }
+	void* DevAllocBytes(Ctx&, size_t bytes) { return malloc(bytes ? bytes : 1); }
+	void DevFreeBytes(void* p) { free(p); }
+	void DevUpload(Ctx&, void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
+	void DevDownload(Ctx&, void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
+	void DevMemset(Ctx&, void* dst, int byte, size_t bytes) { memset(dst, byte, bytes); }
+	void DevCopy(Ctx&, void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
+	void ExclusiveScanU32(Ctx& ctx, const uint32_t* in, uint32_t* out, uint32_t n, DevBuf<uint32_t>&)
+	{
+		uint32_t s = 0;
+		for (uint32_t i = 0; i < n; i++) { out[i] = s; s += in[i]; }
+		out[n] = s;
+		ctx.kernelLaunches += 3;
+	}
+#endif
+}

@@ -1,0 +1,120 @@
+// backend.h — device memory, stream, launch and atomic primitives used by the pipeline.
+//
+// PRODUCT BUILD (nvcc, sm_100a): CUDA stream + cudaMalloc + real kernels.  There is no CPU execution path in the
+// product library: Ctx::Init() fails with SAILOR_PT_ERR_NO_DEVICE when no usable CUDA device exists.
+//
+// SPT_EMU (g++, tests/emu only): the same kernel bodies are compiled for the host and each "launch" is a serial
+// loop.  This exists because the development container has no GPU; it lets tests/ check the host orchestration and
+// the kernel logic against the oracle on CPU.  It is built only by tests/emu/build_emu.py into tests/emu/_build/,
+// is never loaded by the sailor_b200 package, and is not a fallback.
+#pragma once
+#include "hd.h"
+#include <stddef.h>
+#include <string>
+#include <vector>
+#include <string.h>
+#include <stdlib.h>
+
+#if !defined(SPT_EMU)
+#include <cuda_runtime.h>
+#endif
+
+namespace spt
+{
+	struct Ctx
+	{
+#if !defined(SPT_EMU)
+		cudaStream_t stream = nullptr;
+		cudaEvent_t evA = nullptr, evB = nullptr;
+		cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };   // per-iteration stage markers (integrator)
+#endif
+		uint32_t kernelLaunches = 0;
+		std::string error;
+		bool ok = true;
+
+		int Init();       // SAILOR_PT_OK or SAILOR_PT_ERR_NO_DEVICE
+		void Destroy();
+		void Sync();
+		bool Fail(const char* what, int code);
+		// GPU time of a bracketed region on the launch stream (seconds); emu: host clock
+		void TimerStart();
+		double TimerStop();
+		void Mark(int i);                  // record marker i on the launch stream
+		double Between(int i, int j);      // seconds between two recorded markers (after a sync)
+	};
+
+#if !defined(SPT_EMU)
+#define SPT_CUDA_CHECK(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { (ctx).Fail(#call, (int)e_); } } while (0)
+#endif
+
+	void* DevAllocBytes(Ctx& ctx, size_t bytes);
+	void DevFreeBytes(void* p);
+	void DevUpload(Ctx& ctx, void* dst, const void* src, size_t bytes);
+	void DevDownload(Ctx& ctx, void* dst, const void* src, size_t bytes);   // synchronises
+	void DevMemset(Ctx& ctx, void* dst, int byte, size_t bytes);
+	void DevCopy(Ctx& ctx, void* dst, const void* src, size_t bytes);
+
+	template<class T>
+	struct DevBuf
+	{
+		T* p = nullptr;
+		size_t n = 0;
+		DevBuf() = default;
+		DevBuf(const DevBuf&) = delete;
+		DevBuf& operator=(const DevBuf&) = delete;
+		~DevBuf() { Free(); }
+		void Free() { if (p) DevFreeBytes(p); p = nullptr; n = 0; }
+		void Alloc(Ctx& ctx, size_t count) { Free(); if (count) { p = (T*)DevAllocBytes(ctx, count * sizeof(T)); n = p ? count : 0; } }
+		void Ensure(Ctx& ctx, size_t count) { if (count > n) Alloc(ctx, count); }
+		void Upload(Ctx& ctx, const T* src, size_t count) { Ensure(ctx, count); if (count) DevUpload(ctx, p, src, count * sizeof(T)); }
+		void Upload(Ctx& ctx, const std::vector<T>& v) { Upload(ctx, v.data(), v.size()); }
+		void Download(Ctx& ctx, T* dst, size_t count) const { if (count) DevDownload(ctx, dst, p, count * sizeof(T)); }
+		void Zero(Ctx& ctx) { if (n) DevMemset(ctx, p, 0, n * sizeof(T)); }
+		void Zero(Ctx& ctx, size_t count) { if (count) DevMemset(ctx, p, 0, count * sizeof(T)); }
+	};
+
+	// ---- atomics usable from kernel bodies -------------------------------------------------------------
+#if !defined(SPT_EMU)
+	__device__ __forceinline__ void atomic_min_u32(uint32_t* p, uint32_t v) { atomicMin(p, v); }
+	__device__ __forceinline__ void atomic_max_u32(uint32_t* p, uint32_t v) { atomicMax(p, v); }
+	__device__ __forceinline__ uint32_t atomic_add_u32(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
+	__device__ __forceinline__ unsigned long long atomic_add_u64(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
+#define SPT_KERNEL_BODY __device__ __forceinline__
+#else
+	inline void atomic_min_u32(uint32_t* p, uint32_t v) { if (v < *p) *p = v; }
+	inline void atomic_max_u32(uint32_t* p, uint32_t v) { if (v > *p) *p = v; }
+	inline uint32_t atomic_add_u32(uint32_t* p, uint32_t v) { const uint32_t o = *p; *p = o + v; return o; }
+	inline unsigned long long atomic_add_u64(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
+#define SPT_KERNEL_BODY inline
+#endif
+
+	// ---- launch_for: functor f(i) for i in [0,n) ---------------------------------------------------------
+#if !defined(SPT_EMU)
+	template<class F>
+	__global__ void __launch_bounds__(256) k_for(uint32_t n, F f)
+	{
+		const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+		if (i < n) f(i);
+	}
+
+	template<class F>
+	inline void launch_for(Ctx& ctx, uint32_t n, const F& f)
+	{
+		if (!n || !ctx.ok) return;
+		k_for<F><<<(n + 255u) / 256u, 256, 0, ctx.stream>>>(n, f);
+		ctx.kernelLaunches++;
+		SPT_CUDA_CHECK(ctx, cudaGetLastError());
+	}
+#else
+	template<class F>
+	inline void launch_for(Ctx& ctx, uint32_t n, const F& f)
+	{
+		if (!ctx.ok) return;
+		for (uint32_t i = 0; i < n; i++) f(i);
+		ctx.kernelLaunches++;
+	}
+#endif
+
+	// out[i] = sum(in[0..i)), out has n+1 entries (out[n] = total).  in/out may not alias.
+	void ExclusiveScanU32(Ctx& ctx, const uint32_t* in, uint32_t* out, uint32_t n, DevBuf<uint32_t>& scratch);
+}

@@ -1,0 +1,361 @@
+// capi.cu — the C-ABI of include/sailor_pt.h for the product library libsailor_pt_cuda.so.
+//
+// Thin layer: argument checks, host<->device staging of the caller's buffers, stage sequencing.  All arithmetic of
+// the hot path runs in the kernels (flatten.cuh, bvh_build.cuh, traverse.cuh, integrator.cuh, output.cuh).
+// There is no CPU fallback: without a CUDA device every computing entry point returns SAILOR_PT_ERR_NO_DEVICE.
+#include "pipeline.cuh"
+#include "textures.cuh"
+#include "integrator.cuh"
+#include "render.cuh"
+#include "output.cuh"
+
+#include <memory>
+#include <string>
+#include <vector>
+
+using namespace spt;
+
+struct SailorPtScene { SceneDevice dev; };
+
+namespace
+{
+	thread_local std::string t_lastError;
+	SailorPtStats g_stats{};
+
+	int SetError(int code, const std::string& msg) { t_lastError = msg; return code; }
+	int FromCtx(SceneDevice& d, int rc)
+	{
+		if (!d.ctx.ok) { t_lastError = d.ctx.error; return rc == SAILOR_PT_OK ? SAILOR_PT_ERR_CUDA : rc; }
+		if (rc != SAILOR_PT_OK && !d.ctx.error.empty()) t_lastError = d.ctx.error;
+		return rc;
+	}
+
+	CameraGpu ToGpuCamera(const CameraSetup& c)
+	{
+		CameraGpu g;
+		g.pos = v3(c.pos[0], c.pos[1], c.pos[2]); g.pixel00Dir = v3(c.pixel00Dir[0], c.pixel00Dir[1], c.pixel00Dir[2]);
+		g.deltaU = v3(c.deltaU[0], c.deltaU[1], c.deltaU[2]); g.deltaV = v3(c.deltaV[0], c.deltaV[1], c.deltaV[2]);
+		g.width = c.width; g.height = c.height;
+		return g;
+	}
+
+	CameraSetup CameraOf(const SceneDevice& d, const SailorPtParams* p)
+	{
+		SailorPtParamsView v; v.camera = p->camera; v.height = p->height; v.widthOverride = p->widthOverride;
+		return SetupCamera(d.host, v);
+	}
+
+	// standalone context for entry points that take no scene (OutputStage, EvalLighting)
+	struct ScopedCtx
+	{
+		Ctx ctx; int rc;
+		ScopedCtx() { rc = ctx.Init(); }
+		~ScopedCtx() { ctx.Destroy(); }
+	};
+}
+
+extern "C" {
+
+const char* SailorPt_Backend(void)
+{
+#if defined(SPT_EMU)
+	return "emu-host (tests only)";
+#else
+	return "cuda sm_100a";
+#endif
+}
+const char* SailorPt_LastError(void) { return t_lastError.c_str(); }
+int32_t SailorPt_GetStats(SailorPtStats* s) { if (!s) return SAILOR_PT_ERR_ARG; *s = g_stats; return SAILOR_PT_OK; }
+
+int32_t SailorPt_ParseCommandLineArgs(SailorPtParams* res, const char** args, int32_t num)
+{
+	// PathTracer::ParseCommandLineArgs (PathTracer.cpp:30-73) + Utils::GetArgValue (Core/Utils.cpp:466-487)
+	if (!res || (!args && num > 0)) return SAILOR_PT_ERR_ARG;
+	static thread_local std::string sIn, sOut, sCam;
+	auto argValue = [&](int32_t& i) -> std::string
+		{
+			if (i + 1 >= num) return "";
+			std::string v = args[++i];
+			if (!v.empty() && v[0] == '\"')
+			{
+				while (i < num && v[v.length() - 1] != '\"') { ++i; v += " " + std::string(args[i]); }
+				v = v.substr(1, v.length() - 2);
+			}
+			return v;
+		};
+	for (int32_t i = 1; i < num; i++)
+	{
+		const std::string arg = args[i];
+		if (arg == "--in") { sIn = argValue(i); res->pathToModel = sIn.c_str(); }
+		else if (arg == "--out") { sOut = argValue(i); res->output = sOut.c_str(); }
+		else if (arg == "--height") res->height = (uint32_t)atoi(argValue(i).c_str());
+		else if (arg == "--samples")
+		{
+			const uint32_t samples = (uint32_t)atoi(argValue(i).c_str());
+			res->msaa = samples <= 32 ? (samples < 4u ? samples : 4u) : 8u;
+			const long r = lroundf((float)samples / (float)res->msaa);
+			res->numSamples = r > 1 ? (uint32_t)r : 1u;
+		}
+		else if (arg == "--bounces") res->maxBounces = (uint32_t)atoi(argValue(i).c_str());
+		else if (arg == "--camera") { sCam = argValue(i); res->camera = sCam.c_str(); }
+		else if (arg == "--ambient")
+		{
+			const std::string hex = argValue(i);
+			if (hex.size() < 6) return SAILOR_PT_ERR_ARG;   // the reference would throw from std::stoi here
+			const int r = (int)strtol(hex.substr(0, 2).c_str(), nullptr, 16), g = (int)strtol(hex.substr(2, 2).c_str(), nullptr, 16), b = (int)strtol(hex.substr(4, 2).c_str(), nullptr, 16);
+			res->ambient[0] = r / 255.0f; res->ambient[1] = g / 255.0f; res->ambient[2] = b / 255.0f;
+		}
+	}
+	return SAILOR_PT_OK;
+}
+
+int32_t SailorPt_SceneLoad(const char* path, SailorPtScene** outScene)
+{
+	if (!path || !outScene) return SAILOR_PT_ERR_ARG;
+	*outScene = nullptr;
+	std::unique_ptr<SailorPtScene> s(new SailorPtScene());
+	int rc = s->dev.ctx.Init();
+	if (rc != SAILOR_PT_OK) return SetError(rc, s->dev.ctx.error);
+	std::string err;
+	rc = LoadGltf(path, s->dev.host, err);
+	if (rc != SAILOR_PT_OK) { s->dev.ctx.Destroy(); return SetError(rc, err); }
+	s->dev.ctx.kernelLaunches = 0;
+	rc = FromCtx(s->dev, s->dev.Upload());
+	g_stats = s->dev.stats; g_stats.kernelLaunches = s->dev.ctx.kernelLaunches;
+	if (rc != SAILOR_PT_OK) { s->dev.ctx.Destroy(); return rc; }
+	*outScene = s.release();
+	return SAILOR_PT_OK;
+}
+
+void SailorPt_SceneFree(SailorPtScene* s)
+{
+	if (!s) return;
+	s->dev.ctx.Sync();
+	Ctx keep = s->dev.ctx;
+	delete s;
+	keep.Destroy();
+}
+
+int32_t SailorPt_SceneCounts(const SailorPtScene* s, uint32_t c[6])
+{
+	if (!s || !c) return SAILOR_PT_ERR_ARG;
+	c[0] = s->dev.numTris; c[1] = (uint32_t)s->dev.host.materials.size(); c[2] = (uint32_t)s->dev.host.textures.size();
+	c[3] = (uint32_t)s->dev.host.lights.size(); c[4] = (uint32_t)s->dev.host.cameras.size(); c[5] = s->dev.built ? s->dev.nodesUsed : 0;
+	return SAILOR_PT_OK;
+}
+
+int32_t SailorPt_SceneGetTriangles(const SailorPtScene* cs, float* tris, uint8_t* mat)
+{
+	if (!cs) return SAILOR_PT_ERR_ARG;
+	SailorPtScene* s = const_cast<SailorPtScene*>(cs);
+	const uint32_t n = s->dev.numTris;
+	if (!n) return SAILOR_PT_OK;
+	std::vector<V4> vtx((size_t)n * 3), cen(n), sh((size_t)n * 9); std::vector<V2> uv2((size_t)n * 3);
+	s->dev.vtx.Download(s->dev.ctx, vtx.data(), vtx.size()); s->dev.centroid.Download(s->dev.ctx, cen.data(), cen.size());
+	s->dev.shade.Download(s->dev.ctx, sh.data(), sh.size()); s->dev.uv2.Download(s->dev.ctx, uv2.data(), uv2.size());
+	if (!s->dev.ctx.ok) return FromCtx(s->dev, SAILOR_PT_ERR_CUDA);
+	for (uint32_t i = 0; i < n; i++)
+	{
+		if (tris)
+		{
+			float* o = tris + (size_t)i * SAILOR_PT_TRI_FLOATS;
+			const V4* S = sh.data() + (size_t)i * 9;
+			o[0] = cen[i].x; o[1] = cen[i].y; o[2] = cen[i].z;
+			for (int k = 0; k < 3; k++) { const V4& v = vtx[(size_t)i * 3 + k]; o[3 + k * 3] = v.x; o[4 + k * 3] = v.y; o[5 + k * 3] = v.z; }
+			for (int k = 0; k < 3; k++) { o[12 + k * 3] = S[k].x; o[13 + k * 3] = S[k].y; o[14 + k * 3] = S[k].z; }
+			for (int k = 0; k < 3; k++) { o[21 + k * 3] = S[3 + k].x; o[22 + k * 3] = S[3 + k].y; o[23 + k * 3] = S[3 + k].z; }
+			for (int k = 0; k < 3; k++) { o[30 + k * 3] = S[6 + k].x; o[31 + k * 3] = S[6 + k].y; o[32 + k * 3] = S[6 + k].z; }
+			o[39] = S[0].w; o[40] = S[1].w; o[41] = S[2].w; o[42] = S[3].w; o[43] = S[4].w; o[44] = S[5].w;
+			for (int k = 0; k < 3; k++) { o[45 + k * 2] = uv2[(size_t)i * 3 + k].x; o[46 + k * 2] = uv2[(size_t)i * 3 + k].y; }
+		}
+		if (mat) mat[i] = (uint8_t)f2u(cen[i].w);
+	}
+	return SAILOR_PT_OK;
+}
+
+int32_t SailorPt_BuildBVH(SailorPtScene* s)
+{
+	if (!s) return SAILOR_PT_ERR_ARG;
+	const bool was = s->dev.built;
+	s->dev.ctx.kernelLaunches = 0;
+	const int rc = FromCtx(s->dev, s->dev.BuildBvh());
+	if (!was) { g_stats = s->dev.stats; g_stats.kernelLaunches = s->dev.ctx.kernelLaunches; }
+	return rc;
+}
+
+int32_t SailorPt_GetBVH(const SailorPtScene* cs, SailorPtBvhNode* nodes, uint32_t* mapping)
+{
+	if (!cs || !cs->dev.built) return SAILOR_PT_ERR_ARG;
+	SailorPtScene* s = const_cast<SailorPtScene*>(cs);
+	if (nodes) s->dev.refNodes.Download(s->dev.ctx, nodes, (size_t)2 * s->dev.numTris - 1);
+	if (mapping) s->dev.mapping.Download(s->dev.ctx, mapping, s->dev.numTris);
+	return FromCtx(s->dev, SAILOR_PT_OK);
+}
+
+int32_t SailorPt_GetCamera(const SailorPtScene* s, const SailorPtParams* p, uint32_t* w, uint32_t* h, float cam[12])
+{
+	if (!s || !p || !p->height) return SAILOR_PT_ERR_ARG;
+	const CameraSetup c = CameraOf(s->dev, p);
+	if (w) *w = c.width;
+	if (h) *h = c.height;
+	if (cam) { memcpy(cam, c.pos, 12); memcpy(cam + 3, c.pixel00Dir, 12); memcpy(cam + 6, c.deltaU, 12); memcpy(cam + 9, c.deltaV, 12); }
+	return SAILOR_PT_OK;
+}
+
+int32_t SailorPt_IntersectRays(SailorPtScene* s, uint32_t count, const float* o, const float* d, const uint32_t* ignore, SailorPtHit* hits)
+{
+	if (!s || !o || !d || !hits) return SAILOR_PT_ERR_ARG;
+	int rc = SailorPt_BuildBVH(s);
+	if (rc != SAILOR_PT_OK) return rc;
+	if (!count) return SAILOR_PT_OK;
+	SceneDevice& D = s->dev;
+	const double t0 = HostNow();
+	D.ctx.kernelLaunches = 0;
+	std::vector<RayRec> rays(count);
+	for (uint32_t i = 0; i < count; i++)
+	{
+		RayRec& r = rays[i];
+		r.ox = o[3 * i]; r.oy = o[3 * i + 1]; r.oz = o[3 * i + 2]; r.ignoreTri = ignore ? ignore[i] : kNoHit;
+		r.dx = d[3 * i]; r.dy = d[3 * i + 1]; r.dz = d[3 * i + 2]; r.tmax = kFltMax;
+	}
+	DevBuf<RayRec> dRays; DevBuf<Hit> dHits;
+	dRays.Upload(D.ctx, rays); dHits.Alloc(D.ctx, count);
+	if (!D.ctx.ok) return FromCtx(D, SAILOR_PT_ERR_CUDA);
+	D.ctx.TimerStart();
+	LaunchTraceRays(D.ctx, D.View(), dRays.p, dHits.p, count, D.counter.p);
+	const double tk = D.ctx.TimerStop();
+	dHits.Download(D.ctx, reinterpret_cast<Hit*>(hits), count);
+	g_stats = SailorPtStats{};
+	g_stats.rays = count; g_stats.secondsTraverse = tk; g_stats.traverseLaunches = 1; g_stats.kernelLaunches = D.ctx.kernelLaunches;
+	g_stats.secondsTotal = HostNow() - t0;
+	return FromCtx(D, SAILOR_PT_OK);
+}
+
+int32_t SailorPt_PrimaryHits(SailorPtScene* s, const SailorPtParams* p, SailorPtHit* hits)
+{
+	if (!s || !p || !hits || !p->height) return SAILOR_PT_ERR_ARG;
+	int rc = SailorPt_BuildBVH(s);
+	if (rc != SAILOR_PT_OK) return rc;
+	SceneDevice& D = s->dev;
+	const double t0 = HostNow();
+	D.ctx.kernelLaunches = 0;
+	const CameraSetup c = CameraOf(D, p);
+	const size_t n = (size_t)c.width * c.height;
+	if (!n) return SAILOR_PT_ERR_ARG;
+	DevBuf<Hit> dHits;
+	dHits.Alloc(D.ctx, n);
+	if (!D.ctx.ok) return FromCtx(D, SAILOR_PT_ERR_CUDA);
+	D.ctx.TimerStart();
+	LaunchTracePrimary(D.ctx, D.View(), ToGpuCamera(c), dHits.p, D.counter.p);
+	const double tk = D.ctx.TimerStop();
+	dHits.Download(D.ctx, reinterpret_cast<Hit*>(hits), n);
+	g_stats = SailorPtStats{};
+	g_stats.rays = n; g_stats.secondsTraverse = tk; g_stats.traverseLaunches = 1; g_stats.kernelLaunches = D.ctx.kernelLaunches;
+	g_stats.secondsTotal = HostNow() - t0;
+	return FromCtx(D, SAILOR_PT_OK);
+}
+
+int32_t SailorPt_OutputStage(uint32_t width, uint32_t height, const float* linearRGB, uint8_t* srgb8)
+{
+	if (!linearRGB || !srgb8 || !width || !height) return SAILOR_PT_ERR_ARG;
+	ScopedCtx sc;
+	if (sc.rc != SAILOR_PT_OK) return SetError(sc.rc, sc.ctx.error);
+	const size_t n = (size_t)width * height;
+	DevBuf<float> dLin; DevBuf<uint8_t> dOut;
+	dLin.Upload(sc.ctx, linearRGB, n * 3); dOut.Alloc(sc.ctx, n * 3);
+	RunOutputStage(sc.ctx, width, height, dLin.p, dOut.p);
+	dOut.Download(sc.ctx, srgb8, n * 3);
+	if (!sc.ctx.ok) return SetError(SAILOR_PT_ERR_CUDA, sc.ctx.error);
+	return SAILOR_PT_OK;
+}
+
+int32_t SailorPt_Render(SailorPtScene* s, const SailorPtParams* p, float* linearRGB, uint8_t* srgb8)
+{
+	if (!s || !p || !linearRGB || !p->height || !p->msaa) return SAILOR_PT_ERR_ARG;
+	int rc = SailorPt_BuildBVH(s);
+	if (rc != SAILOR_PT_OK) return rc;
+	SceneDevice& D = s->dev;
+	const double t0 = HostNow();
+	D.ctx.kernelLaunches = 0;
+	const CameraSetup c = CameraOf(D, p);
+	const size_t n = (size_t)c.width * c.height;
+	if (!n) return SAILOR_PT_ERR_ARG;
+	DevBuf<float> dLin; DevBuf<uint8_t> dOut;
+	dLin.Alloc(D.ctx, n * 3);
+	RenderStats rs{};
+	rc = RenderFrame(D, ToGpuCamera(c), *p, dLin.p, rs);
+	if (rc != SAILOR_PT_OK) return FromCtx(D, rc);
+	double tOut = 0.0;
+	if (srgb8)
+	{
+		dOut.Alloc(D.ctx, n * 3);
+		D.ctx.TimerStart();
+		RunOutputStage(D.ctx, c.width, c.height, dLin.p, dOut.p);
+		tOut = D.ctx.TimerStop();
+		dOut.Download(D.ctx, srgb8, n * 3);
+	}
+	dLin.Download(D.ctx, linearRGB, n * 3);
+	g_stats = SailorPtStats{};
+	g_stats.rays = rs.rays; g_stats.primarySamples = rs.primarySamples; g_stats.secondsTraverse = rs.secondsTraverse;
+	g_stats.secondsShade = rs.secondsShade; g_stats.secondsOutput = tOut; g_stats.traverseLaunches = rs.traverseLaunches;
+	g_stats.kernelLaunches = D.ctx.kernelLaunches; g_stats.secondsTotal = HostNow() - t0;
+	return FromCtx(D, SAILOR_PT_OK);
+}
+
+int32_t SailorPt_Run(const SailorPtParams* p)
+{
+	// PathTracer::Run (PathTracer.cpp:75-575)
+	if (!p || !p->pathToModel) return SAILOR_PT_ERR_ARG;
+	SailorPtScene* s = nullptr;
+	int rc = SailorPt_SceneLoad(p->pathToModel, &s);
+	if (rc != SAILOR_PT_OK) return rc;
+	uint32_t w = 0, h = 0;
+	rc = SailorPt_GetCamera(s, p, &w, &h, nullptr);
+	if (rc == SAILOR_PT_OK)
+	{
+		std::vector<float> lin((size_t)w * h * 3);
+		std::vector<uint8_t> srgb((size_t)w * h * 3);
+		rc = SailorPt_Render(s, p, lin.data(), srgb.data());
+		if (rc == SAILOR_PT_OK && p->output && p->output[0])
+		{
+			std::string err;
+			rc = EncodePngRgb8(p->output, w, h, srgb.data(), err);   // stbi_write_png (PathTracer.cpp:560-564)
+			if (rc != SAILOR_PT_OK) t_lastError = err;
+		}
+	}
+	SailorPt_SceneFree(s);
+	return rc;
+}
+
+int32_t SailorPt_SampleTexture(SailorPtScene* s, uint32_t textureIndex, uint32_t count, const float* uv, float* out)
+{
+	if (!s || !uv || !out || textureIndex >= s->dev.hostTextures.size()) return SAILOR_PT_ERR_ARG;
+	if (!count) return SAILOR_PT_OK;
+	SceneDevice& D = s->dev;
+	DevBuf<V2> dUv; DevBuf<V4> dOut;
+	dUv.Upload(D.ctx, reinterpret_cast<const V2*>(uv), count); dOut.Alloc(D.ctx, count);
+	if (!D.ctx.ok) return FromCtx(D, SAILOR_PT_ERR_CUDA);
+	SampleTextureKernel k; k.ts.texels = D.texels.p; k.ts.textures = D.textures.p; k.index = textureIndex; k.uv = dUv.p; k.out = dOut.p;
+	launch_for(D.ctx, count, k);
+	std::vector<V4> host(count);
+	dOut.Download(D.ctx, host.data(), count);
+	for (uint32_t i = 0; i < count; i++) { out[4 * i] = host[i].x; out[4 * i + 1] = host[i].y; out[4 * i + 2] = host[i].z; out[4 * i + 3] = host[i].w; }
+	return FromCtx(D, SAILOR_PT_OK);
+}
+
+int32_t SailorPt_EvalLighting(uint32_t count, const float* in, float* out)
+{
+	if (!in || !out) return SAILOR_PT_ERR_ARG;
+	if (!count) return SAILOR_PT_OK;
+	ScopedCtx sc;
+	if (sc.rc != SAILOR_PT_OK) return SetError(sc.rc, sc.ctx.error);
+	DevBuf<float> dIn, dOut;
+	dIn.Upload(sc.ctx, in, (size_t)count * 24); dOut.Alloc(sc.ctx, (size_t)count * 28);
+	if (!sc.ctx.ok) return SetError(SAILOR_PT_ERR_CUDA, sc.ctx.error);
+	launch_for(sc.ctx, count, EvalLightingKernel{ dIn.p, dOut.p });
+	dOut.Download(sc.ctx, out, (size_t)count * 28);
+	if (!sc.ctx.ok) return SetError(SAILOR_PT_ERR_CUDA, sc.ctx.error);
+	return SAILOR_PT_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,195 @@
+// pipeline.cuh — the device-resident scene and the stage drivers behind the C-ABI (product).
+//
+// Stages: upload + flatten (a10) -> BVH build (a6) -> traversal layout pack -> trace (a7-a9) ->
+// integrator (a15/a16, integrator.cuh) -> output stage (a18, output.cuh).  Everything after the glTF parse runs on
+// the device; host code only sequences launches and reads back the per-level node counts of the BVH build.
+#pragma once
+#include "backend.h"
+#include "host_scene.h"
+#include "flatten.cuh"
+#include "bvh_build.cuh"
+#include "trace_kernels.cuh"
+#include "../../include/sailor_pt.h"
+
+#include <chrono>
+
+namespace spt
+{
+	inline double HostNow() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+	struct DeviceTexture { uint32_t width, height, channels, clamping; uint64_t offset; };   // offset into the texel pool (float4 units)
+
+	struct SceneDevice
+	{
+		Ctx ctx;
+		HostScene host;
+		uint32_t numTris = 0;
+
+		// flattened triangles
+		DevBuf<V4> vtx, centroid, shade;
+		DevBuf<V2> uv2;
+		DevBuf<MaterialGpu> materials;
+		DevBuf<V4> texels;                    // all textures, float4 texels (vec3 textures leave w = 0)
+		DevBuf<DeviceTexture> textures;
+		std::vector<DeviceTexture> hostTextures;
+		DevBuf<V4> lights;                    // 2 float4 per light: direction, intensity
+
+		// BVH: reference layout (parity / C-ABI) and traversal layout
+		bool built = false;
+		uint32_t nodesUsed = 0, numInternal = 0, numLevels = 0;
+		DevBuf<SailorPtBvhNode> refNodes;
+		DevBuf<uint32_t> mapping;
+		DevBuf<TNode> tnodes;
+		DevBuf<TTri> ttris;
+		uint32_t rootRef = 0;
+
+		DevBuf<uint32_t> counter;             // persistent-kernel work counters
+		SailorPtStats stats{};
+
+		BvhView View() const { BvhView v; v.nodes = tnodes.p; v.tris = ttris.p; v.rootRef = rootRef; return v; }
+
+		int Fail(int code) { return code; }
+		int CudaStatus() { return ctx.ok ? SAILOR_PT_OK : SAILOR_PT_ERR_CUDA; }
+
+		// ---------------------------------------------------------------------------------------------- load
+		int Upload()
+		{
+			const double t0 = HostNow();
+			numTris = (uint32_t)host.numTriangles;
+			counter.Alloc(ctx, 16);
+			if (numTris == 0) return CudaStatus();
+			// concatenate the primitive streams
+			std::vector<PrimDesc> descs(host.prims.size());
+			std::vector<float> pos, nrm, uv0, uv1, tan; std::vector<uint32_t> idx;
+			uint32_t triStart = 0, vtxOffset = 0;
+			for (size_t i = 0; i < host.prims.size(); i++)
+			{
+				const HostPrimitive& hp = host.prims[i];
+				PrimDesc& d = descs[i];
+				memset(&d, 0, sizeof(d));
+				memcpy(d.world, hp.world, sizeof(d.world));
+				const uint32_t nv = (uint32_t)(hp.pos.size() / 3);
+				d.triStart = triStart; d.triCount = (uint32_t)(hp.idx.size() / 3);
+				d.vtxOffset = vtxOffset; d.idxOffset = (uint32_t)idx.size();
+				d.hasNrm = !hp.nrm.empty(); d.hasUv0 = !hp.uv0.empty(); d.hasUv1 = !hp.uv1.empty(); d.hasTan = !hp.tan.empty();
+				d.material = hp.material;
+				pos.insert(pos.end(), hp.pos.begin(), hp.pos.end());
+				nrm.resize((size_t)(vtxOffset + nv) * 3, 0.0f); if (d.hasNrm) memcpy(nrm.data() + (size_t)vtxOffset * 3, hp.nrm.data(), hp.nrm.size() * 4);
+				uv0.resize((size_t)(vtxOffset + nv) * 2, 0.0f); if (d.hasUv0) memcpy(uv0.data() + (size_t)vtxOffset * 2, hp.uv0.data(), hp.uv0.size() * 4);
+				uv1.resize((size_t)(vtxOffset + nv) * 2, 0.0f); if (d.hasUv1) memcpy(uv1.data() + (size_t)vtxOffset * 2, hp.uv1.data(), hp.uv1.size() * 4);
+				tan.resize((size_t)(vtxOffset + nv) * 4, 0.0f); if (d.hasTan) memcpy(tan.data() + (size_t)vtxOffset * 4, hp.tan.data(), hp.tan.size() * 4);
+				idx.insert(idx.end(), hp.idx.begin(), hp.idx.end());
+				triStart += d.triCount; vtxOffset += nv;
+			}
+			// empty primitives would break the binary search in FlattenKernel: drop them
+			std::vector<PrimDesc> live;
+			for (const auto& d : descs) if (d.triCount) live.push_back(d);
+
+			DevBuf<PrimDesc> dPrims; DevBuf<float> dPos, dNrm, dUv0, dUv1, dTan; DevBuf<uint32_t> dIdx;
+			dPrims.Upload(ctx, live); dPos.Upload(ctx, pos); dNrm.Upload(ctx, nrm); dUv0.Upload(ctx, uv0); dUv1.Upload(ctx, uv1); dTan.Upload(ctx, tan); dIdx.Upload(ctx, idx);
+			vtx.Alloc(ctx, (size_t)numTris * 3); centroid.Alloc(ctx, numTris); shade.Alloc(ctx, (size_t)numTris * 9); uv2.Alloc(ctx, (size_t)numTris * 3);
+			if (!ctx.ok) return CudaStatus();
+
+			ctx.TimerStart();
+			FlattenKernel fk;
+			fk.prims = dPrims.p; fk.numPrims = (uint32_t)live.size();
+			fk.pos = dPos.p; fk.nrm = dNrm.p; fk.uv0 = dUv0.p; fk.uv1 = dUv1.p; fk.tan = dTan.p; fk.idx = dIdx.p;
+			fk.vtx = vtx.p; fk.centroid = centroid.p; fk.shade = shade.p; fk.uv2 = uv2.p;
+			launch_for(ctx, numTris, fk);
+			stats.secondsFlatten = ctx.TimerStop();
+
+			materials.Upload(ctx, host.materials);
+			std::vector<V4> lightData;
+			for (const auto& l : host.lights) { lightData.push_back(v4(l.direction[0], l.direction[1], l.direction[2], 0.0f)); lightData.push_back(v4(l.intensity[0], l.intensity[1], l.intensity[2], 0.0f)); }
+			lights.Upload(ctx, lightData);
+			const int rc = UploadTextures();
+			ctx.Sync();
+			stats.secondsTotal = HostNow() - t0;
+			return rc != SAILOR_PT_OK ? rc : CudaStatus();
+		}
+
+		int UploadTextures();   // textures.cuh
+
+		// ---------------------------------------------------------------------------------------------- BVH
+		int BuildBvh()
+		{
+			if (built) return SAILOR_PT_OK;
+			if (numTris == 0) { ctx.error = "scene has no triangles"; return SAILOR_PT_ERR_FORMAT; }
+			const uint32_t N = numTris, maxNodes = 2 * N - 1;
+			const double t0 = HostNow();
+			DevBuf<uint32_t> idxA, idxB, nodeOfA, nodeOfB, flags, scan, holes, srcs, first, count, left, keys, state, splitAxis, nL, bins, splitFlag, splitScan, scanScratch;
+			DevBuf<float> aabb, splitPos, binScale;
+			idxA.Alloc(ctx, N); idxB.Alloc(ctx, N); nodeOfA.Alloc(ctx, N); nodeOfB.Alloc(ctx, N); flags.Alloc(ctx, N); scan.Alloc(ctx, (size_t)N + 1);
+			holes.Alloc(ctx, N); srcs.Alloc(ctx, N);
+			first.Alloc(ctx, maxNodes); count.Alloc(ctx, maxNodes); left.Alloc(ctx, maxNodes); keys.Alloc(ctx, (size_t)maxNodes * 12);
+			aabb.Alloc(ctx, (size_t)maxNodes * 6); state.Alloc(ctx, maxNodes); splitPos.Alloc(ctx, maxNodes); splitAxis.Alloc(ctx, maxNodes); nL.Alloc(ctx, maxNodes);
+			binScale.Alloc(ctx, (size_t)maxNodes * 6);
+			if (!ctx.ok) return CudaStatus();
+
+			BuildState s;
+			s.vtx = vtx.p; s.centroid = centroid.p; s.idxA = idxA.p; s.idxB = idxB.p; s.nodeOfA = nodeOfA.p; s.nodeOfB = nodeOfB.p;
+			s.flags = flags.p; s.scan = scan.p; s.holes = holes.p; s.srcs = srcs.p;
+			s.first = first.p; s.count = count.p; s.left = left.p; s.keys = keys.p; s.aabb = aabb.p; s.state = state.p;
+			s.splitPos = splitPos.p; s.splitAxis = splitAxis.p; s.nL = nL.p; s.binScale = binScale.p; s.bins = nullptr;
+			s.splitFlag = nullptr; s.splitScan = nullptr; s.n = N;
+
+			ctx.TimerStart();
+			launch_for(ctx, N, InitSlotsKernel{ s });
+			const uint32_t rootInit[2] = { 0u, N };
+			DevUpload(ctx, first.p, &rootInit[0], 4); DevUpload(ctx, count.p, &rootInit[1], 4);   // BVH.cpp:291-293
+
+			std::vector<uint32_t> levelStart; std::vector<uint32_t> levelCount;
+			uint32_t start = 0, cnt = 1;
+			while (cnt && ctx.ok)
+			{
+				levelStart.push_back(start); levelCount.push_back(cnt);
+				bins.Ensure(ctx, (size_t)cnt * kNodeBinWords); splitFlag.Ensure(ctx, cnt); splitScan.Ensure(ctx, (size_t)cnt + 1);
+				s.bins = bins.p; s.splitFlag = splitFlag.p; s.splitScan = splitScan.p;
+				launch_for(ctx, cnt, InitNodesKernel{ s, start });
+				launch_for(ctx, N, BoundsKernel{ s, start });
+				launch_for(ctx, cnt, PrepareKernel{ s, start });
+				launch_for(ctx, N, BinKernel{ s, start });
+				launch_for(ctx, cnt, SplitKernel{ s, start });
+				launch_for(ctx, N, FlagKernel{ s, start });
+				ExclusiveScanU32(ctx, flags.p, scan.p, N, scanScratch);
+				launch_for(ctx, cnt, CountKernel{ s, start });
+				ExclusiveScanU32(ctx, splitFlag.p, splitScan.p, cnt, scanScratch);
+				launch_for(ctx, cnt, AllocKernel{ s, start, start + cnt });
+				launch_for(ctx, N, HoleKernel{ s, start });
+				launch_for(ctx, N, ScatterKernel{ s, start });
+				uint32_t numSplit = 0;
+				DevDownload(ctx, &numSplit, splitScan.p + cnt, 4);
+				{ uint32_t* t = s.idxA; s.idxA = s.idxB; s.idxB = t; t = s.nodeOfA; s.nodeOfA = s.nodeOfB; s.nodeOfB = t; }
+				start += cnt; cnt = 2 * numSplit;
+			}
+			nodesUsed = start;
+			numLevels = (uint32_t)levelStart.size();
+
+			// renumber into the reference's allocation order and emit both layouts
+			DevBuf<uint32_t> internalCount, refIdx, rank, leafCountByRef, leafOffsetByRef, leafCountAtSlot;
+			DevBuf<float> areaScratch;
+			internalCount.Alloc(ctx, nodesUsed); refIdx.Alloc(ctx, nodesUsed); rank.Alloc(ctx, nodesUsed);
+			leafCountByRef.Alloc(ctx, nodesUsed); leafOffsetByRef.Alloc(ctx, (size_t)nodesUsed + 1); leafCountAtSlot.Alloc(ctx, N); areaScratch.Alloc(ctx, N);
+			refNodes.Alloc(ctx, maxNodes); mapping.Alloc(ctx, N);
+			if (!ctx.ok) return CudaStatus();
+			refNodes.Zero(ctx); refIdx.Zero(ctx); rank.Zero(ctx); leafCountAtSlot.Zero(ctx);
+			for (size_t l = levelStart.size(); l-- > 0;) launch_for(ctx, levelCount[l], SubtreeKernel{ s, levelStart[l], internalCount.p });
+			for (size_t l = 0; l < levelStart.size(); l++) launch_for(ctx, levelCount[l], RenumberKernel{ s, levelStart[l], internalCount.p, refIdx.p, rank.p });
+			launch_for(ctx, nodesUsed, LeafCountKernel{ s, refIdx.p, leafCountByRef.p });
+			ExclusiveScanU32(ctx, leafCountByRef.p, leafOffsetByRef.p, nodesUsed, scanScratch);
+			launch_for(ctx, nodesUsed, EmitKernel{ s, refIdx.p, leafOffsetByRef.p, s.idxA, refNodes.p, mapping.p, areaScratch.p });
+			DevDownload(ctx, &numInternal, internalCount.p, 4);
+
+			tnodes.Alloc(ctx, numInternal ? numInternal : 1); ttris.Alloc(ctx, N);
+			if (!ctx.ok) return CudaStatus();
+			launch_for(ctx, nodesUsed, LeafCountAtSlotKernel{ s.left, s.count, refIdx.p, leafOffsetByRef.p, leafCountAtSlot.p });
+			launch_for(ctx, nodesUsed, PackNodesKernel{ s.left, rank.p, refIdx.p, leafOffsetByRef.p, s.aabb, tnodes.p });
+			launch_for(ctx, N, PackTrisKernel{ vtx.p, mapping.p, leafCountAtSlot.p, ttris.p });
+			rootRef = numInternal ? 0u : kLeafBit;      // a root that never split is one leaf at slot 0
+			stats.secondsBvhBuild = ctx.TimerStop();
+			stats.secondsTotal = HostNow() - t0;
+			built = ctx.ok;
+			return CudaStatus();
+		}
+	};
+}

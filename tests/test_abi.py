@@ -1,0 +1,84 @@
+"""CPU-side checks of the drop-in boundary: both libraries export every symbol include/sailor_pt.h declares, the
+header and the ctypes mirror agree, and the product library refuses to compute without a CUDA device."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from sailor_b200.capi import ERR_ARG, ERR_NO_DEVICE, SYMBOLS, Library, Params, SailorPtParams, SailorPtStats
+import scenes
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "sailor_pt.h")).read()
+    return sorted(set(re.findall(r"SAILOR_PT_API\s+[\w\s\*]+?\b(SailorPt_\w+)\s*\(", text)))
+
+
+def test_header_and_binding_list_the_same_symbols():
+    assert _header_symbols() == sorted(SYMBOLS)
+
+
+def test_product_library_builds_and_exports_every_symbol():
+    from sailor_b200 import build as product_build
+    lib = product_build.build()
+    out = subprocess.run(["nm", "-D", "--defined-only", lib], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r"\bT (SailorPt_\w+)", out))
+    assert set(SYMBOLS) <= exported, sorted(set(SYMBOLS) - exported)
+    sass = subprocess.run(["cuobjdump", "-lelf", lib], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass, "the product library must carry an sm_100a image"
+
+
+def test_oracle_exports_every_symbol(oracle):
+    for s in SYMBOLS:
+        getattr(oracle.lib, s)
+    assert oracle.backend() == "reference-cpu"
+
+
+def test_struct_layouts_match_the_header():
+    # 3 pointers + 5 u32 + 3 f32 + u32 + (pad) u64 + 4 u32
+    assert C.sizeof(SailorPtParams) == 88
+    assert SailorPtParams.seed.offset == 64 and SailorPtParams.rowBegin.offset == 72
+    assert C.sizeof(SailorPtStats) == 96
+
+
+def test_product_fails_loudly_without_a_cuda_device(scene_dir):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    import sailor_b200
+    from sailor_b200 import build as product_build
+    product_build.build()
+    L = sailor_b200.library()
+    assert L.backend() == "cuda sm_100a"
+    h = C.c_void_p()
+    rc = L.lib.SailorPt_SceneLoad(scenes.ensure(scene_dir, "cube").encode(), C.byref(h))
+    assert rc == ERR_NO_DEVICE and not h.value
+    assert b"no CPU path" in L.lib.SailorPt_LastError()
+    lin = np.zeros((4, 4, 3), np.float32)
+    out = np.zeros((4, 4, 3), np.uint8)
+    assert L.lib.SailorPt_OutputStage(4, 4, lin.ctypes.data_as(C.POINTER(C.c_float)), out.ctypes.data_as(C.POINTER(C.c_uint8))) == ERR_NO_DEVICE
+    assert sailor_b200.PathTracer().Run(Params(path_to_model=scenes.ensure(scene_dir, "cube"), height=8)) == ERR_NO_DEVICE
+
+
+def test_argument_errors(emu):
+    assert emu.lib.SailorPt_SceneLoad(None, None) == ERR_ARG
+    assert emu.lib.SailorPt_GetStats(None) == ERR_ARG
+
+
+@pytest.mark.parametrize("which", ["oracle", "emu"])
+def test_parse_command_line_args_matches_the_reference(which, request):
+    lib = request.getfixturevalue(which)
+    for samples, msaa, s in ((1, 1, 1), (3, 3, 1), (16, 4, 4), (32, 4, 8), (33, 8, 4), (256, 8, 32), (1024, 8, 128), (4096, 8, 512)):
+        p = lib.parse_command_line_args(Params(), ["exe", "--in", "a b.glb", "--out", "o.png", "--height", "77", "--samples", str(samples),
+                                                   "--bounces", "6", "--camera", "cam", "--ambient", "80ff00"])
+        assert (p.m_pathToModel, p.m_output, p.m_camera) == ("a b.glb", "o.png", "cam")
+        assert (p.m_height, p.m_maxBounces, p.m_msaa, p.m_numSamples) == (77, 6, msaa, s)
+        assert tuple(np.float32(v) for v in p.m_ambient) == (np.float32(128) / np.float32(255), np.float32(1), np.float32(0))
+        q = Params.from_samples(samples)
+        assert (q.m_msaa, q.m_numSamples) == (msaa, s)
+    p = lib.parse_command_line_args(Params(), ["exe", "--in", '"my', 'scene.glb"'])
+    assert p.m_pathToModel == "my scene.glb"

@@ -1,0 +1,142 @@
+"""CPU-side tests of the product's host orchestration and kernel bodies (compiled for the host by tests/emu, every
+launch a serial loop) against the oracle and the goldens.  The same checks run against the real CUDA library in
+tests/test_gpu_parity.py; this file exists so logic errors are caught where there is no GPU."""
+import numpy as np
+import pytest
+
+import parity_checks as pc
+import scenes
+from golden.make_golden import HIT_CASES
+from sailor_b200.capi import Params
+
+
+def _scene(scene_dir, name, kw):
+    return scenes.ensure(scene_dir, name, **kw)
+
+
+def test_partition_closed_form_equals_the_reference_swap_loop():
+    """bvh_build.cuh ScatterKernel: closed form of BVH.cpp:238-251, checked exhaustively for n <= 10 and at random."""
+    def seq(c):
+        n = len(c); idx = list(range(n)); i, j = 0, n - 1
+        while i <= j:
+            if c[idx[i]]:
+                i += 1
+            else:
+                idx[i], idx[j] = idx[j], idx[i]; j -= 1
+        return idx
+
+    def closed(c):
+        n = len(c); nL = sum(c); pref = [0] * (n + 1)
+        for p in range(n):
+            pref[p + 1] = pref[p] + c[p]
+        holes, srcs = {}, {}
+        for p in range(n):
+            if p < nL and not c[p]:
+                holes[p - pref[p]] = p
+            if p >= nL and c[p]:
+                srcs[nL - pref[p] - 1] = p
+        num_holes = nL - pref[nL]
+        out = [None] * n
+        for p in range(n):
+            if c[p]:
+                dest = p if p < nL else holes[nL - pref[p] - 1]
+            elif p > nL:
+                dest = p - 1
+            else:
+                r = (p - pref[p]) if p < nL else num_holes
+                dest = n - 1 if r == 0 else srcs[r - 1] - 1
+            assert out[dest] is None
+            out[dest] = p
+        return out
+    for n in range(1, 11):
+        for m in range(1 << n):
+            c = [(m >> k) & 1 for k in range(n)]
+            assert seq(c) == closed(c)
+    r = np.random.RandomState(0)
+    for _ in range(300):
+        c = list((r.uniform(size=r.randint(1, 400)) < r.uniform()).astype(int))
+        assert seq(c) == closed(c)
+
+
+@pytest.mark.parametrize("key,name,kw", [("cube", "cube", {}), ("pbr", "pbr", {}), ("hf64", "heightfield", {"n": 64})])
+def test_flatten_and_bvh_match_goldens(emu, G, scene_dir, key, name, kw):
+    pc.check_flatten(emu, _scene(scene_dir, name, kw), G[key + "_tris"], G[key + "_mat"])
+    pc.check_bvh(emu, _scene(scene_dir, name, kw), G[key + "_nodes"], G[key + "_mapping"])
+
+
+@pytest.mark.parametrize("case", HIT_CASES, ids=[c[0] for c in HIT_CASES])
+def test_primary_hits_match_goldens(emu, G, scene_dir, case):
+    name, scene, kw, h, wo, cam = case
+    pc.check_primary_hits(emu, _scene(scene_dir, scene, kw), h, wo, cam, G[name + "_cam"], G[name + "_hits"])
+
+
+@pytest.mark.parametrize("name,kw", [("cube", {}), ("pbr", {}), ("heightfield", {"n": 64})])
+def test_random_and_degenerate_rays_match_the_oracle(emu, oracle, scene_dir, name, kw):
+    pc.check_random_rays(emu, oracle, _scene(scene_dir, name, kw), n=6000)
+
+
+def test_bvh_of_ragged_scenes(emu, oracle, scene_dir, tmp_path):
+    """1 triangle (root is a leaf), 4 and 5 triangles (the <= 4 stop), coplanar duplicates (no-gain stop, equal areas)."""
+    for tag, count, dup in (("one", 1, False), ("four", 4, False), ("five", 5, False), ("dups", 40, True)):
+        g = scenes.GlbBuilder()
+        r = np.random.RandomState(count)
+        pos = r.uniform(-1, 1, (count * 3, 3)).astype(np.float32)
+        if dup:
+            pos = np.tile(np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32), (count, 1))
+            pos[: count * 3 // 2, 2] = 0.5
+        mat = g.material(pbrMetallicRoughness={"metallicFactor": 0.0})
+        g.node(mesh=g.mesh(pos, None, mat))
+        path = g.write(str(tmp_path / (tag + ".glb")))
+        with oracle.load_scene(path) as o:
+            nodes, mapping = o.bvh()
+        pc.check_bvh(emu, path, nodes, mapping)
+        pc.check_random_rays(emu, oracle, path, n=2000, seed=count)
+
+
+def test_texture_sampler_output_stage_and_bsdf_table(emu, G, scene_dir):
+    pc.check_textures(emu, _scene(scene_dir, "pbr", {}), G["uv_grid"], [G["pbr_tex%d" % t] for t in range(4)])
+    pc.check_output_stage(emu, G["output_in"], G["output_srgb"])
+    pc.check_lighting(emu, G["lighting_in"], G["lighting_out"], rtol=1e-5)
+
+
+def test_error_paths(emu, tmp_path):
+    from sailor_b200.capi import ERR_FORMAT, ERR_IO, SailorPtError
+    with pytest.raises(SailorPtError) as e:
+        emu.load_scene(str(tmp_path / "missing.glb"))
+    assert e.value.code == ERR_IO
+    bad = tmp_path / "bad.gltf"
+    bad.write_text("{ not json")
+    with pytest.raises(SailorPtError) as e:
+        emu.load_scene(str(bad))
+    assert e.value.code == ERR_FORMAT
+    empty = tmp_path / "empty.gltf"
+    empty.write_text('{"asset":{"version":"2.0"},"scenes":[{"nodes":[]}],"nodes":[]}')
+    with emu.load_scene(str(empty)) as s:
+        assert s.counts()["triangles"] == 0
+        with pytest.raises(SailorPtError):
+            s.build_bvh()
+
+
+def test_render_is_deterministic_and_partition_invariant(emu, scene_dir):
+    """Row shards and primary-sample shards reassemble to the unsharded image (the multi-GPU contract)."""
+    path = _scene(scene_dir, "pbr", {})
+    base = dict(height=20, camera="main_cam", num_samples=2, num_ambient_samples=2, max_bounces=3, msaa=4, ambient=(1, 1, 1), seed=9)
+    with emu.load_scene(path) as s:
+        full, _ = s.render(Params(**base))
+        again, _ = s.render(Params(**base))
+        assert np.array_equal(full, again)
+        w, h, _ = s.camera(Params(**base))
+        top, _ = s.render(Params(rows=(0, 7), **base))
+        bottom, _ = s.render(Params(rows=(7, h), **base))
+        # task row y lands in image row h-1-y (PathTracer.cpp:449)
+        assert np.array_equal(top[h - 7:], full[h - 7:]) and np.array_equal(bottom[:h - 7], full[:h - 7])
+        parts = [s.render(Params(msaa_range=(a, b), **base))[0].astype(np.float64) for a, b in ((0, 1), (1, 3), (3, 4))]
+        assert np.allclose(sum(parts), full, rtol=1e-6, atol=1e-7)
+
+
+def test_converged_image_tolerance_cpu(emu, G, scene_dir):
+    """Converged-image parity at reduced size (the full-size run is the GPU test): mean relative error vs the
+    reference's own high-spp render below 3 %, with the reference-vs-reference noise floor at the same budget ~2 %."""
+    p = Params(height=24, camera="main_cam", num_samples=64, num_ambient_samples=64, max_bounces=4, msaa=8, ambient=(1.0, 1.0, 1.0))
+    img = pc.render_mean(emu, _scene(scene_dir, "pbr", {}), p, seeds=range(300, 304))
+    assert pc.mean_rel_error(img, G["pbr_converged"]) < 0.03
