@@ -89,7 +89,7 @@ typedef struct SailorPtStats {
 	uint64_t boxTests;        /* oracle (counting build) only: IntersectRayAABB calls */
 	uint64_t triTests;        /* oracle (counting build) only: IntersectRayTriangle calls */
 	double secondsTotal;      /* wall time of the last call (host clock) */
-	double secondsFlatten;    /* device/CPU time per stage of the last call, seconds */
+	double secondsFlatten;    /* SceneLoad: flatten kernel. RenderResident: the whole call between two CUDA events on the launch stream */
 	double secondsBvhBuild;
 	double secondsTraverse;   /* product: sum of traversal-kernel launches (CUDA events on the launch stream) */
 	double secondsShade;
@@ -98,6 +98,8 @@ typedef struct SailorPtStats {
 	uint32_t kernelLaunches;  /* product: all kernel launches of the last call */
 	uint32_t threads;         /* oracle: worker threads used */
 	uint32_t reserved;
+	uint64_t h2dBytes;        /* product: bytes copied host->device by the last call */
+	uint64_t d2hBytes;        /* product: bytes copied device->host by the last call */
 } SailorPtStats;
 
 /* ---- the reference entry points (PathTracer.h:34-36) ---- */
@@ -141,6 +143,16 @@ SAILOR_PT_API int32_t SailorPt_PrimaryHits(SailorPtScene* scene, const SailorPtP
  * reference stores them (flipped, :449).  srgb8 (width*height*3 bytes, may be NULL) = output stage (:535-565). */
 SAILOR_PT_API int32_t SailorPt_Render(SailorPtScene* scene, const SailorPtParams* params, float* linearRGB,
 	uint8_t* srgb8);
+
+/* Same as SailorPt_Render but the accumulator and the sRGB8 image stay resident with the scene (device memory in the
+ * product): no host copies inside the call.  flags bit0: rebuild the BVH first (BuildBVH is part of the timed pass),
+ * bit1: also run the output stage.  Used by bench.py for the device-resident number and by the multi-GPU path. */
+SAILOR_PT_API int32_t SailorPt_RenderResident(SailorPtScene* scene, const SailorPtParams* params, uint32_t flags);
+/* Read the resident results back to host buffers (either may be NULL). */
+SAILOR_PT_API int32_t SailorPt_ReadResident(SailorPtScene* scene, float* linearRGB, uint8_t* srgb8);
+/* Product only: copy the resident linear accumulator (width*height*3 floats) into a caller-owned DEVICE buffer
+ * (e.g. a torch tensor handed to NCCL). */
+SAILOR_PT_API int32_t SailorPt_CopyResidentToDevice(SailorPtScene* scene, void* dstDevice, uint64_t bytes);
 
 /* Output stage alone (PathTracer.cpp:535-565 + Core/Utils.cpp:48-57). */
 SAILOR_PT_API int32_t SailorPt_OutputStage(uint32_t width, uint32_t height, const float* linearRGB, uint8_t* srgb8);

@@ -115,6 +115,7 @@ struct SailorPtScene
 	RefTracer tracer;
 	RefBVH* bvh = nullptr;
 	std::vector<CameraDesc> cameras;
+	std::vector<float> residentLin; std::vector<uint8_t> residentSrgb; uint32_t residentW = 0, residentH = 0;
 	~SailorPtScene() { delete bvh; }
 };
 
@@ -840,6 +841,27 @@ int32_t SailorPt_Render(SailorPtScene* s, const SailorPtParams* p, float* linear
 	}
 	return SAILOR_PT_OK;
 }
+
+int32_t SailorPt_RenderResident(SailorPtScene* s, const SailorPtParams* p, uint32_t flags)
+{
+	if (!s || !p) return SAILOR_PT_ERR_ARG;
+	if ((flags & 1u) && s->bvh) { delete s->bvh; s->bvh = nullptr; }
+	const CameraSetup c = SetupCamera(*s, *p);
+	s->residentW = c.width; s->residentH = c.height;
+	s->residentLin.resize((size_t)c.width * c.height * 3);
+	if (flags & 2u) s->residentSrgb.resize((size_t)c.width * c.height * 3);
+	return SailorPt_Render(s, p, s->residentLin.data(), (flags & 2u) ? s->residentSrgb.data() : nullptr);
+}
+
+int32_t SailorPt_ReadResident(SailorPtScene* s, float* linearRGB, uint8_t* srgb8)
+{
+	if (!s || !s->residentW) return SAILOR_PT_ERR_ARG;
+	if (linearRGB) memcpy(linearRGB, s->residentLin.data(), s->residentLin.size() * sizeof(float));
+	if (srgb8) { if (s->residentSrgb.empty()) return SAILOR_PT_ERR_ARG; memcpy(srgb8, s->residentSrgb.data(), s->residentSrgb.size()); }
+	return SAILOR_PT_OK;
+}
+
+int32_t SailorPt_CopyResidentToDevice(SailorPtScene*, void*, uint64_t) { t_lastError = "the CPU oracle has no device memory"; return SAILOR_PT_ERR_UNSUPPORTED; }
 
 int32_t SailorPt_Run(const SailorPtParams* p)
 {

@@ -36,7 +36,7 @@ class SailorPtStats(C.Structure):
         ("secondsTotal", C.c_double), ("secondsFlatten", C.c_double), ("secondsBvhBuild", C.c_double),
         ("secondsTraverse", C.c_double), ("secondsShade", C.c_double), ("secondsOutput", C.c_double),
         ("traverseLaunches", C.c_uint32), ("kernelLaunches", C.c_uint32), ("threads", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("reserved", C.c_uint32), ("h2dBytes", C.c_uint64), ("d2hBytes", C.c_uint64),
     ]
 
     def as_dict(self):
@@ -52,7 +52,7 @@ SYMBOLS = [
     "SailorPt_SceneCounts", "SailorPt_SceneGetTriangles", "SailorPt_BuildBVH", "SailorPt_GetBVH",
     "SailorPt_GetCamera", "SailorPt_IntersectRays", "SailorPt_PrimaryHits", "SailorPt_Render",
     "SailorPt_OutputStage", "SailorPt_SampleTexture", "SailorPt_EvalLighting", "SailorPt_GetStats",
-    "SailorPt_LastError", "SailorPt_Backend",
+    "SailorPt_LastError", "SailorPt_Backend", "SailorPt_RenderResident", "SailorPt_ReadResident", "SailorPt_CopyResidentToDevice",
 ]
 
 
@@ -127,6 +127,9 @@ class Library:
         lib.SailorPt_IntersectRays.argtypes = [C.c_void_p, C.c_uint32, P(C.c_float), P(C.c_float), P(C.c_uint32), C.c_void_p]
         lib.SailorPt_PrimaryHits.argtypes = [C.c_void_p, P(SailorPtParams), C.c_void_p]
         lib.SailorPt_Render.argtypes = [C.c_void_p, P(SailorPtParams), P(C.c_float), P(C.c_uint8)]
+        lib.SailorPt_RenderResident.argtypes = [C.c_void_p, P(SailorPtParams), C.c_uint32]
+        lib.SailorPt_ReadResident.argtypes = [C.c_void_p, P(C.c_float), P(C.c_uint8)]
+        lib.SailorPt_CopyResidentToDevice.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         lib.SailorPt_OutputStage.argtypes = [C.c_uint32, C.c_uint32, P(C.c_float), P(C.c_uint8)]
         lib.SailorPt_SampleTexture.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, P(C.c_float), P(C.c_float)]
         lib.SailorPt_EvalLighting.argtypes = [C.c_uint32, P(C.c_float), P(C.c_float)]
@@ -266,6 +269,20 @@ class Scene:
         srgb = np.empty((h, w, 3), np.uint8) if want_srgb else None
         self.L.check(self.L.lib.SailorPt_Render(self.h, C.byref(cp), _ptr(lin, C.c_float), _ptr(srgb, C.c_uint8)), "SailorPt_Render")
         return lin, srgb
+
+    def render_resident(self, params: Params, rebuild_bvh=False, output_stage=True):
+        cp = params.to_c()
+        self.L.check(self.L.lib.SailorPt_RenderResident(self.h, C.byref(cp), (1 if rebuild_bvh else 0) | (2 if output_stage else 0)), "SailorPt_RenderResident")
+
+    def read_resident(self, params: Params, want_srgb=True):
+        w, h, _ = self.camera(params)
+        lin = np.empty((h, w, 3), np.float32)
+        srgb = np.empty((h, w, 3), np.uint8) if want_srgb else None
+        self.L.check(self.L.lib.SailorPt_ReadResident(self.h, _ptr(lin, C.c_float), _ptr(srgb, C.c_uint8)), "SailorPt_ReadResident")
+        return lin, srgb
+
+    def copy_resident_to_device(self, device_ptr, nbytes):
+        self.L.check(self.L.lib.SailorPt_CopyResidentToDevice(self.h, C.c_void_p(device_ptr), nbytes), "SailorPt_CopyResidentToDevice")
 
     def sample_texture(self, index, uv):
         uv = np.ascontiguousarray(uv, dtype=np.float32)

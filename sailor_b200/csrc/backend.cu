@@ -36,7 +36,8 @@ namespace spt
 		}
 		if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess ||
 			cudaEventCreate(&evA) != cudaSuccess || cudaEventCreate(&evB) != cudaSuccess ||
-			cudaEventCreate(&ev[0]) != cudaSuccess || cudaEventCreate(&ev[1]) != cudaSuccess || cudaEventCreate(&ev[2]) != cudaSuccess || cudaEventCreate(&ev[3]) != cudaSuccess)
+			cudaEventCreate(&ev[0]) != cudaSuccess || cudaEventCreate(&ev[1]) != cudaSuccess || cudaEventCreate(&ev[2]) != cudaSuccess || cudaEventCreate(&ev[3]) != cudaSuccess ||
+			cudaEventCreate(&ev[4]) != cudaSuccess || cudaEventCreate(&ev[5]) != cudaSuccess)
 		{
 			Fail("cudaStreamCreate/cudaEventCreate", (int)cudaGetLastError());
 			return SAILOR_PT_ERR_CUDA;
@@ -48,7 +49,7 @@ namespace spt
 	{
 		if (evA) cudaEventDestroy(evA);
 		if (evB) cudaEventDestroy(evB);
-		for (int i = 0; i < 4; i++) { if (ev[i]) cudaEventDestroy(ev[i]); ev[i] = nullptr; }
+		for (int i = 0; i < 6; i++) { if (ev[i]) cudaEventDestroy(ev[i]); ev[i] = nullptr; }
 		if (stream) cudaStreamDestroy(stream);
 		evA = evB = nullptr; stream = nullptr;
 	}
@@ -80,10 +81,11 @@ namespace spt
 		return ctx.ok ? p : nullptr;
 	}
 	void DevFreeBytes(void* p) { cudaFree(p); }
-	void DevUpload(Ctx& ctx, void* dst, const void* src, size_t bytes) { if (ctx.ok) SPT_CUDA_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx.stream)); }
+	void DevUpload(Ctx& ctx, void* dst, const void* src, size_t bytes) { ctx.h2dBytes += bytes; if (ctx.ok) SPT_CUDA_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx.stream)); }
 	void DevDownload(Ctx& ctx, void* dst, const void* src, size_t bytes)
 	{
 		if (!ctx.ok) return;
+		ctx.d2hBytes += bytes;
 		SPT_CUDA_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx.stream));
 		SPT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx.stream));
 	}
@@ -176,7 +178,7 @@ namespace spt
 
 #else
 	// ------------------------------------------------------------------------------------------------ EMU (tests only)
-	static std::chrono::steady_clock::time_point g_t0, g_marks[4];
+	static std::chrono::steady_clock::time_point g_t0, g_marks[6];
 	void Ctx::Mark(int i) { g_marks[i] = std::chrono::steady_clock::now(); }
 	double Ctx::Between(int i, int j) { return std::chrono::duration<double>(g_marks[j] - g_marks[i]).count(); }
 	int Ctx::Init() { ok = true; return SAILOR_PT_OK; }
@@ -186,8 +188,8 @@ namespace spt
 	double Ctx::TimerStop() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - g_t0).count(); }
 	void* DevAllocBytes(Ctx&, size_t bytes) { return malloc(bytes ? bytes : 1); }
 	void DevFreeBytes(void* p) { free(p); }
-	void DevUpload(Ctx&, void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
-	void DevDownload(Ctx&, void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
+	void DevUpload(Ctx& ctx, void* dst, const void* src, size_t bytes) { ctx.h2dBytes += bytes; memcpy(dst, src, bytes); }
+	void DevDownload(Ctx& ctx, void* dst, const void* src, size_t bytes) { ctx.d2hBytes += bytes; memcpy(dst, src, bytes); }
 	void DevMemset(Ctx&, void* dst, int byte, size_t bytes) { memset(dst, byte, bytes); }
 	void DevCopy(Ctx&, void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
 	void ExclusiveScanU32(Ctx& ctx, const uint32_t* in, uint32_t* out, uint32_t n, DevBuf<uint32_t>&)

@@ -26,9 +26,10 @@ namespace spt
 #if !defined(SPT_EMU)
 		cudaStream_t stream = nullptr;
 		cudaEvent_t evA = nullptr, evB = nullptr;
-		cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };   // per-iteration stage markers (integrator)
+		cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };   // stage markers: 0-2 per wavefront iteration, 4-5 whole call
 #endif
 		uint32_t kernelLaunches = 0;
+		uint64_t h2dBytes = 0, d2hBytes = 0;
 		std::string error;
 		bool ok = true;
 

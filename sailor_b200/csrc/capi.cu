@@ -121,7 +121,7 @@ int32_t SailorPt_SceneLoad(const char* path, SailorPtScene** outScene)
 	if (rc != SAILOR_PT_OK) { s->dev.ctx.Destroy(); return SetError(rc, err); }
 	s->dev.ctx.kernelLaunches = 0;
 	rc = FromCtx(s->dev, s->dev.Upload());
-	g_stats = s->dev.stats; g_stats.kernelLaunches = s->dev.ctx.kernelLaunches;
+	g_stats = s->dev.stats; g_stats.kernelLaunches = s->dev.ctx.kernelLaunches; g_stats.h2dBytes = s->dev.ctx.h2dBytes;
 	if (rc != SAILOR_PT_OK) { s->dev.ctx.Destroy(); return rc; }
 	*outScene = s.release();
 	return SAILOR_PT_OK;
@@ -269,37 +269,79 @@ int32_t SailorPt_OutputStage(uint32_t width, uint32_t height, const float* linea
 	return SAILOR_PT_OK;
 }
 
-int32_t SailorPt_Render(SailorPtScene* s, const SailorPtParams* p, float* linearRGB, uint8_t* srgb8)
+int32_t SailorPt_RenderResident(SailorPtScene* s, const SailorPtParams* p, uint32_t flags)
 {
-	if (!s || !p || !linearRGB || !p->height || !p->msaa) return SAILOR_PT_ERR_ARG;
-	int rc = SailorPt_BuildBVH(s);
-	if (rc != SAILOR_PT_OK) return rc;
+	if (!s || !p || !p->height || !p->msaa) return SAILOR_PT_ERR_ARG;
 	SceneDevice& D = s->dev;
 	const double t0 = HostNow();
-	D.ctx.kernelLaunches = 0;
+	D.ctx.kernelLaunches = 0; D.ctx.h2dBytes = D.ctx.d2hBytes = 0;
+	double tBuild = 0.0;
+	D.ctx.Mark(4);
+	if (flags & 1u) D.built = false;                      // BVH build is part of this pass
+	if (!D.built)
+	{
+		const int rcb = FromCtx(D, D.BuildBvh());
+		if (rcb != SAILOR_PT_OK) return rcb;
+		tBuild = D.stats.secondsBvhBuild;
+	}
 	const CameraSetup c = CameraOf(D, p);
 	const size_t n = (size_t)c.width * c.height;
 	if (!n) return SAILOR_PT_ERR_ARG;
-	DevBuf<float> dLin; DevBuf<uint8_t> dOut;
-	dLin.Alloc(D.ctx, n * 3);
+	D.residentLin.Ensure(D.ctx, n * 3);
+	D.residentW = c.width; D.residentH = c.height;
+	if ((p->rowEnd && (p->rowBegin > 0 || p->rowEnd < c.height))) D.residentLin.Zero(D.ctx, n * 3);   // rows outside the shard stay 0
 	RenderStats rs{};
-	rc = RenderFrame(D, ToGpuCamera(c), *p, dLin.p, rs);
+	const int rc = RenderFrame(D, ToGpuCamera(c), *p, D.residentLin.p, rs);
 	if (rc != SAILOR_PT_OK) return FromCtx(D, rc);
 	double tOut = 0.0;
-	if (srgb8)
+	if (flags & 2u)
 	{
-		dOut.Alloc(D.ctx, n * 3);
+		D.residentSrgb.Ensure(D.ctx, n * 3);
 		D.ctx.TimerStart();
-		RunOutputStage(D.ctx, c.width, c.height, dLin.p, dOut.p);
+		RunOutputStage(D.ctx, c.width, c.height, D.residentLin.p, D.residentSrgb.p);
 		tOut = D.ctx.TimerStop();
-		dOut.Download(D.ctx, srgb8, n * 3);
 	}
-	dLin.Download(D.ctx, linearRGB, n * 3);
+	D.ctx.Mark(5);
+	D.ctx.Sync();
 	g_stats = SailorPtStats{};
+	g_stats.secondsFlatten = D.ctx.Between(4, 5);         // whole call on the launch stream (CUDA events); field reused: no flatten here
 	g_stats.rays = rs.rays; g_stats.primarySamples = rs.primarySamples; g_stats.secondsTraverse = rs.secondsTraverse;
-	g_stats.secondsShade = rs.secondsShade; g_stats.secondsOutput = tOut; g_stats.traverseLaunches = rs.traverseLaunches;
-	g_stats.kernelLaunches = D.ctx.kernelLaunches; g_stats.secondsTotal = HostNow() - t0;
+	g_stats.secondsShade = rs.secondsShade; g_stats.secondsOutput = tOut; g_stats.secondsBvhBuild = tBuild; g_stats.traverseLaunches = rs.traverseLaunches;
+	g_stats.kernelLaunches = D.ctx.kernelLaunches; g_stats.h2dBytes = D.ctx.h2dBytes; g_stats.d2hBytes = D.ctx.d2hBytes;
+	g_stats.secondsTotal = HostNow() - t0;
 	return FromCtx(D, SAILOR_PT_OK);
+}
+
+int32_t SailorPt_ReadResident(SailorPtScene* s, float* linearRGB, uint8_t* srgb8)
+{
+	if (!s || !s->dev.residentW) return SAILOR_PT_ERR_ARG;
+	SceneDevice& D = s->dev;
+	const size_t n = (size_t)D.residentW * D.residentH;
+	if (linearRGB) D.residentLin.Download(D.ctx, linearRGB, n * 3);
+	if (srgb8) { if (D.residentSrgb.n < n * 3) return SAILOR_PT_ERR_ARG; D.residentSrgb.Download(D.ctx, srgb8, n * 3); }
+	g_stats.d2hBytes = D.ctx.d2hBytes;
+	return FromCtx(D, SAILOR_PT_OK);
+}
+
+int32_t SailorPt_CopyResidentToDevice(SailorPtScene* s, void* dstDevice, uint64_t bytes)
+{
+	if (!s || !dstDevice || !s->dev.residentW) return SAILOR_PT_ERR_ARG;
+	SceneDevice& D = s->dev;
+	if (bytes != (uint64_t)D.residentW * D.residentH * 3 * sizeof(float)) return SAILOR_PT_ERR_ARG;
+	DevCopy(D.ctx, dstDevice, D.residentLin.p, (size_t)bytes);
+	D.ctx.Sync();
+	return FromCtx(D, SAILOR_PT_OK);
+}
+
+int32_t SailorPt_Render(SailorPtScene* s, const SailorPtParams* p, float* linearRGB, uint8_t* srgb8)
+{
+	if (!s || !p || !linearRGB || !p->height || !p->msaa) return SAILOR_PT_ERR_ARG;
+	const double t0 = HostNow();
+	int rc = SailorPt_RenderResident(s, p, srgb8 ? 2u : 0u);
+	if (rc != SAILOR_PT_OK) return rc;
+	rc = SailorPt_ReadResident(s, linearRGB, srgb8);
+	g_stats.secondsTotal = HostNow() - t0;
+	return rc;
 }
 
 int32_t SailorPt_Run(const SailorPtParams* p)

@@ -43,6 +43,9 @@ namespace spt
 		DevBuf<TTri> ttris;
 		uint32_t rootRef = 0;
 
+		// results of the last RenderResident (stay on the device until read back or handed to NCCL)
+		DevBuf<float> residentLin; DevBuf<uint8_t> residentSrgb; uint32_t residentW = 0, residentH = 0;
+
 		DevBuf<uint32_t> counter;             // persistent-kernel work counters
 		SailorPtStats stats{};
 

@@ -72,6 +72,8 @@ HIT_CASES = [  # name, scene, scene kwargs, height, width override, camera
     ("hf64_small", "heightfield", {"n": 64}, 90, 0, ""),
     ("pbr_main", "pbr", {}, 96, 0, "main_cam"),
 ]
+CONVERGED_SEEDS = 96   # oracle renders averaged into each converged image
+
 BIG_HIT_CASES = [
     ("cube_c1", "cube", {}, 512, 0, ""),          # BASELINE config C1: 682x512 by the reference's aspect rule
     ("cube_c1_square", "cube", {}, 512, 512, ""),
@@ -115,19 +117,19 @@ def main():
             # converged images for the tolerance test: the reference's own high-spp render (S = A = 64 at the first hit, msaa 8)
             p = Params(height=24, camera="main_cam", num_samples=64, num_ambient_samples=64, max_bounces=4, msaa=8, ambient=(1.0, 1.0, 1.0), seed=11)
             acc = None
-            for seed in range(16):
+            for seed in range(CONVERGED_SEEDS):
                 p.seed = 100 + seed
                 lin, _ = s.render(p, want_srgb=False)
                 acc = lin.astype(np.float64) if acc is None else acc + lin
-            out["pbr_converged"] = (acc / 16).astype(np.float32)
+            out["pbr_converged"] = (acc / CONVERGED_SEEDS).astype(np.float32)
         with L.load_scene(scenes.ensure(d, "heightfield", n=64)) as s:
             p = Params(height=18, num_samples=32, num_ambient_samples=32, max_bounces=3, msaa=8, ambient=(0.6, 0.7, 0.9), seed=1)
             acc = None
-            for seed in range(16):
+            for seed in range(CONVERGED_SEEDS):
                 p.seed = 200 + seed
                 lin, _ = s.render(p, want_srgb=False)
                 acc = lin.astype(np.float64) if acc is None else acc + lin
-            out["hf64_converged"] = (acc / 16).astype(np.float32)
+            out["hf64_converged"] = (acc / CONVERGED_SEEDS).astype(np.float32)
     rec = lighting_inputs()
     out["lighting_in"] = rec
     out["lighting_out"] = L.eval_lighting(rec)

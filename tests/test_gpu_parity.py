@@ -126,9 +126,13 @@ def test_gpu_render_equals_host_compiled_kernel_bodies(gpu, emu, scene_dir):
 ])
 def test_converged_image_tolerance(gpu, G, scene_dir, key, name, kw, params):
     """north_star: converged images agree with the reference's own high-spp render within a stated mean relative
-    error.  Stated tolerance: 1.5 % (64 GPU renders averaged vs 16 oracle renders averaged; the residual is noise)."""
-    img = pc.render_mean(gpu, _scene(scene_dir, name, kw), Params(**params), seeds=range(1000, 1064))
-    assert pc.mean_rel_error(img, G[key]) < 0.015
+    error.  Stated tolerance: 1.5 % mean relative error (mean |a-b| / mean b over all pixels and channels) with 256
+    GPU renders averaged against 96 oracle renders averaged; what remains is Monte-Carlo noise of the two averages
+    (the oracle against its own average converges as 7.4 % / sqrt(renders))."""
+    img = pc.render_mean(gpu, _scene(scene_dir, name, kw), Params(**params), seeds=range(1000, 1256))
+    err = pc.mean_rel_error(img, G[key])
+    print("converged-image mean relative error %s: %.4f" % (key, err))
+    assert err < 0.015
 
 
 def test_run_writes_a_png(gpu, scene_dir, tmp_path):

@@ -136,7 +136,8 @@ def test_render_is_deterministic_and_partition_invariant(emu, scene_dir):
 
 def test_converged_image_tolerance_cpu(emu, G, scene_dir):
     """Converged-image parity at reduced size (the full-size run is the GPU test): mean relative error vs the
-    reference's own high-spp render below 3 %, with the reference-vs-reference noise floor at the same budget ~2 %."""
+    reference's own high-spp render (96 oracle renders averaged) below 3.5 % with 8 renders averaged here; the
+    reference measured against itself at the same budget gives 2.6 % (Monte-Carlo noise, error ~ 7.4 % / sqrt(renders))."""
     p = Params(height=24, camera="main_cam", num_samples=64, num_ambient_samples=64, max_bounces=4, msaa=8, ambient=(1.0, 1.0, 1.0))
-    img = pc.render_mean(emu, _scene(scene_dir, "pbr", {}), p, seeds=range(300, 304))
-    assert pc.mean_rel_error(img, G["pbr_converged"]) < 0.03
+    img = pc.render_mean(emu, _scene(scene_dir, "pbr", {}), p, seeds=range(300, 308))
+    assert pc.mean_rel_error(img, G["pbr_converged"]) < 0.035
