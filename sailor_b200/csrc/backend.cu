@@ -35,12 +35,14 @@ namespace spt
 			return SAILOR_PT_ERR_NO_DEVICE;
 		}
 		if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess ||
-			cudaEventCreate(&evA) != cudaSuccess || cudaEventCreate(&evB) != cudaSuccess ||
-			cudaEventCreate(&ev[0]) != cudaSuccess || cudaEventCreate(&ev[1]) != cudaSuccess || cudaEventCreate(&ev[2]) != cudaSuccess || cudaEventCreate(&ev[3]) != cudaSuccess ||
-			cudaEventCreate(&ev[4]) != cudaSuccess || cudaEventCreate(&ev[5]) != cudaSuccess)
+			cudaEventCreate(&evA) != cudaSuccess || cudaEventCreate(&evB) != cudaSuccess)
 		{
 			Fail("cudaStreamCreate/cudaEventCreate", (int)cudaGetLastError());
 			return SAILOR_PT_ERR_CUDA;
+		}
+		for (int i = 0; i < kMarkers; i++)
+		{
+			if (cudaEventCreate(&ev[i]) != cudaSuccess) { Fail("cudaEventCreate", (int)cudaGetLastError()); return SAILOR_PT_ERR_CUDA; }
 		}
 		ok = true;
 		return SAILOR_PT_OK;
@@ -49,7 +51,7 @@ namespace spt
 	{
 		if (evA) cudaEventDestroy(evA);
 		if (evB) cudaEventDestroy(evB);
-		for (int i = 0; i < 6; i++) { if (ev[i]) cudaEventDestroy(ev[i]); ev[i] = nullptr; }
+		for (int i = 0; i < kMarkers; i++) { if (ev[i]) cudaEventDestroy(ev[i]); ev[i] = nullptr; }
 		if (stream) cudaStreamDestroy(stream);
 		evA = evB = nullptr; stream = nullptr;
 	}
@@ -178,7 +180,7 @@ namespace spt
 
 #else
 	// ------------------------------------------------------------------------------------------------ EMU (tests only)
-	static std::chrono::steady_clock::time_point g_t0, g_marks[6];
+	static std::chrono::steady_clock::time_point g_t0, g_marks[64];
 	void Ctx::Mark(int i) { g_marks[i] = std::chrono::steady_clock::now(); }
 	double Ctx::Between(int i, int j) { return std::chrono::duration<double>(g_marks[j] - g_marks[i]).count(); }
 	int Ctx::Init() { ok = true; return SAILOR_PT_OK; }

@@ -26,10 +26,12 @@ namespace spt
 #if !defined(SPT_EMU)
 		cudaStream_t stream = nullptr;
 		cudaEvent_t evA = nullptr, evB = nullptr;
-		cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };   // stage markers: 0-2 per wavefront iteration, 4-5 whole call
+		static constexpr int kMarkers = 64;
+		cudaEvent_t ev[kMarkers] = {};      // stage markers: 0..59 wavefront iterations (3 per iteration), 60-61 whole call
 #endif
 		uint32_t kernelLaunches = 0;
 		uint64_t h2dBytes = 0, d2hBytes = 0;
+		static constexpr int kMarkCall0 = 60, kMarkCall1 = 61;
 		std::string error;
 		bool ok = true;
 

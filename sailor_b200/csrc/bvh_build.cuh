@@ -45,7 +45,8 @@ namespace spt
 		uint32_t* state;                              // per node: bit0 binning, bit1 partitioning, bit2 split
 		float* splitPos; uint32_t* splitAxis; uint32_t* nL;
 		float* binScale;                              // 6 per node: boundsMin[3], scale[3]; scale = 0 marks a skipped axis
-		uint32_t* bins;                               // per node of the CURRENT level: kNodeBinWords
+		uint32_t* bins;                               // per BINNED node of the current level: kNodeBinWords
+		uint32_t* binSlot; uint32_t* binCounter;      // node -> its slot in `bins` (handed out per level)
 		uint32_t* splitFlag; uint32_t* splitScan;     // per node of the current level (+1)
 		uint32_t n;
 	};
@@ -121,7 +122,9 @@ namespace spt
 					bs[a] = bmin;
 					bs[3 + a] = (bmin == bmax) ? 0.0f : (float)kBins / (bmax - bmin);   // :36-43 (0 = axis skipped)
 				}
-				uint32_t* bins = s.bins + (size_t)i * kNodeBinWords;
+				const uint32_t slot = atomic_add_u32(s.binCounter, 1u);                 // slot order is irrelevant: bins are per node
+				s.binSlot[node] = slot;
+				uint32_t* bins = s.bins + (size_t)slot * kNodeBinWords;
 				const uint32_t kmin = float_key(10e30f), kmax = float_key(-10e30f);     // AABB defaults, Bounds.h:112-113
 				for (uint32_t w = 0; w < 3 * kBins; w++)
 				{
@@ -147,7 +150,7 @@ namespace spt
 			const float mx[3] = { glm_max(glm_max(a.x, b.x), c.x), glm_max(glm_max(a.y, b.y), c.y), glm_max(glm_max(a.z, b.z), c.z) };
 			const float cc[3] = { ce.x, ce.y, ce.z };
 			const float* bs = s.binScale + (size_t)node * 6;
-			uint32_t* bins = s.bins + (size_t)(node - levelStart) * kNodeBinWords;
+			uint32_t* bins = s.bins + (size_t)s.binSlot[node] * kNodeBinWords;
 			for (int ax = 0; ax < 3; ax++)
 			{
 				const float scale = bs[3 + ax];
@@ -170,7 +173,7 @@ namespace spt
 			const uint32_t node = levelStart + i;
 			if (!(s.state[node] & kStBinning)) return;
 			const float* bs = s.binScale + (size_t)node * 6;
-			const uint32_t* bins = s.bins + (size_t)i * kNodeBinWords;
+			const uint32_t* bins = s.bins + (size_t)s.binSlot[node] * kNodeBinWords;
 			float bestCost = kFltMax;
 			int32_t axis = 0; float splitPos = 0.0f;                                     // Subdivide: int32_t axis{}; float splitPos{};
 			for (uint32_t a = 0; a < 3; a++)

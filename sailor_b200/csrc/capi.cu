@@ -276,7 +276,7 @@ int32_t SailorPt_RenderResident(SailorPtScene* s, const SailorPtParams* p, uint3
 	const double t0 = HostNow();
 	D.ctx.kernelLaunches = 0; D.ctx.h2dBytes = D.ctx.d2hBytes = 0;
 	double tBuild = 0.0;
-	D.ctx.Mark(4);
+	D.ctx.Mark(Ctx::kMarkCall0);
 	if (flags & 1u) D.built = false;                      // BVH build is part of this pass
 	if (!D.built)
 	{
@@ -301,10 +301,10 @@ int32_t SailorPt_RenderResident(SailorPtScene* s, const SailorPtParams* p, uint3
 		RunOutputStage(D.ctx, c.width, c.height, D.residentLin.p, D.residentSrgb.p);
 		tOut = D.ctx.TimerStop();
 	}
-	D.ctx.Mark(5);
+	D.ctx.Mark(Ctx::kMarkCall1);
 	D.ctx.Sync();
 	g_stats = SailorPtStats{};
-	g_stats.secondsFlatten = D.ctx.Between(4, 5);         // whole call on the launch stream (CUDA events); field reused: no flatten here
+	g_stats.secondsFlatten = D.ctx.Between(Ctx::kMarkCall0, Ctx::kMarkCall1);         // whole call on the launch stream (CUDA events); field reused: no flatten here
 	g_stats.rays = rs.rays; g_stats.primarySamples = rs.primarySamples; g_stats.secondsTraverse = rs.secondsTraverse;
 	g_stats.secondsShade = rs.secondsShade; g_stats.secondsOutput = tOut; g_stats.secondsBvhBuild = tBuild; g_stats.traverseLaunches = rs.traverseLaunches;
 	g_stats.kernelLaunches = D.ctx.kernelLaunches; g_stats.h2dBytes = D.ctx.h2dBytes; g_stats.d2hBytes = D.ctx.d2hBytes;

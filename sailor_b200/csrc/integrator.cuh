@@ -88,6 +88,10 @@ namespace spt
 		uint32_t pad;
 	};
 
+	// One first hit of the primary pass: which (pixel, primary sample) and the closest hit of its camera ray.
+	struct alignas(16) PrimaryHitRec { uint32_t pixel, sample, pad0, pad1; float t, u, v; uint32_t tri; };
+	static_assert(sizeof(PrimaryHitRec) == 32, "PrimaryHitRec layout");
+
 	struct RenderStats { uint64_t rays, primarySamples; double secondsTraverse, secondsShade; uint32_t traverseLaunches; };
 
 	struct IntegratorArgs
@@ -102,14 +106,19 @@ namespace spt
 		uint32_t poolSize; uint32_t maxDepth;
 		PathHeader* headers; Frame* frames; RayRec* rays; const Hit* hits;
 		float* sampleBuf;                       // 3 floats per (pixel in band, sample in range)
-		uint32_t* nextSample; uint32_t totalSamples;   // work counter over primary samples of this shard
-		uint32_t* activeCount; unsigned long long* rayCount; unsigned long long* sampleCount;
+		const PrimaryHitRec* hitQueue; uint32_t queueCount;   // first hits found by the primary pass
+		uint32_t* nextSample;                                   // work counter over hitQueue
+		uint32_t* activeCount; unsigned long long* rayCount;
 	};
 
 	// ---- random numbers --------------------------------------------------------------
 	SPT_HD uint64_t Mix64(uint64_t z)
 	{
 		z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL; z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL; return z ^ (z >> 31);
+	}
+	SPT_HD uint64_t PrimaryRngKey(uint64_t seed, uint32_t pixel, uint32_t msaa, uint32_t sample)
+	{
+		return Mix64(seed * 0x9E3779B97F4A7C15ULL + ((uint64_t)pixel * msaa + sample) + 0x632BE59BD9B4E019ULL);
 	}
 	struct Rng
 	{
@@ -178,32 +187,26 @@ namespace spt
 			f->skyAtt = v3(1.0f); f->skyPrev = start; f->skyStart = start; f->skyDir = toL; f->skyIor = ior; f->skyIgnore = ignore; f->skyJ = 0;
 		}
 
-		// Pull the next primary sample (:444-466). Returns false when the shard is exhausted.
-		SPT_KERNEL_BODY bool NextPrimary()
+		// Start the next first-hit record of the primary pass (:444-466): frame 0 is set up exactly as Raytrace would
+		// see it and resumed with the hit the primary pass already found.  Returns false when the queue is exhausted.
+		SPT_KERNEL_BODY bool NextFromQueue()
 		{
 			const uint32_t g = atomic_add_u32(a.nextSample, 1u);
-			if (g >= a.totalSamples) return false;
-			// enumeration: 8x4 pixel tiles, all lanes of a tile share the sample index -> coherent primary batches
-			const uint32_t rows = a.rowEnd - a.rowBegin, ns = a.msEnd - a.msBegin;
-			const uint32_t tilesX = (a.cam.width + 7u) / 8u;
-			const uint32_t lane = g & 31u, rest = g >> 5;
-			const uint32_t s = rest % ns, tile = rest / ns;
-			const uint32_t x = (tile % tilesX) * 8u + (lane & 7u), yb = (tile / tilesX) * 4u + (lane >> 3);
-			if (x >= a.cam.width || yb >= rows) { hd.active = 2; return true; }   // padding lane of an edge tile
-			const uint32_t y = a.rowBegin + yb, sample = a.msBegin + s;
-			hd.active = 1; hd.depth = 0; hd.pixel = y * a.cam.width + x; hd.sample = sample;
-			hd.rngKey = Mix64(a.seed * 0x9E3779B97F4A7C15ULL + ((uint64_t)hd.pixel * a.msaa + sample) + 0x632BE59BD9B4E019ULL);
-			hd.rngCounter = 0;
+			if (g >= a.queueCount) return false;
+			const PrimaryHitRec rec = a.hitQueue[g];
+			const uint32_t x = rec.pixel % a.cam.width, y = rec.pixel / a.cam.width;
+			hd.active = 1; hd.depth = 0; hd.pixel = rec.pixel; hd.sample = rec.sample;
+			hd.rngKey = PrimaryRngKey(a.seed, rec.pixel, a.msaa, rec.sample);
 			rng.key = hd.rngKey; rng.counter = 0;
 			float ox = 0.5f, oy = 0.5f;                                           // :460
-			if (sample != 0) { ox = rng.Float01(); oy = rng.Float01(); }
+			if (rec.sample != 0) { ox = rng.Float01(); oy = rng.Float01(); }
 			f = FrameAt(0);
 			f->rayO = a.cam.pos; f->rayD = PrimaryDir(a.cam, x, y, ox, oy);
 			f->ignoreTri = kNoHit; f->bounceLimit = a.maxBounces; f->inAcc = 1.0f; f->envIor = 1.0f;
 			f->pMaxBounces = a.maxBounces; f->pNumSamples = a.numSamples; f->pNumAmbient = a.numAmbientSamples;
 			BeginCall();
-			Emit(f->rayO, f->rayD, f->ignoreTri);
-			atomic_add_u64(a.sampleCount, 1ull);
+			Hit h; h.t = rec.t; h.u = rec.u; h.v = rec.v; h.tri = rec.tri;
+			Advance(h);
 			return true;
 		}
 
@@ -580,7 +583,7 @@ namespace spt
 		}
 	};
 
-	// One thread per pool slot: resume with the hit of the pending ray, refill finished slots.
+	// One thread per pool slot: resume with the hit of the pending ray, refill finished slots from the hit queue.
 	struct AdvanceKernel
 	{
 		IntegratorArgs a; uint32_t firstIteration;
@@ -589,6 +592,7 @@ namespace spt
 			PathMachine pm(a, slot);
 			pm.hd = a.headers[slot];
 			if (firstIteration) { pm.hd.active = 0; pm.hd.depth = 0; }
+			else if (pm.hd.active == 0) return;                               // idle for good: queue was exhausted when it finished
 			if (pm.hd.active == 1)
 			{
 				pm.rng.key = pm.hd.rngKey; pm.rng.counter = pm.hd.rngCounter;
@@ -599,8 +603,7 @@ namespace spt
 			// refill: a finished (or never started) slot pulls primary samples until one produces a ray
 			while (!pm.rayEmitted)
 			{
-				if (!pm.NextPrimary()) { pm.hd.active = 0; break; }
-				if (pm.hd.active == 2) { pm.hd.active = 0; continue; }     // padding lane: try the next index
+				if (!pm.NextFromQueue()) { pm.hd.active = 0; break; }
 			}
 			if (pm.rayEmitted)
 			{

@@ -46,6 +46,13 @@ namespace spt
 		// results of the last RenderResident (stay on the device until read back or handed to NCCL)
 		DevBuf<float> residentLin; DevBuf<uint8_t> residentSrgb; uint32_t residentW = 0, residentH = 0;
 
+		// wavefront working set, kept across renders (only ever grows): 0 headers, 1 frames, 2 rays, 3 hits,
+		// 4 per-sample results, 5 primary-hit queue, 6 counters, 7 blue-noise table
+		DevBuf<unsigned char> renderMem[8];
+		// BVH build scratch, kept across builds
+		DevBuf<uint32_t> buildU32[24];
+		DevBuf<float> buildF32[4];
+
 		DevBuf<uint32_t> counter;             // persistent-kernel work counters
 		SailorPtStats stats{};
 
@@ -120,13 +127,23 @@ namespace spt
 			if (numTris == 0) { ctx.error = "scene has no triangles"; return SAILOR_PT_ERR_FORMAT; }
 			const uint32_t N = numTris, maxNodes = 2 * N - 1;
 			const double t0 = HostNow();
-			DevBuf<uint32_t> idxA, idxB, nodeOfA, nodeOfB, flags, scan, holes, srcs, first, count, left, keys, state, splitAxis, nL, bins, splitFlag, splitScan, scanScratch;
-			DevBuf<float> aabb, splitPos, binScale;
-			idxA.Alloc(ctx, N); idxB.Alloc(ctx, N); nodeOfA.Alloc(ctx, N); nodeOfB.Alloc(ctx, N); flags.Alloc(ctx, N); scan.Alloc(ctx, (size_t)N + 1);
-			holes.Alloc(ctx, N); srcs.Alloc(ctx, N);
-			first.Alloc(ctx, maxNodes); count.Alloc(ctx, maxNodes); left.Alloc(ctx, maxNodes); keys.Alloc(ctx, (size_t)maxNodes * 12);
-			aabb.Alloc(ctx, (size_t)maxNodes * 6); state.Alloc(ctx, maxNodes); splitPos.Alloc(ctx, maxNodes); splitAxis.Alloc(ctx, maxNodes); nL.Alloc(ctx, maxNodes);
-			binScale.Alloc(ctx, (size_t)maxNodes * 6);
+			// scratch lives with the scene (Ensure only grows): a rebuild allocates nothing
+			DevBuf<uint32_t>& idxA = buildU32[0]; DevBuf<uint32_t>& idxB = buildU32[1]; DevBuf<uint32_t>& nodeOfA = buildU32[2]; DevBuf<uint32_t>& nodeOfB = buildU32[3];
+			DevBuf<uint32_t>& flags = buildU32[4]; DevBuf<uint32_t>& scan = buildU32[5]; DevBuf<uint32_t>& holes = buildU32[6]; DevBuf<uint32_t>& srcs = buildU32[7];
+			DevBuf<uint32_t>& first = buildU32[8]; DevBuf<uint32_t>& count = buildU32[9]; DevBuf<uint32_t>& left = buildU32[10]; DevBuf<uint32_t>& keys = buildU32[11];
+			DevBuf<uint32_t>& state = buildU32[12]; DevBuf<uint32_t>& splitAxis = buildU32[13]; DevBuf<uint32_t>& nL = buildU32[14]; DevBuf<uint32_t>& bins = buildU32[15];
+			DevBuf<uint32_t>& splitFlag = buildU32[16]; DevBuf<uint32_t>& splitScan = buildU32[17]; DevBuf<uint32_t>& scanScratch = buildU32[18];
+			DevBuf<float>& aabb = buildF32[0]; DevBuf<float>& splitPos = buildF32[1]; DevBuf<float>& binScale = buildF32[2];
+			idxA.Ensure(ctx, N); idxB.Ensure(ctx, N); nodeOfA.Ensure(ctx, N); nodeOfB.Ensure(ctx, N); flags.Ensure(ctx, N); scan.Ensure(ctx, (size_t)N + 1);
+			holes.Ensure(ctx, N); srcs.Ensure(ctx, N);
+			first.Ensure(ctx, maxNodes); count.Ensure(ctx, maxNodes); left.Ensure(ctx, maxNodes); keys.Ensure(ctx, (size_t)maxNodes * 12);
+			aabb.Ensure(ctx, (size_t)maxNodes * 6); state.Ensure(ctx, maxNodes); splitPos.Ensure(ctx, maxNodes); splitAxis.Ensure(ctx, maxNodes); nL.Ensure(ctx, maxNodes);
+			binScale.Ensure(ctx, (size_t)maxNodes * 6);
+			// a node is binned only when it holds > 4 triangles, so one level never bins more than N/5 nodes
+			const size_t maxBinned = (size_t)N / 5 + 1;
+			bins.Ensure(ctx, maxBinned * kNodeBinWords); splitFlag.Ensure(ctx, (size_t)N + 1); splitScan.Ensure(ctx, (size_t)N + 2);
+			DevBuf<uint32_t>& binSlot = buildU32[19]; DevBuf<uint32_t>& binCounter = buildU32[20];
+			binSlot.Ensure(ctx, maxNodes); binCounter.Ensure(ctx, 4);
 			if (!ctx.ok) return CudaStatus();
 
 			BuildState s;
@@ -134,7 +151,7 @@ namespace spt
 			s.flags = flags.p; s.scan = scan.p; s.holes = holes.p; s.srcs = srcs.p;
 			s.first = first.p; s.count = count.p; s.left = left.p; s.keys = keys.p; s.aabb = aabb.p; s.state = state.p;
 			s.splitPos = splitPos.p; s.splitAxis = splitAxis.p; s.nL = nL.p; s.binScale = binScale.p; s.bins = nullptr;
-			s.splitFlag = nullptr; s.splitScan = nullptr; s.n = N;
+			s.bins = bins.p; s.splitFlag = splitFlag.p; s.splitScan = splitScan.p; s.binSlot = binSlot.p; s.binCounter = binCounter.p; s.n = N;
 
 			ctx.TimerStart();
 			launch_for(ctx, N, InitSlotsKernel{ s });
@@ -146,8 +163,7 @@ namespace spt
 			while (cnt && ctx.ok)
 			{
 				levelStart.push_back(start); levelCount.push_back(cnt);
-				bins.Ensure(ctx, (size_t)cnt * kNodeBinWords); splitFlag.Ensure(ctx, cnt); splitScan.Ensure(ctx, (size_t)cnt + 1);
-				s.bins = bins.p; s.splitFlag = splitFlag.p; s.splitScan = splitScan.p;
+				DevMemset(ctx, binCounter.p, 0, sizeof(uint32_t));
 				launch_for(ctx, cnt, InitNodesKernel{ s, start });
 				launch_for(ctx, N, BoundsKernel{ s, start });
 				launch_for(ctx, cnt, PrepareKernel{ s, start });
@@ -169,13 +185,14 @@ namespace spt
 			numLevels = (uint32_t)levelStart.size();
 
 			// renumber into the reference's allocation order and emit both layouts
-			DevBuf<uint32_t> internalCount, refIdx, rank, leafCountByRef, leafOffsetByRef, leafCountAtSlot;
-			DevBuf<float> areaScratch;
-			internalCount.Alloc(ctx, nodesUsed); refIdx.Alloc(ctx, nodesUsed); rank.Alloc(ctx, nodesUsed);
-			leafCountByRef.Alloc(ctx, nodesUsed); leafOffsetByRef.Alloc(ctx, (size_t)nodesUsed + 1); leafCountAtSlot.Alloc(ctx, N); areaScratch.Alloc(ctx, N);
-			refNodes.Alloc(ctx, maxNodes); mapping.Alloc(ctx, N);
+			DevBuf<uint32_t>& internalCount = buildU32[21]; DevBuf<uint32_t>& refIdx = buildU32[22]; DevBuf<uint32_t>& rank = buildU32[23];
+			DevBuf<uint32_t>& leafCountByRef = flags; DevBuf<uint32_t>& leafOffsetByRef = scan; DevBuf<uint32_t>& leafCountAtSlot = holes;   // partition scratch is free now
+			DevBuf<float>& areaScratch = buildF32[3];
+			internalCount.Ensure(ctx, maxNodes); refIdx.Ensure(ctx, maxNodes); rank.Ensure(ctx, maxNodes);
+			leafCountByRef.Ensure(ctx, maxNodes); leafOffsetByRef.Ensure(ctx, (size_t)maxNodes + 1); areaScratch.Ensure(ctx, N);
+			refNodes.Ensure(ctx, maxNodes); mapping.Ensure(ctx, N);
 			if (!ctx.ok) return CudaStatus();
-			refNodes.Zero(ctx); refIdx.Zero(ctx); rank.Zero(ctx); leafCountAtSlot.Zero(ctx);
+			refNodes.Zero(ctx, maxNodes); refIdx.Zero(ctx, nodesUsed); rank.Zero(ctx, nodesUsed); leafCountAtSlot.Zero(ctx, N);
 			for (size_t l = levelStart.size(); l-- > 0;) launch_for(ctx, levelCount[l], SubtreeKernel{ s, levelStart[l], internalCount.p });
 			for (size_t l = 0; l < levelStart.size(); l++) launch_for(ctx, levelCount[l], RenumberKernel{ s, levelStart[l], internalCount.p, refIdx.p, rank.p });
 			launch_for(ctx, nodesUsed, LeafCountKernel{ s, refIdx.p, leafCountByRef.p });
@@ -183,7 +200,7 @@ namespace spt
 			launch_for(ctx, nodesUsed, EmitKernel{ s, refIdx.p, leafOffsetByRef.p, s.idxA, refNodes.p, mapping.p, areaScratch.p });
 			DevDownload(ctx, &numInternal, internalCount.p, 4);
 
-			tnodes.Alloc(ctx, numInternal ? numInternal : 1); ttris.Alloc(ctx, N);
+			tnodes.Ensure(ctx, numInternal ? numInternal : 1); ttris.Ensure(ctx, N);
 			if (!ctx.ok) return CudaStatus();
 			launch_for(ctx, nodesUsed, LeafCountAtSlotKernel{ s.left, s.count, refIdx.p, leafOffsetByRef.p, leafCountAtSlot.p });
 			launch_for(ctx, nodesUsed, PackNodesKernel{ s.left, rank.p, refIdx.p, leafOffsetByRef.p, s.aabb, tnodes.p });
