@@ -94,6 +94,40 @@ namespace spt
 	void DevMemset(Ctx& ctx, void* dst, int byte, size_t bytes) { if (ctx.ok) SPT_CUDA_CHECK(ctx, cudaMemsetAsync(dst, byte, bytes, ctx.stream)); }
 	void DevCopy(Ctx& ctx, void* dst, const void* src, size_t bytes) { if (ctx.ok) SPT_CUDA_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx.stream)); }
 
+	int RangeGridBlocks()
+	{
+		static int blocks = 0;
+		if (!blocks)
+		{
+			int dev = 0, sms = 148;
+			cudaGetDevice(&dev);
+			cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+			blocks = sms * 8;
+		}
+		return blocks;
+	}
+
+	void SpanTimer::Begin(Ctx& ctx)
+	{
+		if (!ctx.ok) return;
+		while (ev.size() < used + 2) { cudaEvent_t e = nullptr; if (cudaEventCreate(&e) != cudaSuccess) { ctx.Fail("cudaEventCreate", (int)cudaGetLastError()); return; } ev.push_back(e); }
+		SPT_CUDA_CHECK(ctx, cudaEventRecord(ev[used], ctx.stream));
+	}
+	void SpanTimer::End(Ctx& ctx)
+	{
+		if (!ctx.ok || ev.size() < used + 2) return;
+		SPT_CUDA_CHECK(ctx, cudaEventRecord(ev[used + 1], ctx.stream));
+		used += 2;
+	}
+	double SpanTimer::Collect(Ctx& ctx)
+	{
+		double s = 0.0;
+		for (size_t i = 0; i + 1 < used && ctx.ok; i += 2) { float ms = 0.0f; SPT_CUDA_CHECK(ctx, cudaEventElapsedTime(&ms, ev[i], ev[i + 1])); s += (double)ms * 1e-3; }
+		used = 0;
+		return s;
+	}
+	void SpanTimer::Destroy() { for (cudaEvent_t e : ev) cudaEventDestroy(e); ev.clear(); used = 0; }
+
 	// ---- exclusive scan: reduce-then-scan, 2048 items per CTA, coalesced, warp shuffles -----------------
 	namespace
 	{
@@ -181,6 +215,11 @@ namespace spt
 #else
 	// ------------------------------------------------------------------------------------------------ EMU (tests only)
 	static std::chrono::steady_clock::time_point g_t0, g_marks[64];
+	static double NowS() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+	void SpanTimer::Begin(Ctx&) { t0 = NowS(); }
+	void SpanTimer::End(Ctx&) { acc += NowS() - t0; used += 2; }
+	double SpanTimer::Collect(Ctx&) { const double s = acc; acc = 0.0; used = 0; return s; }
+	void SpanTimer::Destroy() {}
 	void Ctx::Mark(int i) { g_marks[i] = std::chrono::steady_clock::now(); }
 	double Ctx::Between(int i, int j) { return std::chrono::duration<double>(g_marks[j] - g_marks[i]).count(); }
 	int Ctx::Init() { ok = true; return SAILOR_PT_OK; }

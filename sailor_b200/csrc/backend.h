@@ -118,6 +118,56 @@ namespace spt
 	}
 #endif
 
+	// ---- launch_for_range: functor f(i) for i in [*begin, min(*end, cap)), bounds read from DEVICE memory ----
+	// The wavefront levels are sized by device-side counters; reading them here would cost a host round trip per level,
+	// so the grid is fixed (a few CTAs per SM, grid-stride) and the kernel fetches its own range.
+#if !defined(SPT_EMU)
+	template<class F>
+	__global__ void __launch_bounds__(256) k_for_range(const uint32_t* __restrict__ begin, const uint32_t* __restrict__ end, uint32_t cap, F f)
+	{
+		const uint32_t b = *begin;
+		uint32_t e = *end; if (e > cap) e = cap;
+		for (uint32_t i = b + blockIdx.x * blockDim.x + threadIdx.x; i < e; i += gridDim.x * blockDim.x) f(i);
+	}
+
+	int RangeGridBlocks();    // SMs x 8
+
+	template<class F>
+	inline void launch_for_range(Ctx& ctx, const uint32_t* dBegin, const uint32_t* dEnd, uint32_t cap, uint32_t maxCount, const F& f)
+	{
+		if (!maxCount || !ctx.ok) return;
+		uint32_t blocks = (maxCount + 255u) / 256u;
+		const uint32_t lim = (uint32_t)RangeGridBlocks();
+		if (blocks > lim) blocks = lim;
+		k_for_range<F><<<blocks, 256, 0, ctx.stream>>>(dBegin, dEnd, cap, f);
+		ctx.kernelLaunches++;
+		SPT_CUDA_CHECK(ctx, cudaGetLastError());
+	}
+#else
+	template<class F>
+	inline void launch_for_range(Ctx& ctx, const uint32_t* dBegin, const uint32_t* dEnd, uint32_t cap, uint32_t, const F& f)
+	{
+		if (!ctx.ok) return;
+		uint32_t e = *dEnd; if (e > cap) e = cap;
+		for (uint32_t i = *dBegin; i < e; i++) f(i);
+		ctx.kernelLaunches++;
+	}
+#endif
+
+	// Sum of the device time of bracketed spans on the launch stream (CUDA events, read after a sync); emu: host clock.
+	struct SpanTimer
+	{
+#if !defined(SPT_EMU)
+		std::vector<cudaEvent_t> ev;
+#endif
+		size_t used = 0; double acc = 0.0; double t0 = 0.0;
+		void Begin(Ctx& ctx);
+		void End(Ctx& ctx);
+		double Collect(Ctx& ctx);     // after ctx.Sync(): seconds of all spans since the last Collect
+		uint32_t Spans() const { return (uint32_t)(used / 2); }
+		void Destroy();
+	};
+
 	// out[i] = sum(in[0..i)), out has n+1 entries (out[n] = total).  in/out may not alias.
 	void ExclusiveScanU32(Ctx& ctx, const uint32_t* in, uint32_t* out, uint32_t n, DevBuf<uint32_t>& scratch);
 }

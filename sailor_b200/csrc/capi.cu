@@ -131,6 +131,7 @@ void SailorPt_SceneFree(SailorPtScene* s)
 {
 	if (!s) return;
 	s->dev.ctx.Sync();
+	s->dev.traceTimer.Destroy();
 	Ctx keep = s->dev.ctx;
 	delete s;
 	keep.Destroy();

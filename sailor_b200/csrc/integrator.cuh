@@ -1,24 +1,38 @@
-// integrator.cuh — the path integrator as a WAVEFRONT of resumable paths.
+// integrator.cuh — the path integrator as a BREADTH-FIRST evaluation of the reference's recursion tree
+// (SURVEY §8 rows a13/a15/a17, Appendix A).
 //
 // The reference's Raytrace (reference Raytracing/PathTracer.cpp:622-879) is a recursive estimator, not a flat path
 // sum: per-level clamps to [0,10] (:733,:788,:816), MIS on per-hit AVERAGES (:838-847), S-way branching at the
 // first hit only (:716-717), a deterministic cut-off on the accumulated throughput (:810-811), an alpha-blend
 // continuation that is a second recursive call (:858-871), a tail call when leaving a thick volume (:673-688) and
-// the TraceSky transmission loop (:577-620).  To keep every one of those non-linearities, each pool slot runs ONE
-// primary sample as an explicit state machine over a small stack of call frames (depth <= maxBounces+1, because
-// every recursive call decrements bounceLimit and is only made when it is > 0).  A slot has at most one ray in
-// flight; one wavefront iteration is
-//      trace kernel   : closest hit for every slot's pending ray        (traverse.cuh, persistent threads)
-//      advance kernel : resume every slot with its hit, run shading / sampling / accumulation until the slot needs
-//                       its next ray (or finishes and pulls the next primary sample from the global counter)
-// so all rays of an iteration are traced together and the scene data is only touched by the two kernels.
+// the TraceSky transmission loop (:577-620).  Every one of those non-linearities is kept by evaluating the SAME
+// call tree, but level by level instead of depth first:
+//
+//   record   = one Raytrace() activation whose closest hit is known (NodeRec, 128 B)
+//   expand   : one thread per record of level d: shade the hit (:636-671), then emit EVERY ray the activation needs
+//              at once — D shadow rays (:691-705), nA hemisphere rays (:720-737), nS importance rays (:753-784), the
+//              alpha continuation / thick-volume tail ray — into the level's ray queue, with a 32-byte RayAux per
+//              ray that carries what the ray's result will be weighted with (BRDF, term, pdf, ...)
+//   trace    : closest hit for the whole queue (traverse.cuh, persistent threads)
+//   classify : one thread per ray: misses and shadow tests are final and are folded into the RayAux in place; an
+//              importance ray that hit something and passes the throughput cut (:810-811) spawns a child record of
+//              level d+1 that starts from this very hit (the reference re-traces the same ray at :632)
+//   sky      : TraceSky continuations through thick transmissive surfaces (:591-616), a small side queue
+//   gather   : bottom-up, one thread per record: replays the accumulation of :690-871 over the record's RayAux
+//              entries IN INDEX ORDER (lights, hemisphere, importance samples) and hands  clamp(term*att*L)  to the
+//              parent's RayAux (:816).
+//
+// Every ray of one recursion level of a whole batch of first hits is therefore traced by ONE launch, the number of
+// launches per batch is bounded by maxBounces, and no thread ever waits on another path's tail.
 //
 // Deliberate, documented differences from the reference (none changes the estimator):
 //  * the reference re-traces the importance ray when it recurses (:786 then :632 with the same ray and ignore
-//    index); the child frame here starts from the hit the parent already has;
+//    index); the child record starts from the hit the parent's ray already produced;
+//  * all D shadow rays are traced even after one was blocked; the stale-`hitLight` quirk (:694: every light after
+//    the first blocked one counts as blocked) is applied when the lights are summed;
 //  * random numbers: same distributions as glm::linearRand on rand()%255 bytes and the same blue-noise
-//    table walk (:934-1077), but drawn from a counter-based generator keyed by (seed, pixel, primary-sample index),
-//    so the image does not depend on thread scheduling or on how the frame is split across GPUs;
+//    table walk (:934-1077), but drawn from a counter-based generator keyed per activation (seed, pixel, primary
+//    sample, path in the call tree), so the image does not depend on scheduling or on how the frame is sharded;
 //  * the unbounded rejection loop (:761-767) is capped at 4096 tries; an exhausted sample is skipped.
 #pragma once
 #include "pipeline.cuh"
@@ -28,71 +42,83 @@
 
 namespace spt
 {
-	enum Phase : uint32_t
-	{
-		kPhMain = 0,        // waiting for the closest hit of the frame's own ray (:632)
-		kPhLight,           // waiting for a directional-light shadow ray (:699)
-		kPhSkyHemi,         // inside TraceSky for a hemisphere sample (:729)
-		kPhSample,          // waiting for the importance-sampled ray (:786)
-		kPhSkySample,       // inside TraceSky behind a transmissive hit (:825)
-		kPhChildSample,     // child Raytrace of an importance sample is running (:813)
-		kPhChildAlpha,      // child Raytrace of the alpha-blend continuation is running (:869)
-	};
-
-	enum : uint32_t { kFlOpposite = 1u, kFlThick = 2u, kFlAlpha = 4u, kFlHasTransRay = 8u, kFlTransRay = 16u, kFlFirst = 32u, kFlLightBlocked = 64u };
-
-	// One Raytrace() activation record.
-	struct alignas(16) Frame
-	{
-		// call arguments (:622)
-		V3 rayO; uint32_t ignoreTri;
-		V3 rayD; uint32_t bounceLimit;
-		float inAcc, envIor; uint32_t pMaxBounces, pNumSamples;
-		uint32_t pNumAmbient, seedX, seedY, phase;
-		// shading context of the hit (:636-671)
-		V3 hitPoint; uint32_t hitTri;
-		V3 N; uint32_t matIdx;
-		V3 V; uint32_t flags;
-		V3 offset; uint32_t loopI;
-		V4 baseColor;
-		V3 orm; float ior;
-		V3 emissive; float transmission;
-		uint32_t S, A, nA, nS;
-		// accumulators (:690, :712, :742-747)
-		V3 res; float avgPdf;
-		V3 amb1; float cnt;
-		V3 amb2; float pdf;
-		V3 indirect; float newIor;
-		// pending importance sample (:755-781)
-		V3 term; uint32_t h2tri;
-		V3 att; float toIor;
-		V3 r2o; float thickness;
-		V3 r2d; float pad0;
-		V3 value; float pad1;
-		// TraceSky state (:577-620)
-		V3 skyAtt; uint32_t skyIgnore;
-		V3 skyPrev; uint32_t skyJ;
-		V3 skyStart; float skyIor;
-		V3 skyDir; float pad2;
-		V3 skyToL; float pad3;
-	};
-
-	struct alignas(16) PathHeader
-	{
-		uint32_t depth;       // index of the running frame
-		uint32_t active;      // 0 = slot idle (no more primary samples)
-		uint32_t pixel;       // y*width + x, task coordinates
-		uint32_t sample;      // primary-sample (msaa) index
-		uint64_t rngKey;
-		uint32_t rngCounter;
-		uint32_t pad;
-	};
-
 	// One first hit of the primary pass: which (pixel, primary sample) and the closest hit of its camera ray.
 	struct alignas(16) PrimaryHitRec { uint32_t pixel, sample, pad0, pad1; float t, u, v; uint32_t tri; };
 	static_assert(sizeof(PrimaryHitRec) == 32, "PrimaryHitRec layout");
 
 	struct RenderStats { uint64_t rays, primarySamples; double secondsTraverse, secondsShade; uint32_t traverseLaunches; };
+
+	constexpr uint32_t kNone = 0xFFFFFFFFu;
+
+	// record flags
+	enum : uint32_t
+	{
+		kNfOpposite = 1u, kNfThick = 2u, kNfAlpha = 4u, kNfFirst = 8u, kNfAmbientOn = 16u,
+		kNfDone = 32u,          // result is final (own ray missed / tail call refused): expand and gather leave it alone
+		kNfTail = 64u,          // thick-volume tail call (:673-688): result = the child's result
+		kNfLevel0 = 128u,       // parent = pixel, parentAux = primary-sample index
+	};
+
+	// One Raytrace() activation (:622).  Rows 1-6 are written when the record is created, rows 7-8 by expand/gather.
+	struct alignas(16) NodeRec
+	{
+		V3 rayO; uint32_t parent;            // parent record (or pixel for level 0)
+		V3 rayD; uint32_t parentAux;         // global RayAux index of the importance sample this activation hangs on; kNone for alpha/tail children
+		float t, u, v; uint32_t tri;         // closest hit of (rayO, rayD)
+		float inAcc, envIor; uint32_t bounces; uint32_t flags;   // bounces = bounceLimit | params.m_maxBounces << 16
+		uint64_t rngKey; uint32_t auxBase; uint32_t child;       // auxBase: first RayAux of this record; child: alpha / tail child record
+		uint32_t pNumSamples, pNumAmbient, nA, nS;               // params.m_numSamples / m_numAmbientSamples; loop counts of :716-717
+		V3 emissive; float alpha;            // sample.m_emissive, sample.m_baseColor.a
+		V3 result; uint32_t nLights;
+	};
+	static_assert(sizeof(NodeRec) == 128, "NodeRec layout");
+
+	// ray kinds (RayAux::tag low 3 bits) and state bits
+	enum : uint32_t
+	{
+		kRkInactive = 0, kRkLight = 1, kRkHemi = 2, kRkSample = 3, kRkOwn = 4, kRkMask = 7u,
+		kRsBlocked = 8u,        // light: shadow ray hit something
+		kRsTransRay = 16u,      // sample: bTransmissionRay
+		kRsMiss = 32u,          // sample: ray missed -> a = clamp(term*ambient)
+		kRsHit = 64u,           // sample: hit with bounceLimit > 0 -> a = clamp(term*att*L) (written by the child's gather, or by classify when no child runs)
+		kRsHit0 = 128u,         // sample: hit with bounceLimit == 0 (:835 only)
+		kRsSky2 = 256u,         // sample: TraceSky behind the hit returned non-zero -> b = att (:825-831)
+		kRsSkipped = 512u,      // sample: rejection budget exhausted
+	};
+
+	// What a ray's result is weighted with; rewritten in place by classify / sky / the child's gather.
+	struct alignas(16) RayAux
+	{
+		float a0, a1, a2, a3;    // light: BRDF*intensity*angle | hemi: BRDF, angle -> contribution | sample: term, pdf -> value, pdf
+		float b0, b1, b2;        // sample: b0 = new environment IOR -> b = TraceSky attenuation
+		uint32_t tag;            // kind | state | owner... (owner record lives in `owner`)
+	};
+	static_assert(sizeof(RayAux) == 32, "RayAux layout");
+
+	// TraceSky (:577-620) in flight through a thick transmissive surface
+	struct alignas(16) SkyState
+	{
+		V3 att; uint32_t targetAux;
+		V3 prev; uint32_t ignore;
+		V3 start; float ior;
+		V3 dir; uint32_t jAndMax;      // j | maxBounces << 16
+	};
+	static_assert(sizeof(SkyState) == 64, "SkyState layout");
+
+	struct LevelInfo { uint32_t recBegin, recEnd, rayCount, auxBase; };
+
+	// device-side allocation state of one batch
+	struct BatchCounters
+	{
+		uint32_t recAlloc;         // records allocated so far (all levels)
+		uint32_t auxAlloc;         // RayAux entries handed to finished levels
+		uint32_t overflow;         // any arena ran out: the batch is invalid, the host retries with a smaller one
+		uint32_t skyCount[2];      // ping-pong sky queues
+		uint32_t zero;             // always 0 (range begin)
+		uint32_t pad[2];
+		unsigned long long rays;   // closest-hit queries of the batch
+		LevelInfo level[66];
+	};
 
 	struct IntegratorArgs
 	{
@@ -102,13 +128,14 @@ namespace spt
 		// camera / params
 		CameraGpu cam; uint32_t rowBegin, rowEnd, msBegin, msEnd, msaa;
 		uint32_t maxBounces, numSamples, numAmbientSamples; V3 ambient; uint64_t seed;
-		// pool
-		uint32_t poolSize; uint32_t maxDepth;
-		PathHeader* headers; Frame* frames; RayRec* rays; const Hit* hits;
+		// batch
+		const PrimaryHitRec* hitQueue; uint32_t queueBegin, queueCount;     // first hits [queueBegin, queueBegin+queueCount) are level 0
+		NodeRec* recs; uint32_t recCap;
+		RayAux* aux; uint32_t* auxOwner; uint32_t auxCap;                     // auxOwner: record (or child record for kRkOwn) of each RayAux
+		RayRec* rays; Hit* hits; uint32_t rayCap;                             // ray queue of the current level
+		SkyState* sky[2]; RayRec* skyRays; Hit* skyHits; uint32_t skyCap;
+		BatchCounters* c;
 		float* sampleBuf;                       // 3 floats per (pixel in band, sample in range)
-		const PrimaryHitRec* hitQueue; uint32_t queueCount;   // first hits found by the primary pass
-		uint32_t* nextSample;                                   // work counter over hitQueue
-		uint32_t* activeCount; unsigned long long* rayCount;
 	};
 
 	// ---- random numbers --------------------------------------------------------------
@@ -120,6 +147,7 @@ namespace spt
 	{
 		return Mix64(seed * 0x9E3779B97F4A7C15ULL + ((uint64_t)pixel * msaa + sample) + 0x632BE59BD9B4E019ULL);
 	}
+	SPT_HD uint64_t ChildRngKey(uint64_t key, uint32_t slot) { return Mix64(key + 0xD1B54A32D192ED03ULL * (uint64_t)(slot + 1u)); }
 	struct Rng
 	{
 		uint64_t key; uint32_t counter;
@@ -137,487 +165,545 @@ namespace spt
 		SPT_KERNEL_BODY uint32_t Seed681() { return U32() % 681u; }
 	};
 
-	// ---- the state machine --------------------------------------------------------------------------------------
-	struct PathMachine
+	// ---- helpers shared by the kernels ---------------------------------------------------------------------------
+	SPT_KERNEL_BODY uint32_t MaterialOfTri(const IntegratorArgs& a, uint32_t tri) { return f2u(ld4(a.centroid + tri).w); }
+
+	SPT_KERNEL_BODY V3 HitNormalOf(const IntegratorArgs& a, uint32_t tri, float u, float v)   // Bounds.cpp:525-527
 	{
-		const IntegratorArgs& a;
-		uint32_t slot;
-		PathHeader hd;
-		Rng rng;
-		Frame* f;
-		bool rayEmitted;
+		const V4* S = a.shade + (size_t)tri * 9;
+		const V4 n0 = ld4(S), n1 = ld4(S + 1), n2 = ld4(S + 2);
+		const float w = 1.0f - u - v;
+		return w * v3(n0.x, n0.y, n0.z) + u * v3(n1.x, n1.y, n1.z) + v * v3(n2.x, n2.y, n2.z);
+	}
 
-		SPT_KERNEL_BODY PathMachine(const IntegratorArgs& args, uint32_t s) : a(args), slot(s), f(nullptr), rayEmitted(false) {}
+	SPT_KERNEL_BODY void WriteRay(RayRec* q, uint32_t i, V3 o, V3 d, uint32_t ignore, bool active)
+	{
+		RayRec r; r.ox = o.x; r.oy = o.y; r.oz = o.z; r.ignoreTri = ignore; r.dx = d.x; r.dy = d.y; r.dz = d.z; r.tmax = active ? kFltMax : -1.0f;
+		q[i] = r;
+	}
 
-		SPT_KERNEL_BODY Frame* FrameAt(uint32_t depth) const { return a.frames + (size_t)depth * a.poolSize + slot; }
+	SPT_KERNEL_BODY void WriteAux(const IntegratorArgs& a, uint32_t g, float a0, float a1, float a2, float a3, float b0, uint32_t tag, uint32_t owner)
+	{
+		RayAux x; x.a0 = a0; x.a1 = a1; x.a2 = a2; x.a3 = a3; x.b0 = b0; x.b1 = 0.0f; x.b2 = 0.0f; x.tag = tag;
+		a.aux[g] = x; a.auxOwner[g] = owner;
+	}
 
-		SPT_KERNEL_BODY void Emit(V3 o, V3 d, uint32_t ignore)
+	SPT_KERNEL_BODY uint32_t AllocRecord(const IntegratorArgs& a)
+	{
+		const uint32_t i = atomic_add_u32(&a.c->recAlloc, 1u);
+		if (i >= a.recCap) { a.c->overflow = 1u; return kNone; }
+		return i;
+	}
+
+	// One TraceSky loop iteration (:585-616) on the result of the state's pending ray.
+	// Returns true when the walk goes on (state updated, next ray = (start, dir, ignore)); false when done (att = result).
+	SPT_KERNEL_BODY bool SkyAdvance(const IntegratorArgs& a, SkyState& s, const Hit& hit, V3& result)
+	{
+		if (hit.tri == kNoHit) { result = s.att; return false; }                      // :587-590
+		const MaterialGpu& m = a.materials[MaterialOfTri(a, hit.tri)];
+		const V3 hn = HitNormalOf(a, hit.tri, hit.u, hit.v);
+		const bool hitOpp = dot(s.dir, hn) < 0.0f;
+		if (!(m.transmission > 0.0f && m.thickness > 0.0f)) { result = v3(0.0f); return false; }   // :597-600
+		const V3 hp = s.start + s.dir * hit.t;
+		const float distance = length(hp - s.prev);
+		s.prev = hp;
+		const V3 wn = hitOpp ? hn : -hn;
+		const float toIor = hitOpp ? m.ior : 1.0f;
+		s.dir = CalculateRefraction(s.dir, wn, s.ior, toIor);
+		s.ior = toIor;
+		if (!hitOpp)
 		{
-			RayRec r; r.ox = o.x; r.oy = o.y; r.oz = o.z; r.ignoreTri = ignore; r.dx = d.x; r.dy = d.y; r.dz = d.z; r.tmax = kFltMax;
-			a.rays[slot] = r;
-			rayEmitted = true;
+			const V3 c = v3(-logf(m.attenuationColor[0]), -logf(m.attenuationColor[1]), -logf(m.attenuationColor[2])) / m.attenuationDistance;
+			const V3 e = -c * distance;
+			s.att = s.att * v3(expf(e.x), expf(e.y), expf(e.z));
 		}
+		s.start = hp; s.ignore = hit.tri;
+		const uint32_t j = (s.jAndMax & 0xFFFFu) + 1u, mx = s.jAndMax >> 16;
+		s.jAndMax = j | (mx << 16);
+		if (j < mx) return true;
+		result = v3(0.0f);                                                             // loop ran out (:619)
+		return false;
+	}
 
-		SPT_KERNEL_BODY V3 HitNormal(uint32_t tri, float u, float v) const   // Bounds.cpp:525-527
+	// Final value of a TraceSky walk lands in the RayAux it was started for.
+	SPT_KERNEL_BODY void SkyFinish(const IntegratorArgs& a, uint32_t g, V3 att)
+	{
+		RayAux x = a.aux[g];
+		const bool nonZero = att.x != 0.0f || att.y != 0.0f || att.z != 0.0f;
+		if ((x.tag & kRkMask) == kRkHemi)                                               // :730-735
 		{
-			const V4* S = a.shade + (size_t)tri * 9;
-			const V4 n0 = ld4(S), n1 = ld4(S + 1), n2 = ld4(S + 2);
-			const float w = 1.0f - u - v;
-			return w * v3(n0.x, n0.y, n0.z) + u * v3(n1.x, n1.y, n1.z) + v * v3(n2.x, n2.y, n2.z);
+			V3 c = v3(0.0f);
+			if (nonZero)
+			{
+				const float pdfHemisphere = 1.0f / (kPiSailor * 2.0f);
+				const V3 at = att * v3(x.a0, x.a1, x.a2);
+				c = glm_clamp((at * a.ambient * x.a3) / pdfHemisphere, 0.0f, 10.0f);
+			}
+			x.a0 = c.x; x.a1 = c.y; x.a2 = c.z;
 		}
-		SPT_KERNEL_BODY uint32_t MaterialOf(uint32_t tri) const { return f2u(ld4(a.centroid + tri).w); }
-
-		SPT_KERNEL_BODY V2 BlueNoise()                                        // PathTracer.cpp:934-1077
+		else                                                                            // :825-831
 		{
-			if (f->seedX >= 688u) f->seedX = rng.Seed681();
-			if (f->seedY >= 688u) f->seedY = rng.Seed681();
-			const float x = (float)a.blueNoise[f->seedX++] * (1.0f / 1024.0f), y = (float)a.blueNoise[f->seedY++] * (1.0f / 1024.0f);
+			x.b0 = att.x; x.b1 = att.y; x.b2 = att.z;
+			if (nonZero) x.tag |= kRsSky2;
+		}
+		a.aux[g] = x;
+	}
+
+	SPT_KERNEL_BODY void SkyPush(const IntegratorArgs& a, uint32_t q, const SkyState& s)
+	{
+		const uint32_t i = atomic_add_u32(&a.c->skyCount[q], 1u);
+		if (i >= a.skyCap) { a.c->overflow = 1u; return; }
+		a.sky[q][i] = s;
+		WriteRay(a.skyRays + (q ? a.skyCap : 0u), i, s.start, s.dir, s.ignore, true);      // each queue owns one half of skyRays
+	}
+
+	// ---- level 0: first hits of the primary pass become records --------------------------------------------------
+	struct SeedKernel
+	{
+		IntegratorArgs a;
+		SPT_KERNEL_BODY void operator()(uint32_t i) const
+		{
+			const PrimaryHitRec rec = a.hitQueue[a.queueBegin + i];
+			const uint32_t x = rec.pixel % a.cam.width, y = rec.pixel / a.cam.width;
+			Rng rng; rng.key = PrimaryRngKey(a.seed, rec.pixel, a.msaa, rec.sample); rng.counter = 0;
+			float ox = 0.5f, oy = 0.5f;                                           // :460
+			if (rec.sample != 0) { ox = rng.Float01(); oy = rng.Float01(); }
+			NodeRec n;
+			n.rayO = a.cam.pos; n.parent = rec.pixel;
+			n.rayD = PrimaryDir(a.cam, x, y, ox, oy); n.parentAux = rec.sample;
+			n.t = rec.t; n.u = rec.u; n.v = rec.v; n.tri = rec.tri;
+			n.inAcc = 1.0f; n.envIor = 1.0f; n.bounces = a.maxBounces | (a.maxBounces << 16); n.flags = kNfLevel0;
+			n.rngKey = ChildRngKey(rng.key, 0x7FFFFFFFu); n.auxBase = 0; n.child = kNone;
+			n.pNumSamples = a.numSamples; n.pNumAmbient = a.numAmbientSamples; n.nA = 0; n.nS = 0;
+			n.emissive = v3(0.0f); n.alpha = 1.0f; n.result = v3(0.0f); n.nLights = 0;
+			a.recs[i] = n;
+		}
+	};
+
+	// ---- expand: shade one activation and emit all of its rays ----------------------------------------------------
+	struct ExpandKernel
+	{
+		IntegratorArgs a; uint32_t level;
+
+		struct Ctx2
+		{
+			Rng rng; uint32_t seedX, seedY;
+		};
+
+		SPT_KERNEL_BODY V2 BlueNoise(Ctx2& c) const                                  // PathTracer.cpp:934-1077
+		{
+			if (c.seedX >= 688u) c.seedX = c.rng.Seed681();
+			if (c.seedY >= 688u) c.seedY = c.rng.Seed681();
+			const float x = (float)a.blueNoise[c.seedX++] * (1.0f / 1024.0f), y = (float)a.blueNoise[c.seedY++] * (1.0f / 1024.0f);
 			return v2(x, y);
 		}
 
-		// Entry of Raytrace (:622-632): draw the two table seeds; the ray is traced unless the caller already has the hit.
-		SPT_KERNEL_BODY void BeginCall()
+		// child activation that still needs its own closest hit (alpha continuation / thick-volume tail call)
+		SPT_KERNEL_BODY uint32_t SpawnOwn(const NodeRec& n, uint32_t self, V3 o, V3 d, uint32_t bounceLimit, uint32_t pMaxBounces, uint32_t pNumSamples,
+			uint32_t pNumAmbient, float inAcc, float envIor, uint32_t slot) const
 		{
-			f->seedX = rng.Seed681(); f->seedY = rng.Seed681();
-			f->phase = kPhMain;
+			const uint32_t ci = AllocRecord(a);
+			if (ci == kNone) return kNone;
+			NodeRec c;
+			c.rayO = o; c.parent = self; c.rayD = d; c.parentAux = kNone;
+			c.t = 0.0f; c.u = 0.0f; c.v = 0.0f; c.tri = kNoHit;
+			c.inAcc = inAcc; c.envIor = envIor; c.bounces = bounceLimit | (pMaxBounces << 16); c.flags = 0;
+			c.rngKey = ChildRngKey(n.rngKey, slot); c.auxBase = 0; c.child = kNone;
+			c.pNumSamples = pNumSamples; c.pNumAmbient = pNumAmbient; c.nA = 0; c.nS = 0;
+			c.emissive = v3(0.0f); c.alpha = 1.0f; c.result = v3(0.0f); c.nLights = 0;
+			a.recs[ci] = c;
+			return ci;
 		}
 
-		SPT_KERNEL_BODY void StartSky(V3 start, V3 toL, float ior, uint32_t ignore)   // TraceSky prologue (:579-580)
+		SPT_KERNEL_BODY void operator()(uint32_t ri) const
 		{
-			f->skyAtt = v3(1.0f); f->skyPrev = start; f->skyStart = start; f->skyDir = toL; f->skyIor = ior; f->skyIgnore = ignore; f->skyJ = 0;
-		}
+			NodeRec n = a.recs[ri];
+			if (n.flags & kNfDone) return;
+			LevelInfo* L = &a.c->level[level];
+			const uint32_t bounceLimit = n.bounces & 0xFFFFu, pMaxBounces = n.bounces >> 16;
+			Ctx2 cx; cx.rng.key = n.rngKey; cx.rng.counter = 0;
+			cx.seedX = cx.rng.Seed681(); cx.seedY = cx.rng.Seed681();                   // :626-627
 
-		// Start the next first-hit record of the primary pass (:444-466): frame 0 is set up exactly as Raytrace would
-		// see it and resumed with the hit the primary pass already found.  Returns false when the queue is exhausted.
-		SPT_KERNEL_BODY bool NextFromQueue()
-		{
-			const uint32_t g = atomic_add_u32(a.nextSample, 1u);
-			if (g >= a.queueCount) return false;
-			const PrimaryHitRec rec = a.hitQueue[g];
-			const uint32_t x = rec.pixel % a.cam.width, y = rec.pixel / a.cam.width;
-			hd.active = 1; hd.depth = 0; hd.pixel = rec.pixel; hd.sample = rec.sample;
-			hd.rngKey = PrimaryRngKey(a.seed, rec.pixel, a.msaa, rec.sample);
-			rng.key = hd.rngKey; rng.counter = 0;
-			float ox = 0.5f, oy = 0.5f;                                           // :460
-			if (rec.sample != 0) { ox = rng.Float01(); oy = rng.Float01(); }
-			f = FrameAt(0);
-			f->rayO = a.cam.pos; f->rayD = PrimaryDir(a.cam, x, y, ox, oy);
-			f->ignoreTri = kNoHit; f->bounceLimit = a.maxBounces; f->inAcc = 1.0f; f->envIor = 1.0f;
-			f->pMaxBounces = a.maxBounces; f->pNumSamples = a.numSamples; f->pNumAmbient = a.numAmbientSamples;
-			BeginCall();
-			Hit h; h.t = rec.t; h.u = rec.u; h.v = rec.v; h.tri = rec.tri;
-			Advance(h);
-			return true;
-		}
+			// ---- :636-671 shading context
+			const uint32_t tri = n.tri;
+			const V4* S = a.shade + (size_t)tri * 9;
+			const V4 s0 = ld4(S), s1 = ld4(S + 1), s2 = ld4(S + 2), s3 = ld4(S + 3), s4 = ld4(S + 4), s5 = ld4(S + 5), s6 = ld4(S + 6), s7 = ld4(S + 7), s8 = ld4(S + 8);
+			const float bu = n.u, bv = n.v, bw = 1.0f - bu - bv;
+			V3 faceNormal = bw * v3(s0.x, s0.y, s0.z) + bu * v3(s1.x, s1.y, s1.z) + bv * v3(s2.x, s2.y, s2.z);
+			const V3 tangent = bw * v3(s3.x, s3.y, s3.z) + bu * v3(s4.x, s4.y, s4.z) + bv * v3(s5.x, s5.y, s5.z);
+			const V3 bitangent = bw * v3(s6.x, s6.y, s6.z) + bu * v3(s7.x, s7.y, s7.z) + bv * v3(s8.x, s8.y, s8.z);
+			const bool opposite = dot(faceNormal, n.rayD) < 0.0f;
+			if (!opposite) faceNormal = faceNormal * -1.0f;
+			const V2 uv = bw * v2(s0.w, s1.w) + bu * v2(s2.w, s3.w) + bv * v2(s4.w, s5.w);
+			const uint32_t matIdx = f2u(s6.w);
+			const MaterialGpu& m = a.materials[matIdx];
+			const float* T = m.uvTransform;
+			const float tu = T[0] * uv.x + T[4] * uv.y + T[8] * 1.0f, tv = T[1] * uv.x + T[5] * uv.y + T[9] * 1.0f;
+			// GetMaterialData (:881-927)
+			SampledData s;
+			s.baseColor = v4(m.baseColor[0], m.baseColor[1], m.baseColor[2], m.baseColor[3]);
+			V3 nrm = v3(0.0f, 0.0f, 1.0f);
+			s.orm = v3(0.0f, m.roughness, m.metallic);
+			s.emissive = v3(m.emissive[0], m.emissive[1], m.emissive[2]);
+			s.transmission = m.transmission;
+			if (m.texBase != kNoTexture) { const V4 t = SampleTexture(a.tex, m.texBase, tu, tv); s.baseColor = v4(s.baseColor.x * t.x, s.baseColor.y * t.y, s.baseColor.z * t.z, s.baseColor.w * t.w); }
+			if (m.texEmissive != kNoTexture) { const V4 t = SampleTexture(a.tex, m.texEmissive, tu, tv); s.emissive = s.emissive * v3(t.x, t.y, t.z); }
+			if (m.texMetallicRoughness != kNoTexture) { const V4 t = SampleTexture(a.tex, m.texMetallicRoughness, tu, tv); s.orm = v3(t.x, s.orm.y * t.y, s.orm.z * t.z); }
+			if (m.texNormal != kNoTexture) { const V4 t = SampleTexture(a.tex, m.texNormal, tu, tv); nrm = v3(t.x, t.y, t.z); }
+			if (m.texTransmission != kNoTexture) { const V4 t = SampleTexture(a.tex, m.texTransmission, tu, tv); s.transmission *= t.x; }
+			if (m.blendMode == kMask) s.baseColor.w = (s.baseColor.w > m.alphaCutoff) ? 1.0f : 0.0f;
+			s.opaque = m.blendMode == kOpaque;
+			s.normal = nrm; s.ior = m.ior; s.thickness = m.thickness;
 
-		SPT_KERNEL_BODY SampledData Sampled() const
-		{
-			SampledData s; s.baseColor = f->baseColor; s.orm = f->orm; s.emissive = f->emissive; s.normal = v3(0.0f, 0.0f, 1.0f);
-			s.ior = f->ior; s.thickness = f->thickness; s.transmission = f->transmission; s.opaque = true;
-			return s;
-		}
+			const V3 V = -normalize(n.rayD);
+			// tbn * normal, glm mat3 * vec3 order (type_mat3x3.inl:468-474)
+			const V3 N = normalize(v3(tangent.x * nrm.x + bitangent.x * nrm.y + faceNormal.x * nrm.z,
+				tangent.y * nrm.x + bitangent.y * nrm.y + faceNormal.y * nrm.z,
+				tangent.z * nrm.x + bitangent.z * nrm.y + faceNormal.z * nrm.z));
+			const bool alphaBlend = !s.opaque && s.baseColor.w < 1.0f;
+			const uint32_t sRound = (uint32_t)roundf(s.baseColor.w * (float)n.pNumSamples), aRound = (uint32_t)roundf(s.baseColor.w * (float)n.pNumAmbient);
+			const uint32_t numSamples = alphaBlend ? (sRound > 1u ? sRound : 1u) : n.pNumSamples;
+			const uint32_t numAmbient = alphaBlend ? (aRound > 1u ? aRound : 1u) : n.pNumAmbient;
+			const V3 offset = 0.000001f * faceNormal;
+			const bool fullMetal = s.orm.z == 1.0f;
+			const bool hasTrans = !fullMetal && s.transmission > 0.0f;
+			const bool thick = hasTrans && m.thickness > 0.0f;
+			const V3 hitPoint = n.rayO + n.rayD * n.t;
 
-		// Runs until a ray has been emitted or the slot has no more work.  `hit` is the result of the pending ray.
-		SPT_KERNEL_BODY void Advance(Hit hit)
-		{
-			enum Act { OnResult, Shade, LightsNext, AmbientBegin, HemiNext, SkyStep, SkyDone, SamplesBegin, SampleNext, AfterChildSample, AmbientEnd, Finish, AfterChildAlpha, Return, Done };
-			Act act = OnResult;
-			V3 retVal = v3(0.0f);      // value being returned by a finished call
-			V3 skyResult = v3(0.0f);
-			for (;;)
+			if (!opposite && thick)                                                      // :673-688 (tail call)
 			{
-				switch (act)
-				{
-				case OnResult:
-				{
-					switch (f->phase)
-					{
-					case kPhMain:
-						if (hit.tri == kNoHit) { retVal = a.ambient; act = Return; }   // :873-876
-						else act = Shade;
-						break;
-					case kPhLight:
-					{
-						if (hit.tri == kNoHit)                                          // :699-703
-						{
-							const V4 ld = a.lights[f->loopI * 2], li = a.lights[f->loopI * 2 + 1];
-							const V3 toL = -v3(ld.x, ld.y, ld.z);
-							const float angle = glm_max(0.0f, dot(toL, f->N));
-							f->res = f->res + CalculateBRDF(f->V, f->N, toL, Sampled()) * v3(li.x, li.y, li.z) * angle;
-						}
-						else f->flags |= kFlLightBlocked;
-						f->loopI++;
-						act = LightsNext;
-						break;
-					}
-					case kPhSkyHemi:
-					case kPhSkySample:
-					{
-						// TraceSky loop body (:585-616)
-						if (hit.tri == kNoHit) { skyResult = f->skyAtt; act = SkyDone; break; }
-						const MaterialGpu& m = a.materials[MaterialOf(hit.tri)];
-						const V3 hn = HitNormal(hit.tri, hit.u, hit.v);
-						const bool hitOpp = dot(f->skyDir, hn) < 0.0f;
-						if (!(m.transmission > 0.0f && m.thickness > 0.0f)) { skyResult = v3(0.0f); act = SkyDone; break; }
-						const V3 hp = f->skyStart + f->skyDir * hit.t;
-						const float distance = length(hp - f->skyPrev);
-						f->skyPrev = hp;
-						const V3 wn = hitOpp ? hn : -hn;
-						const float toIor = hitOpp ? m.ior : 1.0f;
-						f->skyDir = CalculateRefraction(f->skyDir, wn, f->skyIor, toIor);
-						f->skyIor = toIor;
-						if (!hitOpp)
-						{
-							const V3 c = v3(-logf(m.attenuationColor[0]), -logf(m.attenuationColor[1]), -logf(m.attenuationColor[2])) / m.attenuationDistance;
-							const V3 e = -c * distance;
-							f->skyAtt = f->skyAtt * v3(expf(e.x), expf(e.y), expf(e.z));
-						}
-						f->skyStart = hp; f->skyIgnore = hit.tri; f->skyJ++;
-						act = SkyStep;
-						break;
-					}
-					case kPhSample:
-					{
-						const V3 term = f->term;
-						if (hit.tri == kNoHit)                                          // :786-796
-						{
-							const V3 value = glm_clamp(term * a.ambient, 0.0f, 10.0f);
-							f->amb2 = f->amb2 + value; f->avgPdf += f->pdf; f->indirect = f->indirect + value;
-							f->cnt += 1.0f; f->loopI++;
-							act = SampleNext;
-						}
-						else if (f->bounceLimit > 0)                                    // :797-833
-						{
-							V3 att = v3(1.0f);
-							const V3 h2p = f->r2o + f->r2d * hit.t;
-							if ((f->flags & kFlOpposite) && (f->flags & kFlTransRay) && (f->flags & kFlThick))
-							{
-								const MaterialGpu& m = a.materials[f->matIdx];
-								const float distance = length(h2p - f->hitPoint);
-								const V3 c = v3(-logf(m.attenuationColor[0]), -logf(m.attenuationColor[1]), -logf(m.attenuationColor[2])) / m.attenuationDistance;
-								const V3 e = -c * distance;
-								att = v3(expf(e.x), expf(e.y), expf(e.z));
-							}
-							f->att = att; f->h2tri = hit.tri;
-							const float newAcc = f->inAcc * length(term * att) * f->baseColor.w;
-							if (newAcc > 0.01f)                                         // :810-814
-							{
-								Frame* parent = f;
-								parent->phase = kPhChildSample;
-								hd.depth++;
-								f = FrameAt(hd.depth);
-								f->rayO = parent->r2o; f->rayD = parent->r2d; f->ignoreTri = parent->hitTri; f->bounceLimit = parent->bounceLimit - 1;
-								f->inAcc = newAcc; f->envIor = parent->newIor;
-								f->pMaxBounces = parent->pMaxBounces; f->pNumSamples = parent->pNumSamples; f->pNumAmbient = parent->pNumAmbient;
-								BeginCall();
-								act = Shade;   // the child's own IntersectBVH (:632) would return exactly `hit`
-							}
-							else { retVal = v3(0.0f); act = AfterChildSample; }
-						}
-						else { f->cnt += 1.0f; f->loopI++; act = SampleNext; }        // hit, but no bounces left (:835)
-						break;
-					}
-					default: act = Done; break;   // unreachable
-					}
-					break;
-				}
-				case Shade:
-				{
-					// :636-688
-					const uint32_t tri = hit.tri;
-					const V4* S = a.shade + (size_t)tri * 9;
-					const V4 s0 = ld4(S), s1 = ld4(S + 1), s2 = ld4(S + 2), s3 = ld4(S + 3), s4 = ld4(S + 4), s5 = ld4(S + 5), s6 = ld4(S + 6), s7 = ld4(S + 7), s8 = ld4(S + 8);
-					const float bu = hit.u, bv = hit.v, bw = 1.0f - bu - bv;
-					V3 faceNormal = bw * v3(s0.x, s0.y, s0.z) + bu * v3(s1.x, s1.y, s1.z) + bv * v3(s2.x, s2.y, s2.z);
-					const V3 tangent = bw * v3(s3.x, s3.y, s3.z) + bu * v3(s4.x, s4.y, s4.z) + bv * v3(s5.x, s5.y, s5.z);
-					const V3 bitangent = bw * v3(s6.x, s6.y, s6.z) + bu * v3(s7.x, s7.y, s7.z) + bv * v3(s8.x, s8.y, s8.z);
-					const bool opposite = dot(faceNormal, f->rayD) < 0.0f;
-					if (!opposite) faceNormal = faceNormal * -1.0f;
-					const V2 uv = bw * v2(s0.w, s1.w) + bu * v2(s2.w, s3.w) + bv * v2(s4.w, s5.w);
-					const uint32_t matIdx = f2u(s6.w);
-					const MaterialGpu& m = a.materials[matIdx];
-					const float* T = m.uvTransform;
-					const float tu = T[0] * uv.x + T[4] * uv.y + T[8] * 1.0f, tv = T[1] * uv.x + T[5] * uv.y + T[9] * 1.0f;
-					// GetMaterialData (:881-927)
-					V4 baseColor = v4(m.baseColor[0], m.baseColor[1], m.baseColor[2], m.baseColor[3]);
-					V3 nrm = v3(0.0f, 0.0f, 1.0f);
-					V3 orm = v3(0.0f, m.roughness, m.metallic);
-					V3 emissive = v3(m.emissive[0], m.emissive[1], m.emissive[2]);
-					float transmission = m.transmission;
-					if (m.texBase != kNoTexture) { const V4 t = SampleTexture(a.tex, m.texBase, tu, tv); baseColor = v4(baseColor.x * t.x, baseColor.y * t.y, baseColor.z * t.z, baseColor.w * t.w); }
-					if (m.texEmissive != kNoTexture) { const V4 t = SampleTexture(a.tex, m.texEmissive, tu, tv); emissive = emissive * v3(t.x, t.y, t.z); }
-					if (m.texMetallicRoughness != kNoTexture) { const V4 t = SampleTexture(a.tex, m.texMetallicRoughness, tu, tv); orm = v3(t.x, orm.y * t.y, orm.z * t.z); }
-					if (m.texNormal != kNoTexture) { const V4 t = SampleTexture(a.tex, m.texNormal, tu, tv); nrm = v3(t.x, t.y, t.z); }
-					if (m.texTransmission != kNoTexture) { const V4 t = SampleTexture(a.tex, m.texTransmission, tu, tv); transmission *= t.x; }
-					if (m.blendMode == kMask) baseColor.w = (baseColor.w > m.alphaCutoff) ? 1.0f : 0.0f;
-					const bool opaque = m.blendMode == kOpaque;
+				const V3 nd = CalculateRefraction(n.rayD, N, n.envIor, 1.0f);
+				NodeRec* out = a.recs + ri;
+				if (eq0(nd) || bounceLimit == 0) { out->result = v3(0.0f); out->flags = n.flags | kNfDone; return; }
+				const uint32_t base = atomic_add_u32(&L->rayCount, 1u);
+				if (base >= a.rayCap || L->auxBase + base >= a.auxCap) { a.c->overflow = 1u; out->result = v3(0.0f); out->flags = n.flags | kNfDone; return; }
+				const V3 d = nd - offset;
+				const uint32_t ci = SpawnOwn(n, ri, hitPoint, d, bounceLimit - 1u, pMaxBounces, n.pNumSamples, n.pNumAmbient, n.inAcc, 1.0f, 0x40000000u);
+				WriteRay(a.rays, base, hitPoint, d, tri, ci != kNone);
+				WriteAux(a, L->auxBase + base, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, ci != kNone ? kRkOwn : kRkInactive, ci);
+				out->auxBase = L->auxBase + base; out->child = ci; out->flags = n.flags | kNfTail;
+				out->nLights = 0; out->nA = 0; out->nS = 0;
+				return;
+			}
 
-					const V3 V = -normalize(f->rayD);
-					// tbn * normal, glm mat3 * vec3 order (type_mat3x3.inl:468-474)
-					const V3 N = normalize(v3(tangent.x * nrm.x + bitangent.x * nrm.y + faceNormal.x * nrm.z,
-						tangent.y * nrm.x + bitangent.y * nrm.y + faceNormal.y * nrm.z,
-						tangent.z * nrm.x + bitangent.z * nrm.y + faceNormal.z * nrm.z));
-					const bool alphaBlend = !opaque && baseColor.w < 1.0f;
-					const uint32_t sRound = (uint32_t)roundf(baseColor.w * (float)f->pNumSamples), aRound = (uint32_t)roundf(baseColor.w * (float)f->pNumAmbient);
-					const uint32_t numSamples = alphaBlend ? (sRound > 1u ? sRound : 1u) : f->pNumSamples;
-					const uint32_t numAmbient = alphaBlend ? (aRound > 1u ? aRound : 1u) : f->pNumAmbient;
-					const V3 offset = 0.000001f * faceNormal;
-					const bool fullMetal = orm.z == 1.0f;
-					const bool hasTrans = !fullMetal && transmission > 0.0f;
-					const bool thick = hasTrans && m.thickness > 0.0f;
-					const V3 hitPoint = f->rayO + f->rayD * hit.t;
+			const bool first = bounceLimit == pMaxBounces;                               // :636
+			const bool ambientOn = a.ambient.x + a.ambient.y + a.ambient.z > 0.0f;       // :708
+			const uint32_t nA = ambientOn ? (first ? numAmbient : 1u) : 0u;              // :716
+			const uint32_t nS = ambientOn ? (first ? numSamples : 1u) : 0u;              // :717
+			const uint32_t nHemi = thick ? 0u : nA;                                      // :720
+			const bool alphaChild = bounceLimit > 0 && alphaBlend;                       // :858
+			const uint32_t nRays = a.numLights + nHemi + nS + (alphaChild ? 1u : 0u);
+			NodeRec* out = a.recs + ri;
+			uint32_t base = 0;
+			if (nRays)
+			{
+				base = atomic_add_u32(&L->rayCount, nRays);
+				if (base + nRays > a.rayCap || L->auxBase + base + nRays > a.auxCap)
+				{
+					a.c->overflow = 1u; out->result = v3(0.0f); out->flags = n.flags | kNfDone; return;
+				}
+			}
+			const uint32_t g0 = L->auxBase + base;
+			uint32_t r = base;
 
-					if (!opposite && thick)                                             // :673-688 (tail call)
-					{
-						const V3 nd = CalculateRefraction(f->rayD, N, f->envIor, 1.0f);
-						if (eq0(nd) || f->bounceLimit == 0) { retVal = v3(0.0f); act = Return; break; }
-						f->rayO = hitPoint; f->rayD = nd - offset; f->bounceLimit -= 1; f->ignoreTri = tri; f->envIor = 1.0f;
-						BeginCall();
-						Emit(f->rayO, f->rayD, f->ignoreTri);
-						act = Done;
-						break;
-					}
-					const bool first = f->bounceLimit == f->pMaxBounces;                // :636
-					f->hitPoint = hitPoint; f->hitTri = tri; f->N = N; f->matIdx = matIdx; f->V = V; f->offset = offset;
-					f->flags = (opposite ? kFlOpposite : 0u) | (thick ? kFlThick : 0u) | (alphaBlend ? kFlAlpha : 0u) | (first ? kFlFirst : 0u);
-					f->baseColor = baseColor; f->orm = orm; f->ior = m.ior; f->emissive = emissive; f->transmission = transmission; f->thickness = m.thickness;
-					f->S = numSamples; f->A = numAmbient;
-					f->res = v3(0.0f); f->loopI = 0;
-					act = LightsNext;
-					break;
-				}
-				case LightsNext:                                                        // :691-705
+			// ---- :691-705 directional lights
+			for (uint32_t j = 0; j < a.numLights; j++, r++)
+			{
+				const V4 ld = a.lights[j * 2], li = a.lights[j * 2 + 1];
+				const V3 toL = -v3(ld.x, ld.y, ld.z);
+				const float angle = glm_max(0.0f, dot(toL, N));
+				const V3 w = CalculateBRDF(V, N, toL, s) * v3(li.x, li.y, li.z) * angle;
+				WriteRay(a.rays, r, hitPoint + offset, toL, tri, true);
+				WriteAux(a, L->auxBase + r, w.x, w.y, w.z, 0.0f, 0.0f, kRkLight, ri);
+			}
+			// ---- :720-737 hemisphere samples (TraceSky's first ray)
+			for (uint32_t k = 0; k < nHemi; k++, r++)
+			{
+				const float r0 = cx.rng.Float01(), r1 = cx.rng.Float01();                // NextVec2_Linear (:929-932)
+				const V3 H = ImportanceSampleHemisphere(v2(r0, r1), N);
+				const V3 toL = 2.0f * dot(V, H) * H - V;
+				const bool live = pMaxBounces > 0;                                       // TraceSky's loop runs maxBounces times (:581)
+				const V3 brdf = live ? CalculateBRDF(V, N, toL, s) : v3(0.0f);
+				const float angle = glm_max(0.0f, dot(toL, N));
+				WriteRay(a.rays, r, hitPoint + offset, toL, tri, live);
+				// a dead hemisphere ray contributes 0: kRkInactive with a = 0 is read by gather as a zero contribution
+				WriteAux(a, L->auxBase + r, brdf.x, brdf.y, brdf.z, angle, 0.0f, live ? kRkHemi : kRkInactive, ri);
+			}
+			// ---- :741-784 importance samples
+			{
+				const float toIor = thick ? (opposite ? s.ior : 1.0f) : n.envIor;        // :749
+				const bool mirror = fullMetal && s.orm.y <= 0.001f;
+				bool hasTransRay = false;
+				for (uint32_t i = 0; i < nS; i++, r++)
 				{
-					// QUIRK kept: `RaycastHit hitLight{}` is declared outside the light loop (:694) and IntersectBVH only
-					// writes it on a hit, so after the first shadowed light every later light reads the stale hit and is
-					// treated as shadowed too.  Their rays cannot change the result and are not traced.
-					if (f->loopI < a.numLights && !(f->flags & kFlLightBlocked))
-					{
-						const V4 ld = a.lights[f->loopI * 2];
-						f->phase = kPhLight;
-						Emit(f->hitPoint + f->offset, -v3(ld.x, ld.y, ld.z), f->hitTri);
-						act = Done;
-					}
-					else act = AmbientBegin;
-					break;
-				}
-				case AmbientBegin:                                                      // :708-717
-				{
-					if (!(a.ambient.x + a.ambient.y + a.ambient.z > 0.0f)) { act = Finish; break; }
-					const bool first = (f->flags & kFlFirst) != 0;
-					f->nA = first ? f->A : 1u; f->nS = first ? f->S : 1u;
-					f->amb1 = v3(0.0f); f->loopI = 0;
-					act = HemiNext;
-					break;
-				}
-				case HemiNext:                                                          // :720-739
-				{
-					if (!(f->flags & kFlThick) && f->loopI < f->nA)
-					{
-						const float r0 = rng.Float01(), r1 = rng.Float01();               // NextVec2_Linear (:929-932)
-						const V3 H = ImportanceSampleHemisphere(v2(r0, r1), f->N);
-						const V3 toL = 2.0f * dot(f->V, H) * H - f->V;
-						f->skyToL = toL;
-						StartSky(f->hitPoint + f->offset, toL, f->envIor, f->hitTri);
-						f->phase = kPhSkyHemi;
-						act = SkyStep;
-					}
-					else { f->amb1 = f->amb1 / (float)f->nA; act = SamplesBegin; }
-					break;
-				}
-				case SkyStep:                                                           // for (j < maxBounces) (:581-590)
-				{
-					if (f->skyJ < f->pMaxBounces) { Emit(f->skyStart, f->skyDir, f->skyIgnore); act = Done; }
-					else { skyResult = v3(0.0f); act = SkyDone; }
-					break;
-				}
-				case SkyDone:
-				{
-					const V3 att = skyResult;
-					const bool nonZero = att.x != 0.0f || att.y != 0.0f || att.z != 0.0f;
-					if (f->phase == kPhSkyHemi)                                         // :730-735
-					{
-						if (nonZero)
-						{
-							const float pdfHemisphere = 1.0f / (kPiSailor * 2.0f);
-							const float angle = glm_max(0.0f, dot(f->skyToL, f->N));
-							const V3 at = att * CalculateBRDF(f->V, f->N, f->skyToL, Sampled());
-							f->amb1 = f->amb1 + glm_clamp((at * a.ambient * angle) / pdfHemisphere, 0.0f, 10.0f);
-						}
-						f->loopI++;
-						act = HemiNext;
-					}
-					else                                                                // :827-831
-					{
-						if (nonZero) { f->amb2 = f->amb2 + f->value * att; f->avgPdf += f->pdf; }
-						f->cnt += 1.0f; f->loopI++;
-						act = SampleNext;
-					}
-					break;
-				}
-				case SamplesBegin:                                                      // :741-750
-				{
-					f->amb2 = v3(0.0f); f->avgPdf = 0.0f; f->indirect = v3(0.0f); f->cnt = 0.0f;
-					f->toIor = (f->flags & kFlThick) ? ((f->flags & kFlOpposite) ? f->ior : 1.0f) : f->envIor;
-					f->loopI = 0;
-					act = SampleNext;
-					break;
-				}
-				case SampleNext:                                                        // :753-784
-				{
-					if (f->loopI >= f->nS) { act = AmbientEnd; break; }
-					const SampledData s = Sampled();
-					const bool thick = (f->flags & kFlThick) != 0;
-					const bool fullMetal = s.orm.z == 1.0f, mirror = fullMetal && s.orm.y <= 0.001f, hasTrans = !fullMetal && s.transmission > 0.0f;
 					V3 term = v3(0.0f), direction = v3(0.0f);
-					float pdf = 0.0f; bool transRay = false, ok = false, hasTransRay = (f->flags & kFlHasTransRay) != 0;
+					float pdf = 0.0f; bool transRay = false, ok = false;
 					int tries = 0;
-					while ((!ok || (thick && !hasTransRay && f->loopI == (f->nS - 1))) && tries < 4096)
+					while ((!ok || (thick && !hasTransRay && i == (nS - 1u))) && tries < 4096)
 					{
 						direction = v3(0.0f);
-						const V2 Xi = BlueNoise();
-						const float rs = mirror ? 1.0f : rng.Float01();
-						const float rt = hasTrans ? rng.Float01() : 0.0f;
-						ok = SampleBsdf(s, f->N, f->V, f->envIor, f->toIor, term, pdf, transRay, direction, Xi, rs, rt);
+						const V2 Xi = BlueNoise(cx);
+						const float rs = mirror ? 1.0f : cx.rng.Float01();
+						const float rt = hasTrans ? cx.rng.Float01() : 0.0f;
+						ok = SampleBsdf(s, N, V, n.envIor, toIor, term, pdf, transRay, direction, Xi, rs, rt);
 						hasTransRay = hasTransRay || transRay;
 						tries++;
 					}
-					if (hasTransRay) f->flags |= kFlHasTransRay;
-					if (!ok) { f->loopI++; break; }                                     // rejection budget exhausted: skip the sample
-					float newIor = f->envIor;                                           // :769-778
-					const bool opposite = (f->flags & kFlOpposite) != 0;
+					if (!ok)
+					{
+						WriteRay(a.rays, r, hitPoint, v3(0.0f), tri, false);
+						WriteAux(a, L->auxBase + r, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, kRkInactive | kRsSkipped, ri);
+						continue;
+					}
+					float newIor = n.envIor;                                             // :769-778
 					if (opposite && transRay && thick) newIor = s.ior;
 					else if (!opposite && transRay && thick) newIor = 1.0f;
-					f->term = term; f->pdf = pdf; f->newIor = newIor;
-					f->flags = (f->flags & ~kFlTransRay) | (transRay ? kFlTransRay : 0u);
-					f->r2o = f->hitPoint + (transRay ? -f->offset : f->offset); f->r2d = direction;
-					f->phase = kPhSample;
-					Emit(f->r2o, f->r2d, f->hitTri);
-					act = Done;
-					break;
+					WriteRay(a.rays, r, hitPoint + (transRay ? -offset : offset), direction, tri, true);
+					WriteAux(a, L->auxBase + r, term.x, term.y, term.z, pdf, newIor, kRkSample | (transRay ? kRsTransRay : 0u), ri);
 				}
-				case AfterChildSample:                                                  // :816-833
+			}
+			// ---- :858-871 alpha-blend continuation: an independent activation, started now
+			uint32_t child = kNone;
+			if (alphaChild)
+			{
+				const uint32_t mb = pMaxBounces - 1u, nsm = n.pNumSamples - numSamples, nam = n.pNumAmbient - numAmbient;   // std::max(0u, x) is x
+				const V3 o = hitPoint + n.rayD * 0.0001f;
+				child = SpawnOwn(n, ri, o, n.rayD, bounceLimit - 1u, mb, (n.pNumSamples > numSamples && nsm > 1u) ? nsm : 1u,
+					(n.pNumAmbient > numAmbient && nam > 1u) ? nam : 1u, n.inAcc * (1.0f - s.baseColor.w), n.envIor, 0x40000001u);
+				WriteRay(a.rays, r, o, n.rayD, tri, child != kNone);
+				WriteAux(a, L->auxBase + r, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, child != kNone ? kRkOwn : kRkInactive, child);
+				r++;
+			}
+			out->auxBase = g0; out->child = child;
+			out->flags = n.flags | (opposite ? kNfOpposite : 0u) | (thick ? kNfThick : 0u) | (alphaBlend ? kNfAlpha : 0u) | (first ? kNfFirst : 0u) | (ambientOn ? kNfAmbientOn : 0u);
+			out->nA = nA; out->nS = nS; out->nLights = a.numLights;
+			out->emissive = s.emissive; out->alpha = s.baseColor.w;
+		}
+	};
+
+	// ---- classify: fold one ray's closest hit into its RayAux, spawn the child activation of an importance hit --------
+	struct ClassifyKernel
+	{
+		IntegratorArgs a; uint32_t level;
+		SPT_KERNEL_BODY void operator()(uint32_t i) const
+		{
+			const uint32_t g = a.c->level[level].auxBase + i;
+			RayAux x = a.aux[g];
+			const uint32_t kind = x.tag & kRkMask;
+			if (kind == kRkInactive) return;
+			const Hit h = a.hits[i];
+			const uint32_t owner = a.auxOwner[g];
+			if (kind == kRkLight)
+			{
+				if (h.tri != kNoHit) a.aux[g].tag = x.tag | kRsBlocked;                  // :699
+				return;
+			}
+			if (kind == kRkOwn)
+			{
+				NodeRec* c = a.recs + owner;
+				if (h.tri == kNoHit) { c->result = a.ambient; c->flags |= kNfDone; }     // :873-876
+				else { c->t = h.t; c->u = h.u; c->v = h.v; c->tri = h.tri; }
+				return;
+			}
+			const RayRec ray = a.rays[i];
+			const V3 ro = v3(ray.ox, ray.oy, ray.oz), rd = v3(ray.dx, ray.dy, ray.dz);
+			if (kind == kRkHemi)
+			{
+				const NodeRec* o = a.recs + owner;
+				SkyState s; s.att = v3(1.0f); s.targetAux = g; s.prev = ro; s.ignore = ray.ignoreTri; s.start = ro; s.ior = o->envIor; s.dir = rd;
+				s.jAndMax = 0u | ((o->bounces >> 16) << 16);
+				V3 att;
+				if (SkyAdvance(a, s, h, att)) SkyPush(a, 0, s);
+				else SkyFinish(a, g, att);
+				return;
+			}
+			// kRkSample (:786-833)
+			const V3 term = v3(x.a0, x.a1, x.a2);
+			if (h.tri == kNoHit)
+			{
+				const V3 value = glm_clamp(term * a.ambient, 0.0f, 10.0f);               // :788
+				x.a0 = value.x; x.a1 = value.y; x.a2 = value.z; x.tag |= kRsMiss;
+				a.aux[g] = x;
+				return;
+			}
+			const NodeRec* o = a.recs + owner;
+			const uint32_t bounceLimit = o->bounces & 0xFFFFu, pMaxBounces = o->bounces >> 16;
+			if (bounceLimit == 0) { a.aux[g].tag = x.tag | kRsHit0; return; }            // :797, :835
+			const uint32_t oflags = o->flags;
+			V3 att = v3(1.0f);
+			if ((oflags & kNfOpposite) && (x.tag & kRsTransRay) && (oflags & kNfThick))  // :801-807
+			{
+				const MaterialGpu& m = a.materials[MaterialOfTri(a, o->tri)];
+				const V3 hitPoint = o->rayO + o->rayD * o->t;
+				const V3 h2p = ro + rd * h.t;
+				const float distance = length(h2p - hitPoint);
+				const V3 c = v3(-logf(m.attenuationColor[0]), -logf(m.attenuationColor[1]), -logf(m.attenuationColor[2])) / m.attenuationDistance;
+				const V3 e = -c * distance;
+				att = v3(expf(e.x), expf(e.y), expf(e.z));
+			}
+			const V3 T = term * att;
+			const float newAcc = o->inAcc * length(T) * o->alpha;                        // :810
+			bool spawned = false;
+			if (newAcc > 0.01f)                                                           // :811-814
+			{
+				const uint32_t ci = AllocRecord(a);
+				if (ci != kNone)
 				{
-					const V3 value = glm_clamp(f->term * f->att * retVal, 0.0f, 10.0f);
-					f->indirect = f->indirect + value;
-					const MaterialGpu& hm = a.materials[MaterialOf(f->h2tri)];
-					if (!(f->flags & kFlThick) && hm.transmission > 0.0f && hm.thickness > 0.0f)
-					{
-						f->value = value;
-						StartSky(f->r2o, f->r2d, f->envIor, f->h2tri);
-						f->phase = kPhSkySample;
-						act = SkyStep;
-					}
-					else { f->cnt += 1.0f; f->loopI++; act = SampleNext; }
-					break;
+					NodeRec c;
+					c.rayO = ro; c.parent = owner; c.rayD = rd; c.parentAux = g;
+					c.t = h.t; c.u = h.u; c.v = h.v; c.tri = h.tri;
+					c.inAcc = newAcc; c.envIor = x.b0; c.bounces = (bounceLimit - 1u) | (pMaxBounces << 16); c.flags = 0;
+					c.rngKey = ChildRngKey(o->rngKey, g - o->auxBase); c.auxBase = 0; c.child = kNone;
+					c.pNumSamples = o->pNumSamples; c.pNumAmbient = o->pNumAmbient; c.nA = 0; c.nS = 0;
+					c.emissive = v3(0.0f); c.alpha = 1.0f; c.result = v3(0.0f); c.nLights = 0;
+					a.recs[ci] = c;
+					spawned = true;
 				}
-				case AmbientEnd:                                                        // :838-852
+			}
+			// a = term*att until the child's gather replaces it by clamp(term*att*L); without a child L = 0 (:809,:816)
+			V3 val = T;
+			if (!spawned) val = glm_clamp(T * v3(0.0f), 0.0f, 10.0f);
+			x.a0 = val.x; x.a1 = val.y; x.a2 = val.z; x.b0 = 0.0f; x.b1 = 0.0f; x.b2 = 0.0f; x.tag |= kRsHit;
+			a.aux[g] = x;
+			// :822-832 sky behind a thick transmissive surface, independent of the child
+			if (!(oflags & kNfThick))
+			{
+				const MaterialGpu& hm = a.materials[MaterialOfTri(a, h.tri)];
+				if (hm.transmission > 0.0f && hm.thickness > 0.0f && pMaxBounces > 0)
 				{
-					const float pdfHemisphere = 1.0f / (kPiSailor * 2.0f);
-					f->amb2 = f->amb2 / f->cnt; f->avgPdf = f->avgPdf / f->cnt;
-					const V3 ambient = f->amb1 + f->amb2;
-					if (ambient.x + ambient.y + ambient.z > 0.0f)
-					{
-						const V3 combined = f->amb1 * PowerHeuristic((int32_t)f->nA, pdfHemisphere, (int32_t)f->cnt, f->avgPdf) +
-							f->amb2 * PowerHeuristic((int32_t)f->cnt, f->avgPdf, (int32_t)f->nA, pdfHemisphere);
-						f->res = f->res + combined;
-					}
-					if (f->cnt > 0.0f) f->res = f->res + (f->indirect / f->cnt);
-					act = Finish;
-					break;
+					SkyState s; s.att = v3(1.0f); s.targetAux = g; s.prev = ro; s.ignore = h.tri; s.start = ro; s.ior = o->envIor; s.dir = rd;
+					s.jAndMax = 0u | (pMaxBounces << 16);
+					SkyPush(a, 0, s);
 				}
-				case Finish:                                                            // :855-871
-				{
-					f->res = f->res + f->emissive;
-					if (f->bounceLimit > 0 && (f->flags & kFlAlpha))
-					{
-						Frame* parent = f;
-						parent->phase = kPhChildAlpha;
-						hd.depth++;
-						f = FrameAt(hd.depth);
-						f->rayD = parent->rayD; f->rayO = parent->hitPoint + parent->rayD * 0.0001f;
-						f->ignoreTri = parent->hitTri; f->bounceLimit = parent->bounceLimit - 1;
-						f->inAcc = parent->inAcc * (1.0f - parent->baseColor.w); f->envIor = parent->envIor;
-						const uint32_t mb = parent->pMaxBounces - 1u, nsm = parent->pNumSamples - parent->S, nam = parent->pNumAmbient - parent->A;
-						f->pMaxBounces = mb;                       // std::max(0u, x) is x
-						f->pNumSamples = nsm > 1u ? nsm : 1u; f->pNumAmbient = nam > 1u ? nam : 1u;
-						BeginCall();
-						Emit(f->rayO, f->rayD, f->ignoreTri);
-						act = Done;
-					}
-					else { retVal = f->res; act = Return; }
-					break;
-				}
-				case AfterChildAlpha:                                                   // :868-870
-				{
-					const float al = f->baseColor.w;
-					f->res = f->res * al + retVal * (1.0f - al);
-					retVal = f->res;
-					act = Return;
-					break;
-				}
-				case Return:
-				{
-					if (hd.depth == 0)
-					{
-						// accumulator += Raytrace(...) (:466): one slot per (pixel, sample); summed in order by ResolveKernel
-						const uint32_t x = hd.pixel % a.cam.width, y = hd.pixel / a.cam.width;
-						const size_t idx = ((size_t)(y - a.rowBegin) * a.cam.width + x) * (a.msEnd - a.msBegin) + (hd.sample - a.msBegin);
-						a.sampleBuf[idx * 3] = retVal.x; a.sampleBuf[idx * 3 + 1] = retVal.y; a.sampleBuf[idx * 3 + 2] = retVal.z;
-						hd.active = 0;
-						act = Done;
-					}
-					else
-					{
-						hd.depth--;
-						f = FrameAt(hd.depth);
-						act = f->phase == kPhChildAlpha ? AfterChildAlpha : AfterChildSample;
-					}
-					break;
-				}
-				case Done:
-					return;
-				}
-				if (act == Done) return;
 			}
 		}
 	};
 
-	// One thread per pool slot: resume with the hit of the pending ray, refill finished slots from the hit queue.
-	struct AdvanceKernel
+	// ---- sky: one TraceSky iteration for every walk in flight ------------------------------------------------------
+	struct SkyKernel
 	{
-		IntegratorArgs a; uint32_t firstIteration;
-		SPT_KERNEL_BODY void operator()(uint32_t slot) const
+		IntegratorArgs a; uint32_t q;            // states in sky[q], survivors go to sky[q^1]
+		SPT_KERNEL_BODY void operator()(uint32_t i) const
 		{
-			PathMachine pm(a, slot);
-			pm.hd = a.headers[slot];
-			if (firstIteration) { pm.hd.active = 0; pm.hd.depth = 0; }
-			else if (pm.hd.active == 0) return;                               // idle for good: queue was exhausted when it finished
-			if (pm.hd.active == 1)
-			{
-				pm.rng.key = pm.hd.rngKey; pm.rng.counter = pm.hd.rngCounter;
-				pm.f = pm.FrameAt(pm.hd.depth);
-				const Hit hit = a.hits[slot];
-				pm.Advance(hit);
-			}
-			// refill: a finished (or never started) slot pulls primary samples until one produces a ray
-			while (!pm.rayEmitted)
-			{
-				if (!pm.NextFromQueue()) { pm.hd.active = 0; break; }
-			}
-			if (pm.rayEmitted)
-			{
-				atomic_add_u32(a.activeCount, 1u);
-				atomic_add_u64(a.rayCount, 1ull);
-			}
+			SkyState s = a.sky[q][i];
+			const Hit h = a.skyHits[i];
+			V3 att;
+			if (SkyAdvance(a, s, h, att)) SkyPush(a, q ^ 1u, s);
+			else SkyFinish(a, s.targetAux, att);
+		}
+	};
+
+	// ---- gather: replay :690-871 over one activation's rays, bottom-up ----------------------------------------------
+	struct GatherKernel
+	{
+		IntegratorArgs a;
+		SPT_KERNEL_BODY void operator()(uint32_t ri) const
+		{
+			NodeRec* rec = a.recs + ri;
+			const uint32_t flags = rec->flags;
+			V3 res;
+			if (flags & kNfDone) res = rec->result;
+			else if (flags & kNfTail) res = rec->child != kNone ? a.recs[rec->child].result : v3(0.0f);
 			else
 			{
-				RayRec r; r.ox = r.oy = r.oz = 0.0f; r.ignoreTri = kNoHit; r.dx = r.dy = r.dz = 0.0f; r.tmax = -1.0f;   // idle marker
-				a.rays[slot] = r;
+				res = v3(0.0f);
+				uint32_t g = rec->auxBase;
+				const uint32_t nLights = rec->nLights, nA = rec->nA, nS = rec->nS;
+				bool blocked = false;                                                     // stale hitLight (:694)
+				for (uint32_t j = 0; j < nLights; j++, g++)
+				{
+					const RayAux x = a.aux[g];
+					if (x.tag & kRsBlocked) blocked = true;
+					if (!blocked) res = res + v3(x.a0, x.a1, x.a2);
+				}
+				if (flags & kNfAmbientOn)
+				{
+					const float pdfHemisphere = 1.0f / (kPiSailor * 2.0f);
+					V3 amb1 = v3(0.0f);
+					if (!(flags & kNfThick))
+					{
+						for (uint32_t k = 0; k < nA; k++, g++)
+						{
+							const RayAux x = a.aux[g];
+							if ((x.tag & kRkMask) == kRkHemi) amb1 = amb1 + v3(x.a0, x.a1, x.a2);
+						}
+					}
+					amb1 = amb1 / (float)nA;                                              // :739
+					V3 amb2 = v3(0.0f), indirect = v3(0.0f); float avgPdf = 0.0f, cnt = 0.0f;
+					for (uint32_t i = 0; i < nS; i++, g++)
+					{
+						const RayAux x = a.aux[g];
+						if (x.tag & kRsSkipped) continue;
+						const V3 value = v3(x.a0, x.a1, x.a2);
+						if (x.tag & kRsMiss) { amb2 = amb2 + value; avgPdf += x.a3; indirect = indirect + value; }         // :786-796
+						else if (x.tag & kRsHit)                                                                          // :816-832
+						{
+							indirect = indirect + value;
+							if (x.tag & kRsSky2) { amb2 = amb2 + value * v3(x.b0, x.b1, x.b2); avgPdf += x.a3; }
+						}
+						cnt += 1.0f;                                                                                      // :835
+					}
+					amb2 = amb2 / cnt; avgPdf = avgPdf / cnt;                             // :838-839
+					const V3 ambient = amb1 + amb2;
+					if (ambient.x + ambient.y + ambient.z > 0.0f)
+					{
+						res = res + (amb1 * PowerHeuristic((int32_t)nA, pdfHemisphere, (int32_t)cnt, avgPdf) +
+							amb2 * PowerHeuristic((int32_t)cnt, avgPdf, (int32_t)nA, pdfHemisphere));
+					}
+					if (cnt > 0.0f) res = res + (indirect / cnt);
+				}
+				res = res + rec->emissive;                                                // :855
+				if ((rec->bounces & 0xFFFFu) > 0 && (flags & kNfAlpha))                   // :858-871
+				{
+					const float al = rec->alpha;
+					const V3 cr = rec->child != kNone ? a.recs[rec->child].result : v3(0.0f);
+					res = res * al + cr * (1.0f - al);
+				}
 			}
-			pm.hd.rngCounter = pm.rng.counter;
-			a.headers[slot] = pm.hd;
+			rec->result = res;
+			if (flags & kNfLevel0)
+			{
+				// accumulator += Raytrace(...) (:466): one slot per (pixel, sample); summed in order by ResolveKernel
+				const uint32_t pixel = rec->parent, sample = rec->parentAux;
+				const uint32_t x = pixel % a.cam.width, y = pixel / a.cam.width;
+				const size_t idx = ((size_t)(y - a.rowBegin) * a.cam.width + x) * (a.msEnd - a.msBegin) + (sample - a.msBegin);
+				a.sampleBuf[idx * 3] = res.x; a.sampleBuf[idx * 3 + 1] = res.y; a.sampleBuf[idx * 3 + 2] = res.z;
+			}
+			else if (rec->parentAux != kNone)
+			{
+				RayAux* px = a.aux + rec->parentAux;                                      // :816  value = clamp(term*att*raytraced)
+				const V3 value = glm_clamp(v3(px->a0, px->a1, px->a2) * res, 0.0f, 10.0f);
+				px->a0 = value.x; px->a1 = value.y; px->a2 = value.z;
+			}
 		}
+	};
+
+	// ---- level bookkeeping (one thread) -----------------------------------------------------------------------------
+	struct BeginBatchKernel      // level 0 = the seeded first hits
+	{
+		BatchCounters* c; uint32_t count;
+		SPT_KERNEL_BODY void operator()(uint32_t) const
+		{
+			c->recAlloc = count; c->auxAlloc = 0; c->overflow = 0; c->skyCount[0] = c->skyCount[1] = 0; c->zero = 0; c->rays = 0;
+			c->level[0].recBegin = 0; c->level[0].recEnd = count; c->level[0].rayCount = 0; c->level[0].auxBase = 0;
+		}
+	};
+	struct NextLevelKernel       // after classify(level): the records allocated since are level+1
+	{
+		BatchCounters* c; uint32_t level; uint32_t recCap;
+		SPT_KERNEL_BODY void operator()(uint32_t) const
+		{
+			const LevelInfo cur = c->level[level];
+			LevelInfo nx; nx.recBegin = cur.recEnd; nx.recEnd = c->recAlloc < recCap ? c->recAlloc : recCap; nx.rayCount = 0; nx.auxBase = cur.auxBase + cur.rayCount;
+			c->level[level + 1] = nx;
+			c->auxAlloc = nx.auxBase;
+			c->rays += cur.rayCount;
+		}
+	};
+	struct SkySwapKernel         // after a sky iteration: queue q is consumed
+	{
+		BatchCounters* c; uint32_t q;
+		SPT_KERNEL_BODY void operator()(uint32_t) const { c->rays += c->skyCount[q]; c->skyCount[q] = 0; }
 	};
 
 	// accumulator / msaa with the row flip of PathTracer.cpp:449,468-469
@@ -635,5 +721,4 @@ namespace spt
 			image[o] = res.x; image[o + 1] = res.y; image[o + 2] = res.z;
 		}
 	};
-
 }

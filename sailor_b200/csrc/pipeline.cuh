@@ -46,9 +46,11 @@ namespace spt
 		// results of the last RenderResident (stay on the device until read back or handed to NCCL)
 		DevBuf<float> residentLin; DevBuf<uint8_t> residentSrgb; uint32_t residentW = 0, residentH = 0;
 
-		// wavefront working set, kept across renders (only ever grows): 0 headers, 1 frames, 2 rays, 3 hits,
-		// 4 per-sample results, 5 primary-hit queue, 6 counters, 7 blue-noise table
-		DevBuf<unsigned char> renderMem[8];
+		// wavefront working set, kept across renders (only ever grows): 0 activation records, 1 RayAux arena, 2 rays,
+		// 3 hits, 4 per-sample results, 5 primary-hit queue, 6 batch counters, 7 blue-noise table, 8 RayAux owners,
+		// 9 sky states, 10 sky rays, 11 sky hits
+		DevBuf<unsigned char> renderMem[12];
+		SpanTimer traceTimer;
 		// BVH build scratch, kept across builds
 		DevBuf<uint32_t> buildU32[24];
 		DevBuf<float> buildF32[4];

@@ -3,9 +3,10 @@
 //   primary pass   one fused kernel: camera ray generation + closest hit for EVERY (pixel, primary sample) of the
 //                  shard.  Misses are final (Raytrace returns the ambient colour, :873-876) and are written straight
 //                  to the per-sample buffer; hits are appended to a compact first-hit queue (warp-aggregated atomics).
-//   wavefront      pool slots pull first hits from the queue and run the Raytrace state machine (integrator.cuh):
-//                  [trace kernel, advance kernel] per iteration, launched in chunks without host synchronisation;
-//                  the host only reads one 4-byte "slots still active" word per chunk.
+//   wavefront      the first hits are processed in batches; a batch evaluates the reference's recursion tree level by
+//                  level (integrator.cuh): [expand, trace, classify, (sky), next-level] per level, then gather bottom-up.
+//                  Level sizes live in device memory, so a whole batch is queued without host synchronisation; the
+//                  host reads one small word (overflow flag + ray count) per batch.
 //   resolve        accumulator = sum over the pixel's primary samples in index order / msaa, row flip (:449,468-469).
 //
 // All working buffers live with the scene and are reused across frames (no allocation in the steady state).
@@ -109,17 +110,48 @@ namespace spt
 	}
 #endif
 
-	inline uint32_t PoolLimit()
-	{
-		long pool = 1l << 21;                                   // 2 Mi resident paths (~14k per SM): hides DRAM latency, bounds memory
-		if (const char* e = getenv("SAILOR_PT_POOL")) { const long v = atol(e); if (v > 0) pool = v; }
-		return (uint32_t)pool;
-	}
-
 	template<class T> inline T* EnsureBytes(Ctx& ctx, DevBuf<unsigned char>& b, size_t count)
 	{
 		b.Ensure(ctx, count * sizeof(T) + 16);
 		return reinterpret_cast<T*>(b.p);
+	}
+
+	// Arena sizes of one batch of first hits.  Per first hit: level 0 needs D+A+S+1 rays; every importance sample can spawn
+	// one child activation with D+2 (+1 alpha) rays; deeper levels shrink (misses, the 0.01 throughput cut), which is
+	// budgeted as `kDepthFactor` levels' worth of the level-1 worst case.  Running out is detected on the device
+	// (BatchCounters::overflow) and the batch is redone at half the size, so the factors only affect speed.
+	struct BatchPlan { uint32_t firstHits, rayCap, auxCap, recCap, skyCap; };
+
+	inline BatchPlan PlanBatch(uint64_t hitCount, uint32_t D, uint32_t A, uint32_t S, uint32_t maxBounces, bool ambientOn, uint32_t shrink)
+	{
+		const uint64_t kDepthFactor = maxBounces < 3u ? maxBounces : 3u;
+		if (!ambientOn) { A = 0; S = 0; }
+		const uint64_t lvl0 = (uint64_t)D + A + S + 1u, lvl1 = (uint64_t)S * (D + 3u) + 1u;
+		const uint64_t raysPer = lvl0 > lvl1 ? lvl0 : lvl1;
+		const uint64_t auxPer = lvl0 + kDepthFactor * lvl1;
+		const uint64_t recPer = 2u + kDepthFactor * S;
+		const uint64_t bytesPer = raysPer * (sizeof(RayRec) + sizeof(Hit)) + auxPer * (sizeof(RayAux) + 4u) + recPer * sizeof(NodeRec);
+		uint64_t budget = 6144ull << 20;
+		if (const char* e = getenv("SAILOR_PT_BATCH_MB")) { const long v = atol(e); if (v > 0) budget = (uint64_t)v << 20; }
+		uint64_t B = budget / bytesPer;
+		B >>= shrink;
+		if (B < 1024u) B = 1024u;
+		if (B > hitCount) B = hitCount;
+		const uint64_t cap32 = 0xFFFF0000ull;
+		while (B > 1u && (B * auxPer >= cap32 || B * recPer >= cap32)) B >>= 1;
+		BatchPlan p;
+		p.firstHits = (uint32_t)B;
+		p.rayCap = (uint32_t)(B * raysPer + 1024u);
+		p.auxCap = (uint32_t)(B * auxPer + 1024u);
+		p.recCap = (uint32_t)(B * recPer + 1024u);
+		p.skyCap = (uint32_t)((B * raysPer) / 4u + 65536u);
+		return p;
+	}
+
+	inline bool SceneHasThickTransmission(const HostScene& h)
+	{
+		for (const auto& m : h.materials) if (m.transmission > 0.0f && m.thickness > 0.0f) return true;
+		return false;
 	}
 
 	inline int RenderFrame(SceneDevice& D, const CameraGpu& cam, const SailorPtParams& p, float* dImage, RenderStats& rs)
@@ -128,90 +160,115 @@ namespace spt
 		const uint32_t rowBegin = p.rowEnd ? p.rowBegin : 0u, rowEnd = p.rowEnd ? (p.rowEnd < cam.height ? p.rowEnd : cam.height) : cam.height;
 		const uint32_t msBegin = p.msaaEnd ? p.msaaBegin : 0u, msEnd = p.msaaEnd ? (p.msaaEnd < p.msaa ? p.msaaEnd : p.msaa) : p.msaa;
 		if (rowBegin >= rowEnd || msBegin >= msEnd) { ctx.error = "empty shard"; return SAILOR_PT_ERR_ARG; }
+		if (p.maxBounces > 64u) { ctx.error = "maxBounces > 64 is not supported"; return SAILOR_PT_ERR_LIMIT; }
 		const uint32_t rows = rowEnd - rowBegin, ns = msEnd - msBegin;
 		const uint64_t tiles = (uint64_t)((cam.width + 7u) / 8u) * ((rows + 3u) / 4u);
 		const uint64_t total = tiles * ns * 32ull;
 		const uint64_t realSamples = (uint64_t)rows * cam.width * ns;
 		if (total >= 0xFFFFFF00ull) { ctx.error = "shard too large for one launch: split rows or samples"; return SAILOR_PT_ERR_LIMIT; }
-		const uint32_t maxDepth = p.maxBounces + 1u;
 
 		float* sampleBuf = EnsureBytes<float>(ctx, D.renderMem[4], (size_t)realSamples * 3);
 		PrimaryHitRec* queue = EnsureBytes<PrimaryHitRec>(ctx, D.renderMem[5], (size_t)realSamples);
-		uint32_t* counters = EnsureBytes<uint32_t>(ctx, D.renderMem[6], 64);
-		unsigned long long* counters64 = reinterpret_cast<unsigned long long*>(counters + 32);
+		BatchCounters* counters = EnsureBytes<BatchCounters>(ctx, D.renderMem[6], 1);
 		if (D.renderMem[7].n == 0) { uint16_t* b = EnsureBytes<uint16_t>(ctx, D.renderMem[7], kBlueNoiseCount); DevUpload(ctx, b, kBlueNoiseK, sizeof(kBlueNoiseK)); }
 		const uint16_t* blue = reinterpret_cast<const uint16_t*>(D.renderMem[7].p);
+		uint32_t* hitCounter = D.counter.p + 2;
 		if (!ctx.ok) return SAILOR_PT_ERR_CUDA;
-		DevMemset(ctx, counters, 0, 64 * sizeof(uint32_t));
+		DevMemset(ctx, hitCounter, 0, sizeof(uint32_t));
 
 		rs = RenderStats{};
 		const BvhView view = D.View();
+		SpanTimer& tt = D.traceTimer;
 
+		ctx.Mark(0);
 		// ---- primary pass ----
 		PrimaryArgs pa;
 		pa.bvh = view; pa.cam = cam; pa.rowBegin = rowBegin; pa.rowEnd = rowEnd; pa.msBegin = msBegin; pa.msEnd = msEnd; pa.msaa = p.msaa; pa.seed = p.seed;
-		pa.ambient = v3(p.ambient[0], p.ambient[1], p.ambient[2]); pa.sampleBuf = sampleBuf; pa.queue = queue; pa.hitCount = counters + 2; pa.total = (uint32_t)total;
-		ctx.Mark(0);
+		pa.ambient = v3(p.ambient[0], p.ambient[1], p.ambient[2]); pa.sampleBuf = sampleBuf; pa.queue = queue; pa.hitCount = hitCounter; pa.total = (uint32_t)total;
+		tt.Begin(ctx);
 		LaunchPrimaryPass(ctx, pa, D.counter.p);
-		ctx.Mark(1);
+		tt.End(ctx);
 		uint32_t hitCount = 0;
-		DevDownload(ctx, &hitCount, counters + 2, 4);
-		rs.secondsTraverse += ctx.Between(0, 1); rs.traverseLaunches++;
+		DevDownload(ctx, &hitCount, hitCounter, 4);
 		rs.rays = realSamples; rs.primarySamples = realSamples;
 
 		if (hitCount && ctx.ok)
 		{
-			uint32_t pool = PoolLimit();
-			if (pool > hitCount) pool = hitCount;
-			pool = (pool + 255u) & ~255u;
-			PathHeader* headers = EnsureBytes<PathHeader>(ctx, D.renderMem[0], pool);
-			Frame* frames = EnsureBytes<Frame>(ctx, D.renderMem[1], (size_t)pool * maxDepth);
-			RayRec* rays = EnsureBytes<RayRec>(ctx, D.renderMem[2], pool);
-			Hit* hits = EnsureBytes<Hit>(ctx, D.renderMem[3], pool);
-			if (!ctx.ok) return SAILOR_PT_ERR_CUDA;
-
-			IntegratorArgs a;
-			a.shade = D.shade.p; a.centroid = D.centroid.p; a.materials = D.materials.p; a.tex.texels = D.texels.p; a.tex.textures = D.textures.p;
-			a.lights = D.lights.p; a.numLights = (uint32_t)D.host.lights.size(); a.blueNoise = blue;
-			a.cam = cam; a.rowBegin = rowBegin; a.rowEnd = rowEnd; a.msBegin = msBegin; a.msEnd = msEnd; a.msaa = p.msaa;
-			a.maxBounces = p.maxBounces; a.numSamples = p.numSamples; a.numAmbientSamples = p.numAmbientSamples;
-			a.ambient = pa.ambient; a.seed = p.seed;
-			a.poolSize = pool; a.maxDepth = maxDepth;
-			a.headers = headers; a.frames = frames; a.rays = rays; a.hits = hits; a.sampleBuf = sampleBuf;
-			a.hitQueue = queue; a.queueCount = hitCount; a.nextSample = counters; a.rayCount = counters64;
-			uint32_t* activeSlots = counters + 8;                        // one word per iteration of a chunk
-			a.activeCount = activeSlots;
-
-			uint32_t active = 0;
-			launch_for(ctx, pool, AdvanceKernel{ a, 1u });                // fill the pool from the first-hit queue
-			DevDownload(ctx, &active, activeSlots, 4);
-			const int kChunk = 16;                                       // iterations launched between two host reads
-			while (active && ctx.ok)
+			const uint32_t numLights = (uint32_t)D.host.lights.size();
+			const bool ambientOn = pa.ambient.x + pa.ambient.y + pa.ambient.z > 0.0f;
+			const bool hasSky = ambientOn && SceneHasThickTransmission(D.host);
+			const uint32_t levels = p.maxBounces + 1u;
+			uint32_t shrink = 0;
+			uint32_t done = 0;
+			while (done < hitCount && ctx.ok)
 			{
-				DevMemset(ctx, activeSlots, 0, kChunk * sizeof(uint32_t));
-				for (int k = 0; k < kChunk; k++)
+				const BatchPlan plan = PlanBatch(hitCount - done, numLights, p.numAmbientSamples, p.numSamples, p.maxBounces, ambientOn, shrink);
+				IntegratorArgs a;
+				a.shade = D.shade.p; a.centroid = D.centroid.p; a.materials = D.materials.p; a.tex.texels = D.texels.p; a.tex.textures = D.textures.p;
+				a.lights = D.lights.p; a.numLights = numLights; a.blueNoise = blue;
+				a.cam = cam; a.rowBegin = rowBegin; a.rowEnd = rowEnd; a.msBegin = msBegin; a.msEnd = msEnd; a.msaa = p.msaa;
+				a.maxBounces = p.maxBounces; a.numSamples = p.numSamples; a.numAmbientSamples = p.numAmbientSamples;
+				a.ambient = pa.ambient; a.seed = p.seed;
+				a.hitQueue = queue; a.queueBegin = done; a.queueCount = plan.firstHits;
+				a.recs = EnsureBytes<NodeRec>(ctx, D.renderMem[0], plan.recCap); a.recCap = plan.recCap;
+				a.aux = EnsureBytes<RayAux>(ctx, D.renderMem[1], plan.auxCap); a.auxOwner = EnsureBytes<uint32_t>(ctx, D.renderMem[8], plan.auxCap); a.auxCap = plan.auxCap;
+				a.rays = EnsureBytes<RayRec>(ctx, D.renderMem[2], plan.rayCap); a.hits = EnsureBytes<Hit>(ctx, D.renderMem[3], plan.rayCap); a.rayCap = plan.rayCap;
+				a.skyCap = hasSky ? plan.skyCap : 16u;
+				a.sky[0] = EnsureBytes<SkyState>(ctx, D.renderMem[9], (size_t)a.skyCap * 2); a.sky[1] = a.sky[0] + a.skyCap;
+				a.skyRays = EnsureBytes<RayRec>(ctx, D.renderMem[10], (size_t)a.skyCap * 2); a.skyHits = EnsureBytes<Hit>(ctx, D.renderMem[11], a.skyCap);
+				a.c = counters; a.sampleBuf = sampleBuf;
+				if (!ctx.ok) return SAILOR_PT_ERR_CUDA;
+
+				launch_for(ctx, 1, BeginBatchKernel{ counters, plan.firstHits });
+				launch_for(ctx, plan.firstHits, SeedKernel{ a });
+				for (uint32_t level = 0; level < levels; level++)
 				{
-					ctx.Mark(3 * k);
-					LaunchTraceRays(ctx, view, rays, hits, pool, D.counter.p);
-					ctx.Mark(3 * k + 1);
-					a.activeCount = activeSlots + k;
-					launch_for(ctx, pool, AdvanceKernel{ a, 0u });
-					ctx.Mark(3 * k + 2);
+					const LevelInfo* L = &counters->level[level];
+					// upper bounds for the grid: level 0 is exact, deeper levels are bounded by the arenas
+					const uint32_t maxRecs = level == 0 ? plan.firstHits : plan.recCap;
+					launch_for_range(ctx, &L->recBegin, &L->recEnd, plan.recCap, maxRecs, ExpandKernel{ a, level });
+					tt.Begin(ctx);
+					LaunchTraceRays(ctx, view, a.rays, a.hits, plan.rayCap, D.counter.p, &L->rayCount);
+					tt.End(ctx);
+					launch_for_range(ctx, &counters->zero, &L->rayCount, plan.rayCap, plan.rayCap, ClassifyKernel{ a, level });
+					if (hasSky)
+					{
+						uint32_t q = 0;
+						for (uint32_t it = 0; it < p.maxBounces; it++, q ^= 1u)     // a TraceSky walk traces at most maxBounces rays (:581)
+						{
+							tt.Begin(ctx);
+							LaunchTraceRays(ctx, view, a.skyRays + (q ? a.skyCap : 0u), a.skyHits, a.skyCap, D.counter.p, &counters->skyCount[q]);
+							tt.End(ctx);
+							launch_for_range(ctx, &counters->zero, &counters->skyCount[q], a.skyCap, a.skyCap, SkyKernel{ a, q });
+							launch_for(ctx, 1, SkySwapKernel{ counters, q });
+						}
+					}
+					launch_for(ctx, 1, NextLevelKernel{ counters, level, plan.recCap });
 				}
-				uint32_t act[kChunk];
-				DevDownload(ctx, act, activeSlots, sizeof(act));          // synchronises
-				for (int k = 0; k < kChunk; k++)
+				for (uint32_t level = levels; level-- > 0;)
 				{
-					rs.secondsTraverse += ctx.Between(3 * k, 3 * k + 1); rs.secondsShade += ctx.Between(3 * k + 1, 3 * k + 2);
-					if (k == 0 || act[k - 1]) rs.traverseLaunches++;        // launches past the end of the frame are empty
+					const LevelInfo* L = &counters->level[level];
+					launch_for_range(ctx, &L->recBegin, &L->recEnd, plan.recCap, level == 0 ? plan.firstHits : plan.recCap, GatherKernel{ a });
 				}
-				active = act[kChunk - 1];
+				struct { uint32_t recAlloc, auxAlloc, overflow, sky0, sky1, zero, pad0, pad1; unsigned long long rays; } head;
+				DevDownload(ctx, &head, counters, sizeof(head));          // synchronises
+				if (!ctx.ok) break;
+				if (head.overflow)
+				{
+					if (plan.firstHits <= 1024u || shrink > 16u) { ctx.error = "wavefront arenas overflow even for the smallest batch"; return SAILOR_PT_ERR_LIMIT; }
+					shrink++;
+					continue;                                                // redo this batch smaller (results are keyed per activation, not per batch)
+				}
+				rs.rays += head.rays;
+				done += plan.firstHits;
 			}
-			unsigned long long c64 = 0;
-			DevDownload(ctx, &c64, counters64, sizeof(c64));
-			rs.rays += c64;
 		}
 		launch_for(ctx, rows * cam.width, ResolveKernel{ sampleBuf, dImage, cam.width, cam.height, rowBegin, rowEnd, ns, p.msaa });
+		ctx.Mark(1);
+		ctx.Sync();
+		rs.traverseLaunches = tt.Spans();
+		rs.secondsTraverse = tt.Collect(ctx);
+		rs.secondsShade = ctx.Between(0, 1) - rs.secondsTraverse;      // everything of the frame that is not a trace launch
 		return ctx.ok ? SAILOR_PT_OK : SAILOR_PT_ERR_CUDA;
 	}
 }

@@ -28,9 +28,11 @@ namespace spt
 
 	__device__ __forceinline__ V4 ldg4(const V4* p) { const float4 f = __ldg(reinterpret_cast<const float4*>(p)); return v4(f.x, f.y, f.z, f.w); }
 
+	// nPtr (optional): the queue length lives in device memory (wavefront levels); n is then its capacity
 	__global__ void __launch_bounds__(kTraceBlock) k_trace_rays(BvhView bvh, const RayRec* __restrict__ rays, Hit* __restrict__ hits,
-		uint32_t n, uint32_t* __restrict__ counter)
+		uint32_t n, const uint32_t* __restrict__ nPtr, uint32_t* __restrict__ counter)
 	{
+		if (nPtr) { const uint32_t m = *nPtr; if (m < n) n = m; }
 		__shared__ uint32_t stackMem[kStackDepth * kTraceBlock];
 		SmemStack stack; stack.base = stackMem + threadIdx.x; stack.n = 0;
 		const uint32_t lane = threadIdx.x & 31;
@@ -95,11 +97,11 @@ namespace spt
 		return grid;
 	}
 
-	inline void LaunchTraceRays(Ctx& ctx, const BvhView& bvh, const RayRec* rays, Hit* hits, uint32_t n, uint32_t* counter)
+	inline void LaunchTraceRays(Ctx& ctx, const BvhView& bvh, const RayRec* rays, Hit* hits, uint32_t n, uint32_t* counter, const uint32_t* nPtr = nullptr)
 	{
 		if (!n || !ctx.ok) return;
 		DevMemset(ctx, counter, 0, sizeof(uint32_t));
-		k_trace_rays<<<TraceGridSize(), kTraceBlock, 0, ctx.stream>>>(bvh, rays, hits, n, counter);
+		k_trace_rays<<<TraceGridSize(), kTraceBlock, 0, ctx.stream>>>(bvh, rays, hits, n, nPtr, counter);
 		ctx.kernelLaunches++;
 		SPT_CUDA_CHECK(ctx, cudaGetLastError());
 	}
@@ -113,9 +115,10 @@ namespace spt
 		SPT_CUDA_CHECK(ctx, cudaGetLastError());
 	}
 #else
-	inline void LaunchTraceRays(Ctx& ctx, const BvhView& bvh, const RayRec* rays, Hit* hits, uint32_t n, uint32_t*)
+	inline void LaunchTraceRays(Ctx& ctx, const BvhView& bvh, const RayRec* rays, Hit* hits, uint32_t n, uint32_t*, const uint32_t* nPtr = nullptr)
 	{
 		LocalStack st;
+		if (nPtr && *nPtr < n) n = *nPtr;
 		for (uint32_t i = 0; i < n; i++)
 			if (!(rays[i].tmax < 0.0f)) TraceClosest(bvh, v3(rays[i].ox, rays[i].oy, rays[i].oz), v3(rays[i].dx, rays[i].dy, rays[i].dz), rays[i].ignoreTri, rays[i].tmax, st, hits[i]);
 		ctx.kernelLaunches++;
