@@ -3,6 +3,8 @@
 #include "../../include/sailor_pt.h"
 #include <chrono>
 #include <stdio.h>
+#include <mutex>
+#include <unordered_map>
 
 namespace spt
 {
@@ -75,19 +77,111 @@ namespace spt
 		return (double)ms * 1e-3;
 	}
 
+	// Device memory comes from CUDA's stream-ordered pool (cudaMallocAsync) with the release threshold lifted, so a
+	// host that renders frame after frame (one scene object per call, like the reference's PathTracer object per Run)
+	// reuses the same HBM instead of paying cudaMalloc/cudaFree of multi-GB arenas every call.  A buffer is freed on
+	// the stream it was allocated on (kept in a small registry), which orders the free after the work that used it.
+	namespace
+	{
+		std::mutex g_allocMutex;
+		std::unordered_map<void*, cudaStream_t> g_allocStream;
+		bool g_poolReady = false;
+
+		void EnsurePool()
+		{
+			if (g_poolReady) return;
+			int dev = 0; cudaMemPool_t pool = nullptr;
+			if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
+			{
+				uint64_t threshold = UINT64_MAX;
+				cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+			}
+			cudaGetLastError();
+			g_poolReady = true;
+		}
+	}
+
 	void* DevAllocBytes(Ctx& ctx, size_t bytes)
 	{
 		void* p = nullptr;
 		if (!ctx.ok) return nullptr;
-		SPT_CUDA_CHECK(ctx, cudaMalloc(&p, bytes));
-		return ctx.ok ? p : nullptr;
+		std::lock_guard<std::mutex> lock(g_allocMutex);
+		EnsurePool();
+		SPT_CUDA_CHECK(ctx, cudaMallocAsync(&p, bytes, ctx.stream));
+		if (!ctx.ok) return nullptr;
+		g_allocStream[p] = ctx.stream;
+		return p;
 	}
-	void DevFreeBytes(void* p) { cudaFree(p); }
+	void DevFreeBytes(void* p)
+	{
+		if (!p) return;
+		cudaStream_t st = nullptr; bool known = false;
+		{
+			std::lock_guard<std::mutex> lock(g_allocMutex);
+			auto it = g_allocStream.find(p);
+			if (it != g_allocStream.end()) { st = it->second; known = true; g_allocStream.erase(it); }
+		}
+		if (known) { if (cudaFreeAsync(p, st) != cudaSuccess) { cudaGetLastError(); cudaFree(p); } }
+		else cudaFree(p);
+	}
 	void DevUpload(Ctx& ctx, void* dst, const void* src, size_t bytes) { ctx.h2dBytes += bytes; if (ctx.ok) SPT_CUDA_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx.stream)); }
+	// Large device->host reads go through two pinned staging chunks: the DMA of chunk k overlaps the host memcpy of
+	// chunk k-1 into the caller's (pageable) buffer.  Small reads use the plain path.
+	namespace
+	{
+		constexpr size_t kStageChunk = 8u << 20;
+		std::mutex g_stageMutex;
+		unsigned char* g_stage[2] = { nullptr, nullptr };
+		cudaEvent_t g_stageEv[2] = { nullptr, nullptr };
+
+		bool EnsureStage()
+		{
+			if (g_stage[0]) return true;
+			for (int k = 0; k < 2; k++)
+			{
+				if (cudaHostAlloc((void**)&g_stage[k], kStageChunk, cudaHostAllocDefault) != cudaSuccess || cudaEventCreateWithFlags(&g_stageEv[k], cudaEventDisableTiming) != cudaSuccess)
+				{
+					cudaGetLastError();
+					for (int j = 0; j < 2; j++) { if (g_stage[j]) cudaFreeHost(g_stage[j]); g_stage[j] = nullptr; }
+					return false;
+				}
+			}
+			return true;
+		}
+	}
+
 	void DevDownload(Ctx& ctx, void* dst, const void* src, size_t bytes)
 	{
 		if (!ctx.ok) return;
 		ctx.d2hBytes += bytes;
+		if (bytes >= (1u << 20))
+		{
+			std::lock_guard<std::mutex> lock(g_stageMutex);
+			if (EnsureStage())
+			{
+				size_t prevOff = 0, prevN = 0; int prevK = -1;
+				int k = 0;
+				for (size_t off = 0; off < bytes && ctx.ok; off += kStageChunk, k ^= 1)
+				{
+					const size_t n = bytes - off < kStageChunk ? bytes - off : kStageChunk;
+					SPT_CUDA_CHECK(ctx, cudaMemcpyAsync(g_stage[k], (const unsigned char*)src + off, n, cudaMemcpyDeviceToHost, ctx.stream));
+					SPT_CUDA_CHECK(ctx, cudaEventRecord(g_stageEv[k], ctx.stream));
+					if (prevK >= 0)
+					{
+						SPT_CUDA_CHECK(ctx, cudaEventSynchronize(g_stageEv[prevK]));
+						memcpy((unsigned char*)dst + prevOff, g_stage[prevK], prevN);
+					}
+					prevOff = off; prevN = n; prevK = k;
+				}
+				if (prevK >= 0 && ctx.ok)
+				{
+					SPT_CUDA_CHECK(ctx, cudaEventSynchronize(g_stageEv[prevK]));
+					memcpy((unsigned char*)dst + prevOff, g_stage[prevK], prevN);
+				}
+				SPT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx.stream));
+				return;
+			}
+		}
 		SPT_CUDA_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx.stream));
 		SPT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx.stream));
 	}

@@ -165,6 +165,141 @@ namespace spt
 		}
 	};
 
+#if !defined(SPT_EMU)
+	// ---- device forms of BoundsKernel / BinKernel --------------------------------------------------------------------
+	// Triangle slots of one node are contiguous, so near the root a whole CTA works on ONE node and 256 threads would
+	// hammer the same dozen addresses.  min/max/add are order independent, so they are first reduced on chip:
+	//   bounds : warp reduction of the 12 integer keys (redux.sync), then shared memory across the CTA's warps -> 12
+	//            global atomics per CTA instead of 3072;
+	//   bins   : a 3 x 8 x 7-word histogram in shared memory per CTA (shared-memory atomics), flushed once.
+	// CTAs that straddle several nodes (deep levels, small nodes, little contention) use the per-slot atomics.
+	constexpr int kBuildBlock = 256;
+
+	__global__ void __launch_bounds__(kBuildBlock) k_build_bounds(BuildState s, uint32_t levelStart)
+	{
+		__shared__ uint32_t sNode[2];
+		__shared__ uint32_t sKeys[kBuildBlock / 32][12];
+		const uint32_t p = blockIdx.x * kBuildBlock + threadIdx.x;
+		const bool inRange = p < s.n;
+		const uint32_t node = inRange ? s.nodeOfA[p] : 0xFFFFFFFFu;
+		const uint32_t firstNode = s.nodeOfA[blockIdx.x * kBuildBlock];
+		const uint32_t lastIdx = min((blockIdx.x + 1u) * kBuildBlock, s.n) - 1u;
+		const bool uniform = firstNode == s.nodeOfA[lastIdx];       // slots of a node are contiguous
+		const bool active = inRange && node >= levelStart;
+		uint32_t k[12];
+		if (active)
+		{
+			const uint32_t tri = s.idxA[p];
+			const V4 a = s.vtx[tri * 3], b = s.vtx[tri * 3 + 1], c = s.vtx[tri * 3 + 2], ce = s.centroid[tri];
+			k[0] = float_key(glm_min(glm_min(a.x, b.x), c.x)); k[1] = float_key(glm_min(glm_min(a.y, b.y), c.y)); k[2] = float_key(glm_min(glm_min(a.z, b.z), c.z));
+			k[3] = float_key(glm_max(glm_max(a.x, b.x), c.x)); k[4] = float_key(glm_max(glm_max(a.y, b.y), c.y)); k[5] = float_key(glm_max(glm_max(a.z, b.z), c.z));
+			k[6] = k[9] = float_key(ce.x); k[7] = k[10] = float_key(ce.y); k[8] = k[11] = float_key(ce.z);
+		}
+		else
+		{
+#pragma unroll
+			for (int d = 0; d < 12; d++) k[d] = ((d % 6) < 3) ? 0xFFFFFFFFu : 0u;    // identities of min / max
+		}
+		if (!uniform)
+		{
+			if (active)
+			{
+				uint32_t* g = s.keys + (size_t)node * 12;
+#pragma unroll
+				for (int d = 0; d < 12; d++) { if ((d % 6) < 3) atomicMin(g + d, k[d]); else atomicMax(g + d, k[d]); }
+			}
+			return;
+		}
+		if (firstNode < levelStart) return;                           // the whole CTA belongs to a finished node
+#pragma unroll
+		for (int d = 0; d < 12; d++) k[d] = ((d % 6) < 3) ? __reduce_min_sync(0xffffffffu, k[d]) : __reduce_max_sync(0xffffffffu, k[d]);
+		const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+		if (lane == 0) { for (int d = 0; d < 12; d++) sKeys[warp][d] = k[d]; }
+		__syncthreads();
+		if (threadIdx.x < 12)
+		{
+			const int d = threadIdx.x;
+			uint32_t v = sKeys[0][d];
+			for (int w = 1; w < kBuildBlock / 32; w++) v = ((d % 6) < 3) ? min(v, sKeys[w][d]) : max(v, sKeys[w][d]);
+			uint32_t* g = s.keys + (size_t)firstNode * 12;
+			if ((d % 6) < 3) atomicMin(g + d, v); else atomicMax(g + d, v);
+		}
+		(void)sNode;
+	}
+
+	__global__ void __launch_bounds__(kBuildBlock) k_build_bin(BuildState s, uint32_t levelStart)
+	{
+		__shared__ uint32_t sBins[kNodeBinWords];
+		const uint32_t p = blockIdx.x * kBuildBlock + threadIdx.x;
+		const bool inRange = p < s.n;
+		const uint32_t node = inRange ? s.nodeOfA[p] : 0xFFFFFFFFu;
+		const uint32_t firstNode = s.nodeOfA[blockIdx.x * kBuildBlock];
+		const uint32_t lastIdx = min((blockIdx.x + 1u) * kBuildBlock, s.n) - 1u;
+		const bool uniform = firstNode == s.nodeOfA[lastIdx];
+		if (uniform)
+		{
+			if (firstNode < levelStart || !(s.state[firstNode] & kStBinning)) return;
+			const uint32_t kmin = float_key(10e30f), kmax = float_key(-10e30f);
+			for (uint32_t w = threadIdx.x; w < kNodeBinWords; w += kBuildBlock) { const uint32_t r = w % kBinWords; sBins[w] = r == 0 ? 0u : (r < 4 ? kmin : kmax); }
+			__syncthreads();
+		}
+		const bool active = inRange && node >= levelStart && (s.state[node] & kStBinning);
+		if (active)
+		{
+			const uint32_t tri = s.idxA[p];
+			const V4 a = s.vtx[tri * 3], b = s.vtx[tri * 3 + 1], c = s.vtx[tri * 3 + 2], ce = s.centroid[tri];
+			const float mn[3] = { glm_min(glm_min(a.x, b.x), c.x), glm_min(glm_min(a.y, b.y), c.y), glm_min(glm_min(a.z, b.z), c.z) };
+			const float mx[3] = { glm_max(glm_max(a.x, b.x), c.x), glm_max(glm_max(a.y, b.y), c.y), glm_max(glm_max(a.z, b.z), c.z) };
+			const float cc[3] = { ce.x, ce.y, ce.z };
+			const float* bs = s.binScale + (size_t)node * 6;
+			uint32_t* bins = uniform ? sBins : (s.bins + (size_t)s.binSlot[node] * kNodeBinWords);
+#pragma unroll
+			for (int ax = 0; ax < 3; ax++)
+			{
+				const float scale = bs[3 + ax];
+				if (scale == 0.0f) continue;
+				int32_t bi = (int32_t)((cc[ax] - bs[ax]) * scale);                      // BVH.cpp:49-50
+				bi = bi < (int32_t)kBins - 1 ? bi : (int32_t)kBins - 1;
+				if (bi < 0) bi = 0;
+				uint32_t* bn = bins + ((uint32_t)ax * kBins + (uint32_t)bi) * kBinWords;
+				atomicAdd(bn, 1u);
+#pragma unroll
+				for (int d = 0; d < 3; d++) { atomicMin(bn + 1 + d, float_key(mn[d])); atomicMax(bn + 4 + d, float_key(mx[d])); }
+			}
+		}
+		if (uniform)
+		{
+			__syncthreads();
+			uint32_t* g = s.bins + (size_t)s.binSlot[firstNode] * kNodeBinWords;
+			for (uint32_t w = threadIdx.x; w < kNodeBinWords; w += kBuildBlock)
+			{
+				const uint32_t r = w % kBinWords, v = sBins[w];
+				if (r == 0) { if (v) atomicAdd(g + w, v); }
+				else if (r < 4) atomicMin(g + w, v);
+				else atomicMax(g + w, v);
+			}
+		}
+	}
+
+	inline void LaunchBuildBounds(Ctx& ctx, const BuildState& s, uint32_t levelStart)
+	{
+		if (!ctx.ok) return;
+		k_build_bounds<<<(s.n + kBuildBlock - 1) / kBuildBlock, kBuildBlock, 0, ctx.stream>>>(s, levelStart);
+		ctx.kernelLaunches++;
+		SPT_CUDA_CHECK(ctx, cudaGetLastError());
+	}
+	inline void LaunchBuildBin(Ctx& ctx, const BuildState& s, uint32_t levelStart)
+	{
+		if (!ctx.ok) return;
+		k_build_bin<<<(s.n + kBuildBlock - 1) / kBuildBlock, kBuildBlock, 0, ctx.stream>>>(s, levelStart);
+		ctx.kernelLaunches++;
+		SPT_CUDA_CHECK(ctx, cudaGetLastError());
+	}
+#else
+	inline void LaunchBuildBounds(Ctx& ctx, const BuildState& s, uint32_t levelStart) { launch_for(ctx, s.n, BoundsKernel{ s, levelStart }); }
+	inline void LaunchBuildBin(Ctx& ctx, const BuildState& s, uint32_t levelStart) { launch_for(ctx, s.n, BinKernel{ s, levelStart }); }
+#endif
+
 	struct SplitKernel       // the plane sweep of FindBestSplitPlane (:56-86) + Subdivide's cost test (:226-234)
 	{
 		BuildState s; uint32_t levelStart;

@@ -167,9 +167,9 @@ namespace spt
 				levelStart.push_back(start); levelCount.push_back(cnt);
 				DevMemset(ctx, binCounter.p, 0, sizeof(uint32_t));
 				launch_for(ctx, cnt, InitNodesKernel{ s, start });
-				launch_for(ctx, N, BoundsKernel{ s, start });
+				LaunchBuildBounds(ctx, s, start);
 				launch_for(ctx, cnt, PrepareKernel{ s, start });
-				launch_for(ctx, N, BinKernel{ s, start });
+				LaunchBuildBin(ctx, s, start);
 				launch_for(ctx, cnt, SplitKernel{ s, start });
 				launch_for(ctx, N, FlagKernel{ s, start });
 				ExclusiveScanU32(ctx, flags.p, scan.p, N, scanScratch);
