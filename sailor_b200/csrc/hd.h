@@ -86,6 +86,8 @@ namespace spt
 	__device__ __forceinline__ uint4 ld4u(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 #else
 	inline V4 ld4(const V4* p) { return *p; }
+	struct U4 { uint32_t x, y, z, w; };
+	inline U4 ld4u(const void* p) { return *reinterpret_cast<const U4*>(p); }
 #endif
 
 	// Reference constants

@@ -55,25 +55,39 @@ namespace spt
 	}
 
 #if !defined(SPT_EMU)
-	__global__ void __launch_bounds__(kTraceBlock) k_primary_pass(PrimaryArgs a, uint32_t* __restrict__ counter)
+	struct PrimaryPassSource
 	{
-		__shared__ uint32_t stackMem[kStackDepth * kTraceBlock];
-		SmemStack stack; stack.base = stackMem + threadIdx.x; stack.n = 0;
-		const uint32_t lane = threadIdx.x & 31;
-		for (;;)
+		PrimaryArgs a;
+		__device__ __forceinline__ bool Load(uint32_t g, V3& o, V3& d, uint32_t& ignore, float& maxLen) const
 		{
-			uint32_t base = 0;
-			if (lane == 0) base = atomicAdd(counter, 32u);
-			base = __shfl_sync(0xffffffffu, base, 0);
-			if (base >= a.total) break;
 			uint32_t x, y, sample;
-			PrimaryHitRec rec;
-			bool hit = false;
-			if (DecodePrimary(a, base + lane, x, y, sample)) hit = PrimarySample(a, x, y, sample, stack, rec);
-			// warp-aggregated append: one atomic per warp, the warp's hits stay contiguous in the queue
+			if (!DecodePrimary(a, g, x, y, sample)) return false;
+			const uint32_t pixel = y * a.cam.width + x;
+			Rng rng; rng.key = PrimaryRngKey(a.seed, pixel, a.msaa, sample); rng.counter = 0;
+			float ox = 0.5f, oy = 0.5f;                                               // PathTracer.cpp:460
+			if (sample != 0) { ox = rng.Float01(); oy = rng.Float01(); }
+			o = a.cam.pos; d = PrimaryDir(a.cam, x, y, ox, oy); ignore = kNoHit; maxLen = kFltMax;
+			return true;
+		}
+	};
+	struct PrimaryPassSink
+	{
+		PrimaryArgs a;
+		__device__ __forceinline__ void Retire(bool finished, uint32_t g, const Hit& h) const
+		{
+			const bool hit = finished && h.tri != kNoHit;
+			uint32_t x = 0, y = 0, sample = 0;
+			if (finished) DecodePrimary(a, g, x, y, sample);
+			if (finished && !hit)
+			{
+				const size_t idx = ((size_t)(y - a.rowBegin) * a.cam.width + x) * (a.msEnd - a.msBegin) + (sample - a.msBegin);
+				a.sampleBuf[idx * 3] = a.ambient.x; a.sampleBuf[idx * 3 + 1] = a.ambient.y; a.sampleBuf[idx * 3 + 2] = a.ambient.z;   // :873-876
+			}
+			// warp-aggregated append: one atomic per warp and iteration, the warp's hits stay contiguous in the queue
 			const uint32_t m = __ballot_sync(0xffffffffu, hit);
 			if (m)
 			{
+				const uint32_t lane = threadIdx.x & 31;
 				const int leader = __ffs(m) - 1;
 				uint32_t qbase = 0;
 				if ((int)lane == leader) qbase = atomicAdd(a.hitCount, (uint32_t)__popc(m));
@@ -82,11 +96,18 @@ namespace spt
 				{
 					const uint32_t slot = qbase + (uint32_t)__popc(m & ((1u << lane) - 1u));
 					float4* q = reinterpret_cast<float4*>(a.queue + slot);
-					q[0] = make_float4(__uint_as_float(rec.pixel), __uint_as_float(rec.sample), 0.0f, 0.0f);
-					q[1] = make_float4(rec.t, rec.u, rec.v, __uint_as_float(rec.tri));
+					q[0] = make_float4(__uint_as_float(y * a.cam.width + x), __uint_as_float(sample), 0.0f, 0.0f);
+					q[1] = make_float4(h.t, h.u, h.v, __uint_as_float(h.tri));
 				}
 			}
 		}
+	};
+
+	__global__ void __launch_bounds__(kTraceBlock) k_primary_pass(PrimaryArgs a, uint32_t* __restrict__ counter)
+	{
+		__shared__ uint32_t stackMem[kSmemStack * kTraceBlock];
+		PrimaryPassSource src{ a }; PrimaryPassSink sink{ a };
+		TraceWarpLoop(a.bvh, a.total, counter, stackMem, src, sink);
 	}
 
 	inline void LaunchPrimaryPass(Ctx& ctx, const PrimaryArgs& a, uint32_t* counter)

@@ -1,10 +1,23 @@
 // trace_kernels.cuh — launchers of the traversal stage.
 //
-// Device form: PERSISTENT THREADS.  The grid is sized to the machine (SMs x resident CTAs), each warp pulls batches
-// of 32 rays from a global counter until the queue is empty, so long and short rays balance across the chip without
-// a tail of half-empty CTAs.  The per-lane traversal stack lives in shared memory, laid out [entry][thread] so the
-// 32 lanes of a warp always hit 32 different banks.  Node and triangle records are fetched as 128-bit loads through
-// the read-only path (see traverse.cuh for the layouts).
+// Device form: PERSISTENT WARPS WITH DYNAMIC RAY FETCH.  The grid is sized to the machine (SMs x resident CTAs).
+// Every lane owns one ray and is in one of three modes: idle, at an INNER node, or inside a LEAF (one triangle per
+// step).  Each iteration the warp votes (ballot) and executes the step the majority of its busy lanes needs, so an
+// instruction is never issued for a handful of lanes while the rest wait in the other branch; lanes that finished
+// are refilled from the global queue as soon as a quarter of the warp is idle (one atomicAdd per refill), so the
+// warp does not drain to its slowest ray.  Per lane the order of box and triangle tests is exactly the
+// reference's (BVH.cpp:122-191) whatever the warp does, so hit ids and barycentrics stay bit-identical.
+//
+// The per-lane traversal stack keeps its first kSmemStack entries in shared memory, laid out [entry][thread] so the
+// 32 lanes of a warp hit 32 different banks, and spills deeper entries to local memory (the reference allows 64;
+// a 1M-triangle tree needs ~22).  Keeping the shared part small leaves the SM's L1 for nodes and triangles and lets
+// ~40 warps per SM hide the L2 latency of the dependent node fetches.  Node and triangle records are fetched as
+// 128-bit loads through the read-only path (see traverse.cuh for the layouts).
+//
+// Slab test: CUDA's FMNMX drops NaNs while the reference's SSE/glm min/max propagate them in operand order
+// (SURVEY H2).  NaNs can only arise from 0 * inf, i.e. when a component of 1/dir is not finite; rays whose
+// reciprocal direction and origin are finite take the FMNMX form (bit-identical results on non-NaN inputs),
+// all others take the reference's compare-select form.
 #pragma once
 #include "traverse.cuh"
 
@@ -16,8 +29,10 @@ namespace spt
 
 #if !defined(SPT_EMU)
 	constexpr int kTraceBlock = 128;
+	constexpr int kSmemStack = 24;
+	constexpr uint32_t kFetchMinIdle = 8;
 
-	struct SmemStack
+	struct SmemStack     // used by the one-ray-per-thread helpers (TraceClosest); whole stack in shared memory
 	{
 		uint32_t* base; int n;     // base already offset by threadIdx.x; stride = blockDim.x
 		__device__ __forceinline__ void clear() { n = 0; }
@@ -26,61 +41,209 @@ namespace spt
 		__device__ __forceinline__ uint32_t pop() { n--; return base[n * kTraceBlock]; }
 	};
 
-	__device__ __forceinline__ V4 ldg4(const V4* p) { const float4 f = __ldg(reinterpret_cast<const float4*>(p)); return v4(f.x, f.y, f.z, f.w); }
+	// Slab test on non-NaN operands: same values as SlabTest, min/max as single FMNMX instructions.
+	__device__ __forceinline__ float SlabTestFast(V3 o, V3 rD, float bminx, float bminy, float bminz, float bmaxx, float bmaxy, float bmaxz, float maxLen)
+	{
+		const float t1x = (bminx - o.x) * rD.x, t1y = (bminy - o.y) * rD.y, t1z = (bminz - o.z) * rD.z;
+		const float t2x = (bmaxx - o.x) * rD.x, t2y = (bmaxy - o.y) * rD.y, t2z = (bmaxz - o.z) * rD.z;
+		const float tmax = fminf(fmaxf(t1x, t2x), fminf(fmaxf(t1y, t2y), fmaxf(t1z, t2z)));
+		const float tmin = fmaxf(fminf(t1x, t2x), fmaxf(fminf(t1y, t2y), fminf(t1z, t2z)));
+		return (tmax >= tmin && tmin < maxLen && tmax > 0.0f) ? tmin : kFltMax;
+	}
+
+	__device__ __forceinline__ bool FiniteF(float f) { return (__float_as_uint(f) & 0x7F800000u) != 0x7F800000u; }
+
+	// The warp loop.  Source: bool Load(uint32_t index, V3& o, V3& d, uint32_t& ignore, float& maxLen) (false = nothing to
+	// trace at this index).  Sink: void Retire(bool finished, uint32_t index, const Hit&) called by ALL lanes each iteration.
+	template<class Source, class Sink>
+	__device__ __forceinline__ void TraceWarpLoop(const BvhView& bvh, uint32_t n, uint32_t* __restrict__ counter, uint32_t* stackMem, Source& src, Sink& sink)
+	{
+		uint32_t* const sbase = stackMem + threadIdx.x;
+		uint32_t ovf[kStackDepth - kSmemStack];
+		const uint32_t lane = threadIdx.x & 31;
+		enum : uint32_t { kIdle = 0, kInner = 1, kLeaf = 2 };
+		uint32_t mode = kIdle;
+		V3 o = v3(0.0f), d = v3(0.0f), rD = v3(0.0f);
+		float maxLen = 0.0f; uint32_t ignore = kNoHit, index = 0;
+		bool safe = false;
+		Hit hit; hit.t = 0.0f; hit.u = 0.0f; hit.v = 0.0f; hit.tri = kNoHit;
+		uint32_t cur = 0, triLeft = 0;
+		int sp = 0;
+		bool exhausted = false;
+
+		for (;;)
+		{
+			// ---- refill idle lanes -------------------------------------------------------------------------
+			const uint32_t idleMask = __ballot_sync(0xffffffffu, mode == kIdle);
+			if (idleMask == 0xffffffffu && exhausted) break;
+			if (!exhausted && (__popc(idleMask) >= (int)kFetchMinIdle))
+			{
+				const uint32_t want = (uint32_t)__popc(idleMask);
+				uint32_t base = 0;
+				if (lane == 0) base = atomicAdd(counter, want);
+				base = __shfl_sync(0xffffffffu, base, 0);
+				if (base + want >= n) exhausted = true;
+				if (mode == kIdle)
+				{
+					const uint32_t i = base + (uint32_t)__popc(idleMask & ((1u << lane) - 1u));
+					if (i < n && src.Load(i, o, d, ignore, maxLen))
+					{
+						index = i;
+						rD = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);          // Ray::SetDirection (Bounds.h:44-48)
+						safe = FiniteF(rD.x) && FiniteF(rD.y) && FiniteF(rD.z) && FiniteF(o.x) && FiniteF(o.y) && FiniteF(o.z);
+						hit.t = u2f(0x7F800000u); hit.u = 0.0f; hit.v = 0.0f; hit.tri = kNoHit;
+						sp = 0;
+						cur = bvh.rootRef;
+						if (cur & kLeafBit) { mode = kLeaf; cur &= ~kLeafBit; triLeft = 0xFFFFFFFFu; } else mode = kInner;
+					}
+				}
+				continue;
+			}
+			// ---- vote: the step most busy lanes need --------------------------------------------------------
+			const uint32_t innerMask = __ballot_sync(0xffffffffu, mode == kInner);
+			const uint32_t leafMask = __ballot_sync(0xffffffffu, mode == kLeaf);
+			bool finished = false;
+			uint32_t next = 0; bool havePopOrNext = false;      // next node reference for this lane after the step
+			if (__popc(innerMask) >= __popc(leafMask))
+			{
+				if (mode == kInner)
+				{
+					const TNode* nd = bvh.nodes + cur;
+					const V4 q0 = ld4(&nd->q0), q1 = ld4(&nd->q1), q2 = ld4(&nd->q2);
+					const auto q3 = ld4u(&nd->left);
+					uint32_t c1 = q3.x, c2 = q3.y;
+					float d1, d2;
+					if (safe)
+					{
+						d1 = SlabTestFast(o, rD, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, maxLen);
+						d2 = SlabTestFast(o, rD, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, maxLen);
+					}
+					else
+					{
+						d1 = SlabTest(o, rD, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, maxLen);
+						d2 = SlabTest(o, rD, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, maxLen);
+					}
+					if (d1 > d2) { const float tf = d1; d1 = d2; d2 = tf; const uint32_t tc = c1; c1 = c2; c2 = tc; }   // BVH.cpp:163-167
+					if (d1 == kFltMax) havePopOrNext = false;               // both missed: pop
+					else
+					{
+						next = c1; havePopOrNext = true;
+						if (d2 != kFltMax) { if (sp < kSmemStack) sbase[sp * kTraceBlock] = c2; else ovf[sp - kSmemStack] = c2; sp++; }
+					}
+				}
+			}
+			else
+			{
+				if (mode == kLeaf)
+				{
+					const TTri* T = bvh.tris + cur;
+					const V4 a = ld4(&T->a), b = ld4(&T->b), c = ld4(&T->c);
+					if (triLeft == 0xFFFFFFFFu) triLeft = f2u(c.z);           // the leaf's size sits in its first record
+					const uint32_t triId = f2u(c.y);
+					if (ignore != triId)                                       // BVH.cpp:136-139
+					{
+						float t, u, v;
+						if (TriTest(o, d, v3(a.x, a.y, a.z), v3(a.w, b.x, b.y), v3(b.z, b.w, c.x), maxLen, t, u, v))
+						{
+							hit.t = t; hit.u = u; hit.v = v; hit.tri = triId;
+							maxLen = std_min(maxLen, t);
+						}
+					}
+					cur++; triLeft--;
+					if (triLeft != 0) { next = cur | kLeafBit; havePopOrNext = true; }
+				}
+			}
+			// ---- move on: descend / next triangle / pop / finish --------------------------------------------
+			const bool stepped = ((__popc(innerMask) >= __popc(leafMask)) ? (mode == kInner) : (mode == kLeaf));
+			if (stepped)
+			{
+				if (!havePopOrNext)
+				{
+					if (sp == 0) { finished = true; mode = kIdle; }
+					else { sp--; next = sp < kSmemStack ? sbase[sp * kTraceBlock] : ovf[sp - kSmemStack]; havePopOrNext = true; }
+				}
+				if (havePopOrNext)
+				{
+					if (next & kLeafBit)
+					{
+						const bool sameLeaf = mode == kLeaf && triLeft != 0 && (next & ~kLeafBit) == cur;
+						if (!sameLeaf) triLeft = 0xFFFFFFFFu;
+						mode = kLeaf; cur = next & ~kLeafBit;
+					}
+					else { mode = kInner; cur = next; }
+				}
+			}
+			sink.Retire(finished, index, hit);
+		}
+	}
+
+	// ---- sources and sinks ---------------------------------------------------------------------------------------
+	struct QueueSource
+	{
+		const RayRec* rays;
+		__device__ __forceinline__ bool Load(uint32_t i, V3& o, V3& d, uint32_t& ignore, float& maxLen) const
+		{
+			const float4 r0 = __ldg(reinterpret_cast<const float4*>(rays + i));
+			const float4 r1 = __ldg(reinterpret_cast<const float4*>(rays + i) + 1);
+			if (r1.w < 0.0f) return false;     // inactive queue entry
+			o = v3(r0.x, r0.y, r0.z); ignore = __float_as_uint(r0.w); d = v3(r1.x, r1.y, r1.z); maxLen = r1.w;
+			return true;
+		}
+	};
+	struct QueueSink
+	{
+		Hit* hits;
+		__device__ __forceinline__ void Retire(bool finished, uint32_t i, const Hit& h) const
+		{
+			if (finished) *reinterpret_cast<float4*>(hits + i) = make_float4(h.t, h.u, h.v, __uint_as_float(h.tri));
+		}
+	};
 
 	// nPtr (optional): the queue length lives in device memory (wavefront levels); n is then its capacity
 	__global__ void __launch_bounds__(kTraceBlock) k_trace_rays(BvhView bvh, const RayRec* __restrict__ rays, Hit* __restrict__ hits,
 		uint32_t n, const uint32_t* __restrict__ nPtr, uint32_t* __restrict__ counter)
 	{
+		__shared__ uint32_t stackMem[kSmemStack * kTraceBlock];
 		if (nPtr) { const uint32_t m = *nPtr; if (m < n) n = m; }
-		__shared__ uint32_t stackMem[kStackDepth * kTraceBlock];
-		SmemStack stack; stack.base = stackMem + threadIdx.x; stack.n = 0;
-		const uint32_t lane = threadIdx.x & 31;
-		for (;;)
-		{
-			uint32_t base = 0;
-			if (lane == 0) base = atomicAdd(counter, 32u);
-			base = __shfl_sync(0xffffffffu, base, 0);
-			if (base >= n) break;
-			const uint32_t i = base + lane;
-			if (i < n)
-			{
-				const float4 r0 = __ldg(reinterpret_cast<const float4*>(rays + i));
-				const float4 r1 = __ldg(reinterpret_cast<const float4*>(rays + i) + 1);
-				if (r1.w < 0.0f) continue;     // idle pool slot
-				Hit h;
-				TraceClosest(bvh, v3(r0.x, r0.y, r0.z), v3(r1.x, r1.y, r1.z), __float_as_uint(r0.w), r1.w, stack, h);
-				*reinterpret_cast<float4*>(hits + i) = make_float4(h.t, h.u, h.v, __uint_as_float(h.tri));
-			}
-		}
+		QueueSource src{ rays }; QueueSink sink{ hits };
+		TraceWarpLoop(bvh, n, counter, stackMem, src, sink);
 	}
 
-	// primary rays of sample 0 generated in-kernel (no ray queue traffic): pixel index = y*width + x, task order
+	// primary rays of sample 0 generated in-kernel (no ray queue traffic): work index -> 8x4 pixel tile + lane
+	struct PrimarySource
+	{
+		CameraGpu cam; uint32_t tilesX;
+		__device__ __forceinline__ void Pixel(uint32_t i, uint32_t& x, uint32_t& y) const
+		{
+			const uint32_t tile = i >> 5, l = i & 31u;
+			x = (tile % tilesX) * 8u + (l & 7u); y = (tile / tilesX) * 4u + (l >> 3);
+		}
+		__device__ __forceinline__ bool Load(uint32_t i, V3& o, V3& d, uint32_t& ignore, float& maxLen) const
+		{
+			uint32_t x, y; Pixel(i, x, y);
+			if (x >= cam.width || y >= cam.height) return false;
+			o = cam.pos; d = PrimaryDir(cam, x, y, 0.5f, 0.5f); ignore = kNoHit; maxLen = kFltMax;
+			return true;
+		}
+	};
+	struct PrimarySink
+	{
+		Hit* hits; PrimarySource src;
+		__device__ __forceinline__ void Retire(bool finished, uint32_t i, const Hit& h) const
+		{
+			if (!finished) return;
+			uint32_t x, y; src.Pixel(i, x, y);
+			*reinterpret_cast<float4*>(hits + (size_t)y * src.cam.width + x) = make_float4(h.t, h.u, h.v, __uint_as_float(h.tri));
+		}
+	};
+
 	__global__ void __launch_bounds__(kTraceBlock) k_trace_primary(BvhView bvh, CameraGpu cam, Hit* __restrict__ hits, uint32_t* __restrict__ counter)
 	{
-		__shared__ uint32_t stackMem[kStackDepth * kTraceBlock];
-		SmemStack stack; stack.base = stackMem + threadIdx.x; stack.n = 0;
-		const uint32_t lane = threadIdx.x & 31;
-		// 8x4 pixel tiles per warp keep the 32 rays of a batch spatially coherent
+		__shared__ uint32_t stackMem[kSmemStack * kTraceBlock];
+		// 8x4 pixel tiles per warp keep the 32 rays of a fetch spatially coherent
 		const uint32_t tilesX = (cam.width + 7) / 8, tilesY = (cam.height + 3) / 4;
-		const uint32_t n = tilesX * tilesY * 32u;
-		for (;;)
-		{
-			uint32_t base = 0;
-			if (lane == 0) base = atomicAdd(counter, 32u);
-			base = __shfl_sync(0xffffffffu, base, 0);
-			if (base >= n) break;
-			{
-				const uint32_t tile = base / 32, tx = tile % tilesX, ty = tile / tilesX;
-				const uint32_t x = tx * 8 + (lane & 7), y = ty * 4 + (lane >> 3);
-				if (x < cam.width && y < cam.height)
-				{
-					Hit h;
-					TraceClosest(bvh, cam.pos, PrimaryDir(cam, x, y, 0.5f, 0.5f), kNoHit, kFltMax, stack, h);
-					*reinterpret_cast<float4*>(hits + (size_t)y * cam.width + x) = make_float4(h.t, h.u, h.v, __uint_as_float(h.tri));
-				}
-			}
-		}
+		PrimarySource src{ cam, tilesX }; PrimarySink sink{ hits, src };
+		TraceWarpLoop(bvh, tilesX * tilesY * 32u, counter, stackMem, src, sink);
 	}
 
 	inline int TraceGridSize()
