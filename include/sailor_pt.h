@@ -168,6 +168,9 @@ SAILOR_PT_API int32_t SailorPt_EvalLighting(uint32_t count, const float* in, flo
 
 SAILOR_PT_API int32_t SailorPt_GetStats(SailorPtStats* stats);
 SAILOR_PT_API const char* SailorPt_LastError(void);
+/* Product: make CUDA device `device` current for the calling thread (one process per GPU sets its LOCAL_RANK before
+ * loading a scene; scenes stay on the device they were created on).  Oracle: accepts 0 only. */
+SAILOR_PT_API int32_t SailorPt_SetDevice(int32_t device);
 /* "cuda sm_100a" for the product, "reference-cpu" for the oracle. */
 SAILOR_PT_API const char* SailorPt_Backend(void);
 

@@ -52,7 +52,7 @@ SYMBOLS = [
     "SailorPt_SceneCounts", "SailorPt_SceneGetTriangles", "SailorPt_BuildBVH", "SailorPt_GetBVH",
     "SailorPt_GetCamera", "SailorPt_IntersectRays", "SailorPt_PrimaryHits", "SailorPt_Render",
     "SailorPt_OutputStage", "SailorPt_SampleTexture", "SailorPt_EvalLighting", "SailorPt_GetStats",
-    "SailorPt_LastError", "SailorPt_Backend", "SailorPt_RenderResident", "SailorPt_ReadResident", "SailorPt_CopyResidentToDevice",
+    "SailorPt_LastError", "SailorPt_Backend", "SailorPt_RenderResident", "SailorPt_ReadResident", "SailorPt_CopyResidentToDevice", "SailorPt_SetDevice",
 ]
 
 
@@ -134,6 +134,7 @@ class Library:
         lib.SailorPt_SampleTexture.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, P(C.c_float), P(C.c_float)]
         lib.SailorPt_EvalLighting.argtypes = [C.c_uint32, P(C.c_float), P(C.c_float)]
         lib.SailorPt_GetStats.argtypes = [P(SailorPtStats)]
+        lib.SailorPt_SetDevice.argtypes = [C.c_int32]
         lib.SailorPt_LastError.restype = C.c_char_p
         lib.SailorPt_Backend.restype = C.c_char_p
         for s in SYMBOLS:
@@ -148,6 +149,9 @@ class Library:
 
     def backend(self):
         return self.lib.SailorPt_Backend().decode()
+
+    def set_device(self, index):
+        self.check(self.lib.SailorPt_SetDevice(index), "SailorPt_SetDevice")
 
     def stats(self):
         s = SailorPtStats()

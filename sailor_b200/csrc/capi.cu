@@ -65,6 +65,18 @@ const char* SailorPt_Backend(void)
 #endif
 }
 const char* SailorPt_LastError(void) { return t_lastError.c_str(); }
+int32_t SailorPt_SetDevice(int32_t device)
+{
+#if defined(SPT_EMU)
+	return device == 0 ? SAILOR_PT_OK : SAILOR_PT_ERR_ARG;
+#else
+	int count = 0;
+	if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) { cudaGetLastError(); return SetError(SAILOR_PT_ERR_NO_DEVICE, "no CUDA device: the sailor_b200 product library has no CPU path"); }
+	if (device < 0 || device >= count) return SetError(SAILOR_PT_ERR_ARG, "device index out of range");
+	if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return SetError(SAILOR_PT_ERR_CUDA, "cudaSetDevice failed"); }
+	return SAILOR_PT_OK;
+#endif
+}
 int32_t SailorPt_GetStats(SailorPtStats* s) { if (!s) return SAILOR_PT_ERR_ARG; *s = g_stats; return SAILOR_PT_OK; }
 
 int32_t SailorPt_ParseCommandLineArgs(SailorPtParams* res, const char** args, int32_t num)
