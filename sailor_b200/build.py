@@ -39,30 +39,31 @@ def needs_build():
     return os.path.getmtime(LIB) < newest
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines/out: tuning variants (tools/trace_variants.py) — extra -D flags, written to another file."""
+    if out is None and not force and not needs_build():
         return LIB
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" if out is None else "build_" + os.path.basename(out))
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
     for s in sources():
         o = os.path.join(objdir, os.path.basename(s) + ".o")
         objs.append(o)
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-I", os.path.join(HERE, "..", "include"), "-c", s, "-o", o]
+        cmd = [_nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-I", os.path.join(HERE, "..", "include"), "-c", s, "-o", o]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for cmd, p in procs:
-        out, _ = p.communicate()
+        log, _ = p.communicate()
         if verbose or p.returncode != 0:
-            sys.stderr.write(" ".join(cmd) + "\n" + out)
+            sys.stderr.write(" ".join(cmd) + "\n" + log)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed for " + cmd[-3])
-    link = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lz", "-Xcompiler", "-fPIC"]
+    link = [_nvcc(), "-shared", "-o", out or LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lz", "-Xcompiler", "-fPIC"]
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("link failed")
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

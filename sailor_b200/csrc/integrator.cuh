@@ -49,6 +49,10 @@ namespace spt
 	struct RenderStats { uint64_t rays, primarySamples; double secondsTraverse, secondsShade; uint32_t traverseLaunches; };
 
 	constexpr uint32_t kNone = 0xFFFFFFFFu;
+#ifndef SPT_FAN_OUT_MIN
+#define SPT_FAN_OUT_MIN 16
+#endif
+	constexpr uint32_t kFanOutMinSamples = SPT_FAN_OUT_MIN;   // activations with at least this many hemisphere + importance samples get a warp
 
 	// record flags
 	enum : uint32_t
@@ -79,19 +83,19 @@ namespace spt
 		kRkInactive = 0, kRkLight = 1, kRkHemi = 2, kRkSample = 3, kRkOwn = 4, kRkMask = 7u,
 		kRsBlocked = 8u,        // light: shadow ray hit something
 		kRsTransRay = 16u,      // sample: bTransmissionRay
-		kRsMiss = 32u,          // sample: ray missed -> a = clamp(term*ambient)
+		kRsMiss = 32u,          // sample / hemi: the ray missed; gather evaluates clamp(term*ambient) / the unattenuated sky term itself
 		kRsHit = 64u,           // sample: hit with bounceLimit > 0 -> a = clamp(term*att*L) (written by the child's gather, or by classify when no child runs)
 		kRsHit0 = 128u,         // sample: hit with bounceLimit == 0 (:835 only)
-		kRsSky2 = 256u,         // sample: TraceSky behind the hit returned non-zero -> b = att (:825-831)
+		kRsSky2 = 256u,         // sample: TraceSky behind the hit returned non-zero -> b = att (:825-831); hemi: a = final contribution of a sky walk
 		kRsSkipped = 512u,      // sample: rejection budget exhausted
 	};
 
 	// What a ray's result is weighted with; rewritten in place by classify / sky / the child's gather.
 	struct alignas(16) RayAux
 	{
-		float a0, a1, a2, a3;    // light: BRDF*intensity*angle | hemi: BRDF, angle -> contribution | sample: term, pdf -> value, pdf
-		float b0, b1, b2;        // sample: b0 = new environment IOR -> b = TraceSky attenuation
-		uint32_t tag;            // kind | state | owner... (owner record lives in `owner`)
+		float a0, a1, a2, a3;    // light: BRDF*intensity*angle | hemi: BRDF, angle (-> contribution after a sky walk) | sample: term, pdf -> value, pdf
+		float b0, b1, b2;        // b0: sample's new environment IOR; b1: bits(owner record; child record for kRkOwn); sample after a sky walk: b = TraceSky attenuation
+		uint32_t tag;            // kind | state
 	};
 	static_assert(sizeof(RayAux) == 32, "RayAux layout");
 
@@ -105,6 +109,7 @@ namespace spt
 	};
 	static_assert(sizeof(SkyState) == 64, "SkyState layout");
 
+	struct ShadeCtx;
 	struct LevelInfo { uint32_t recBegin, recEnd, rayCount, auxBase; };
 
 	// device-side allocation state of one batch
@@ -115,7 +120,8 @@ namespace spt
 		uint32_t overflow;         // any arena ran out: the batch is invalid, the host retries with a smaller one
 		uint32_t skyCount[2];      // ping-pong sky queues
 		uint32_t zero;             // always 0 (range begin)
-		uint32_t pad[2];
+		uint32_t fanThreads;       // 32 x activations handed to FanOutKernel at the current level
+		uint32_t pad;
 		unsigned long long rays;   // closest-hit queries of the batch
 		LevelInfo level[66];
 	};
@@ -131,9 +137,10 @@ namespace spt
 		// batch
 		const PrimaryHitRec* hitQueue; uint32_t queueBegin, queueCount;     // first hits [queueBegin, queueBegin+queueCount) are level 0
 		NodeRec* recs; uint32_t recCap;
-		RayAux* aux; uint32_t* auxOwner; uint32_t auxCap;                     // auxOwner: record (or child record for kRkOwn) of each RayAux
+		RayAux* aux; uint32_t auxCap; uint32_t hasSky;                       // hasSky: the scene has thick transmissive materials (TraceSky can continue)
 		RayRec* rays; Hit* hits; uint32_t rayCap;                             // ray queue of the current level
 		SkyState* sky[2]; RayRec* skyRays; Hit* skyHits; uint32_t skyCap;
+		ShadeCtx* fan; uint32_t fanCap;                                       // activations whose samples are produced by FanOutKernel
 		BatchCounters* c;
 		float* sampleBuf;                       // 3 floats per (pixel in band, sample in range)
 	};
@@ -176,16 +183,18 @@ namespace spt
 		return w * v3(n0.x, n0.y, n0.z) + u * v3(n1.x, n1.y, n1.z) + v * v3(n2.x, n2.y, n2.z);
 	}
 
-	SPT_KERNEL_BODY void WriteRay(RayRec* q, uint32_t i, V3 o, V3 d, uint32_t ignore, bool active)
+	// tmax encodes the query: +FLT_MAX closest hit; -FLT_MAX "any hit" (only hit-or-miss is consumed: the traversal may stop
+	// at the first accepted triangle, which the reference's closest-hit walk would also have accepted); -1 inactive entry.
+	SPT_KERNEL_BODY void WriteRay(RayRec* q, uint32_t i, V3 o, V3 d, uint32_t ignore, bool active, bool anyHit = false)
 	{
-		RayRec r; r.ox = o.x; r.oy = o.y; r.oz = o.z; r.ignoreTri = ignore; r.dx = d.x; r.dy = d.y; r.dz = d.z; r.tmax = active ? kFltMax : -1.0f;
+		RayRec r; r.ox = o.x; r.oy = o.y; r.oz = o.z; r.ignoreTri = ignore; r.dx = d.x; r.dy = d.y; r.dz = d.z; r.tmax = active ? (anyHit ? -kFltMax : kFltMax) : -1.0f;
 		q[i] = r;
 	}
 
 	SPT_KERNEL_BODY void WriteAux(const IntegratorArgs& a, uint32_t g, float a0, float a1, float a2, float a3, float b0, uint32_t tag, uint32_t owner)
 	{
-		RayAux x; x.a0 = a0; x.a1 = a1; x.a2 = a2; x.a3 = a3; x.b0 = b0; x.b1 = 0.0f; x.b2 = 0.0f; x.tag = tag;
-		a.aux[g] = x; a.auxOwner[g] = owner;
+		RayAux x; x.a0 = a0; x.a1 = a1; x.a2 = a2; x.a3 = a3; x.b0 = b0; x.b1 = u2f(owner); x.b2 = 0.0f; x.tag = tag;
+		a.aux[g] = x;
 	}
 
 	SPT_KERNEL_BODY uint32_t AllocRecord(const IntegratorArgs& a)
@@ -239,7 +248,7 @@ namespace spt
 				const V3 at = att * v3(x.a0, x.a1, x.a2);
 				c = glm_clamp((at * a.ambient * x.a3) / pdfHemisphere, 0.0f, 10.0f);
 			}
-			x.a0 = c.x; x.a1 = c.y; x.a2 = c.z;
+			x.a0 = c.x; x.a1 = c.y; x.a2 = c.z; x.tag |= kRsSky2;
 		}
 		else                                                                            // :825-831
 		{
@@ -255,6 +264,107 @@ namespace spt
 		if (i >= a.skyCap) { a.c->overflow = 1u; return; }
 		a.sky[q][i] = s;
 		WriteRay(a.skyRays + (q ? a.skyCap : 0u), i, s.start, s.dir, s.ignore, true);      // each queue owns one half of skyRays
+	}
+
+	// ---- per-sample generation ---------------------------------------------------------------------------------------
+	// The hemisphere and importance samples of one activation are independent of each other except for two walks the
+	// reference does sequentially: the blue-noise table positions (:934-1077) and the "at least one transmission ray"
+	// rule of thick volumes (:761).  Both are re-derived per sample from counters, so sample i can be produced by any
+	// thread: the thread-per-activation loop of ExpandKernel and the warp-per-activation FanOutKernel (first hits
+	// with many samples) emit bit-identical rays.
+	struct alignas(16) ShadeCtx        // shading context of one activation whose samples are fanned out over a warp
+	{
+		V3 N; float rough;
+		V3 V; float metal;
+		V3 hitPoint; float ior;
+		V3 offset; float thickness;
+		V4 baseColor;
+		float transmission, envIor, inAcc; uint32_t flags;       // flags: kNf* of the activation
+		uint64_t rngKey; uint32_t seedX, seedY;
+		uint32_t rec, tri, rayBase, nHemi;                       // rayBase: level-local index of the first hemisphere ray
+		uint32_t nS, bounceLimit, pMaxBounces, pad;
+	};
+	static_assert(sizeof(ShadeCtx) == 144, "ShadeCtx layout");
+
+	SPT_KERNEL_BODY SampledData SampledOf(const ShadeCtx& c)
+	{
+		SampledData s; s.baseColor = c.baseColor; s.orm = v3(0.0f, c.rough, c.metal); s.emissive = v3(0.0f); s.normal = v3(0.0f, 0.0f, 1.0f);
+		s.ior = c.ior; s.thickness = c.thickness; s.transmission = c.transmission; s.opaque = true;
+		return s;
+	}
+
+	// Table position of the m-th draw of a walk that starts at seed0: indices run up to 687, then the walk reseeds with
+	// linearRand(0, 680) (:1068-1076).  Reseed values come from a counter-based stream so the walk has random access.
+	SPT_KERNEL_BODY uint32_t BlueNoiseIndex(uint64_t recKey, uint32_t axis, uint32_t seed0, uint32_t m)
+	{
+		uint32_t s = seed0, rem = m;
+		Rng r; r.key = ChildRngKey(recKey, 0x30000000u + axis); r.counter = 0;
+		while (rem >= 688u - s) { rem -= 688u - s; s = r.Seed681(); }
+		return s + rem;
+	}
+
+	// Hemisphere sample k of an activation (:722-727, 732-733): direction, BRDF and cosine.
+	SPT_KERNEL_BODY void DrawHemisphere(const ShadeCtx& c, const SampledData& s, uint32_t k, V3& toL, V3& brdf, float& angle)
+	{
+		Rng r; r.key = ChildRngKey(c.rngKey, 0x10000000u + k); r.counter = 0;
+		const float r0 = r.Float01(), r1 = r.Float01();                               // NextVec2_Linear (:929-932)
+		const V3 H = ImportanceSampleHemisphere(v2(r0, r1), c.N);
+		toL = 2.0f * dot(c.V, H) * H - c.V;
+		brdf = c.pMaxBounces > 0 ? CalculateBRDF(c.V, c.N, toL, s) : v3(0.0f);       // TraceSky's loop runs maxBounces times (:581)
+		angle = glm_max(0.0f, dot(toL, c.N));
+	}
+
+	// Importance sample i (:755-767).  anyTrans carries bHasTransmissionRay in and out.  Returns false when the (capped)
+	// rejection loop gives up.
+	SPT_KERNEL_BODY bool DrawImportance(const IntegratorArgs& a, const ShadeCtx& c, const SampledData& s, uint32_t i, bool requireTrans, bool& anyTrans,
+		V3& term, float& pdf, bool& transRay, V3& direction)
+	{
+		const bool thick = (c.flags & kNfThick) != 0, opposite = (c.flags & kNfOpposite) != 0;
+		const bool fullMetal = s.orm.z == 1.0f, mirror = fullMetal && s.orm.y <= 0.001f, hasTrans = !fullMetal && s.transmission > 0.0f;
+		const float toIor = thick ? (opposite ? s.ior : 1.0f) : c.envIor;             // :749
+		Rng r; r.key = ChildRngKey(c.rngKey, 0x20000000u + i); r.counter = 0;
+		for (uint32_t tries = 0; tries < 4096u; tries++)
+		{
+			const uint32_t m = i + tries * c.nS;                                       // every retry takes a later position of the walk
+			const V2 Xi = v2((float)a.blueNoise[BlueNoiseIndex(c.rngKey, 0, c.seedX, m)] * (1.0f / 1024.0f),
+				(float)a.blueNoise[BlueNoiseIndex(c.rngKey, 1, c.seedY, m)] * (1.0f / 1024.0f));
+			const float rs = mirror ? 1.0f : r.Float01();
+			const float rt = hasTrans ? r.Float01() : 0.0f;
+			direction = v3(0.0f);
+			const bool ok = SampleBsdf(s, c.N, c.V, c.envIor, toIor, term, pdf, transRay, direction, Xi, rs, rt);
+			anyTrans = anyTrans || transRay;
+			if (ok && !(requireTrans && !anyTrans)) return true;
+		}
+		return false;
+	}
+
+	// Emit hemisphere ray k / importance ray i of an activation into the level's queue (ray r, RayAux g).
+	SPT_KERNEL_BODY void EmitHemisphere(const IntegratorArgs& a, const ShadeCtx& c, const SampledData& s, uint32_t k, uint32_t r, uint32_t g)
+	{
+		V3 toL, brdf; float angle;
+		DrawHemisphere(c, s, k, toL, brdf, angle);
+		const bool live = c.pMaxBounces > 0;
+		WriteRay(a.rays, r, c.hitPoint + c.offset, toL, c.tri, live, !a.hasSky);       // without thick transmissive materials TraceSky is a boolean
+		// a dead hemisphere ray contributes 0: gather skips entries that are neither kRsMiss nor kRsSky2
+		WriteAux(a, g, brdf.x, brdf.y, brdf.z, angle, 0.0f, live ? kRkHemi : kRkInactive, c.rec);
+	}
+	SPT_KERNEL_BODY void EmitImportance(const IntegratorArgs& a, const ShadeCtx& c, const SampledData& s, uint32_t i, bool requireTrans, bool& anyTrans, uint32_t r, uint32_t g)
+	{
+		V3 term = v3(0.0f), direction = v3(0.0f); float pdf = 0.0f; bool transRay = false;
+		if (!DrawImportance(a, c, s, i, requireTrans, anyTrans, term, pdf, transRay, direction))
+		{
+			WriteRay(a.rays, r, c.hitPoint, v3(0.0f), c.tri, false);
+			WriteAux(a, g, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, kRkInactive | kRsSkipped, c.rec);
+			return;
+		}
+		const bool thick = (c.flags & kNfThick) != 0, opposite = (c.flags & kNfOpposite) != 0;
+		float newIor = c.envIor;                                                       // :769-778
+		if (opposite && transRay && thick) newIor = s.ior;
+		else if (!opposite && transRay && thick) newIor = 1.0f;
+		// the hit itself is consumed only when a child activation can start from it (:797-814) or TraceSky can continue (:822-832)
+		const bool boolOnly = c.bounceLimit == 0 || (!thick && !a.hasSky && !(c.inAcc * length(term) * s.baseColor.w > 0.01f));
+		WriteRay(a.rays, r, c.hitPoint + (transRay ? -c.offset : c.offset), direction, c.tri, true, boolOnly);
+		WriteAux(a, g, term.x, term.y, term.z, pdf, newIor, kRkSample | (transRay ? kRsTransRay : 0u), c.rec);
 	}
 
 	// ---- level 0: first hits of the primary pass become records --------------------------------------------------
@@ -289,14 +399,6 @@ namespace spt
 		{
 			Rng rng; uint32_t seedX, seedY;
 		};
-
-		SPT_KERNEL_BODY V2 BlueNoise(Ctx2& c) const                                  // PathTracer.cpp:934-1077
-		{
-			if (c.seedX >= 688u) c.seedX = c.rng.Seed681();
-			if (c.seedY >= 688u) c.seedY = c.rng.Seed681();
-			const float x = (float)a.blueNoise[c.seedX++] * (1.0f / 1024.0f), y = (float)a.blueNoise[c.seedY++] * (1.0f / 1024.0f);
-			return v2(x, y);
-		}
 
 		// child activation that still needs its own closest hit (alpha continuation / thick-volume tail call)
 		SPT_KERNEL_BODY uint32_t SpawnOwn(const NodeRec& n, uint32_t self, V3 o, V3 d, uint32_t bounceLimit, uint32_t pMaxBounces, uint32_t pNumSamples,
@@ -413,54 +515,32 @@ namespace spt
 				const V3 toL = -v3(ld.x, ld.y, ld.z);
 				const float angle = glm_max(0.0f, dot(toL, N));
 				const V3 w = CalculateBRDF(V, N, toL, s) * v3(li.x, li.y, li.z) * angle;
-				WriteRay(a.rays, r, hitPoint + offset, toL, tri, true);
+				WriteRay(a.rays, r, hitPoint + offset, toL, tri, true, true);            // shadow test: boolean (:699)
 				WriteAux(a, L->auxBase + r, w.x, w.y, w.z, 0.0f, 0.0f, kRkLight, ri);
 			}
-			// ---- :720-737 hemisphere samples (TraceSky's first ray)
-			for (uint32_t k = 0; k < nHemi; k++, r++)
+			// ---- :720-784 hemisphere + importance samples
 			{
-				const float r0 = cx.rng.Float01(), r1 = cx.rng.Float01();                // NextVec2_Linear (:929-932)
-				const V3 H = ImportanceSampleHemisphere(v2(r0, r1), N);
-				const V3 toL = 2.0f * dot(V, H) * H - V;
-				const bool live = pMaxBounces > 0;                                       // TraceSky's loop runs maxBounces times (:581)
-				const V3 brdf = live ? CalculateBRDF(V, N, toL, s) : v3(0.0f);
-				const float angle = glm_max(0.0f, dot(toL, N));
-				WriteRay(a.rays, r, hitPoint + offset, toL, tri, live);
-				// a dead hemisphere ray contributes 0: kRkInactive with a = 0 is read by gather as a zero contribution
-				WriteAux(a, L->auxBase + r, brdf.x, brdf.y, brdf.z, angle, 0.0f, live ? kRkHemi : kRkInactive, ri);
-			}
-			// ---- :741-784 importance samples
-			{
-				const float toIor = thick ? (opposite ? s.ior : 1.0f) : n.envIor;        // :749
-				const bool mirror = fullMetal && s.orm.y <= 0.001f;
-				bool hasTransRay = false;
-				for (uint32_t i = 0; i < nS; i++, r++)
+				ShadeCtx c;
+				c.N = N; c.rough = s.orm.y; c.V = V; c.metal = s.orm.z; c.hitPoint = hitPoint; c.ior = s.ior; c.offset = offset; c.thickness = s.thickness;
+				c.baseColor = s.baseColor; c.transmission = s.transmission; c.envIor = n.envIor; c.inAcc = n.inAcc;
+				c.flags = (opposite ? kNfOpposite : 0u) | (thick ? kNfThick : 0u);
+				c.rngKey = n.rngKey; c.seedX = cx.seedX; c.seedY = cx.seedY;
+				c.rec = ri; c.tri = tri; c.rayBase = r; c.nHemi = nHemi; c.nS = nS; c.bounceLimit = bounceLimit; c.pMaxBounces = pMaxBounces; c.pad = 0;
+				bool fanned = false;
+				if (nHemi + nS >= kFanOutMinSamples)
 				{
-					V3 term = v3(0.0f), direction = v3(0.0f);
-					float pdf = 0.0f; bool transRay = false, ok = false;
-					int tries = 0;
-					while ((!ok || (thick && !hasTransRay && i == (nS - 1u))) && tries < 4096)
-					{
-						direction = v3(0.0f);
-						const V2 Xi = BlueNoise(cx);
-						const float rs = mirror ? 1.0f : cx.rng.Float01();
-						const float rt = hasTrans ? cx.rng.Float01() : 0.0f;
-						ok = SampleBsdf(s, N, V, n.envIor, toIor, term, pdf, transRay, direction, Xi, rs, rt);
-						hasTransRay = hasTransRay || transRay;
-						tries++;
-					}
-					if (!ok)
-					{
-						WriteRay(a.rays, r, hitPoint, v3(0.0f), tri, false);
-						WriteAux(a, L->auxBase + r, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, kRkInactive | kRsSkipped, ri);
-						continue;
-					}
-					float newIor = n.envIor;                                             // :769-778
-					if (opposite && transRay && thick) newIor = s.ior;
-					else if (!opposite && transRay && thick) newIor = 1.0f;
-					WriteRay(a.rays, r, hitPoint + (transRay ? -offset : offset), direction, tri, true);
-					WriteAux(a, L->auxBase + r, term.x, term.y, term.z, pdf, newIor, kRkSample | (transRay ? kRsTransRay : 0u), ri);
+					// many samples (first hits): hand them to a warp (FanOutKernel); this thread only reserves the rays
+					const uint32_t e = atomic_add_u32(&a.c->fanThreads, 32u) / 32u;
+					if (e < a.fanCap) { a.fan[e] = c; fanned = true; }
 				}
+				if (!fanned)
+				{
+					const SampledData sc = SampledOf(c);
+					for (uint32_t k = 0; k < nHemi; k++) EmitHemisphere(a, c, sc, k, r + k, L->auxBase + r + k);
+					bool anyTrans = false;
+					for (uint32_t i = 0; i < nS; i++) EmitImportance(a, c, sc, i, thick && i == nS - 1u, anyTrans, r + nHemi + i, L->auxBase + r + nHemi + i);
+				}
+				r += nHemi + nS;
 			}
 			// ---- :858-871 alpha-blend continuation: an independent activation, started now
 			uint32_t child = kNone;
@@ -481,6 +561,37 @@ namespace spt
 		}
 	};
 
+	// ---- fan-out: one warp per activation with many samples; lane l produces samples l, l+32, ... ------------------------
+	struct FanOutKernel
+	{
+		IntegratorArgs a; uint32_t level;
+		SPT_KERNEL_BODY void operator()(uint32_t w) const                             // w = entry * 32 + lane
+		{
+			const uint32_t e = w >> 5, lane = w & 31u;
+			if (e >= a.fanCap) return;
+			const ShadeCtx c = a.fan[e];
+			const SampledData s = SampledOf(c);
+			const uint32_t auxBase = a.c->level[level].auxBase;
+			for (uint32_t k = lane; k < c.nHemi; k += 32u) EmitHemisphere(a, c, s, k, c.rayBase + k, auxBase + c.rayBase + k);
+			const bool thick = (c.flags & kNfThick) != 0;
+			for (uint32_t i = lane; i < c.nS; i += 32u)
+			{
+				bool anyTrans = false;
+				const bool last = thick && i == c.nS - 1u;
+				if (last)
+				{
+					// bHasTransmissionRay (:761) looks back over every attempt of the earlier samples: replay them (thick volumes only)
+					for (uint32_t j = 0; j + 1u < c.nS && !anyTrans; j++)
+					{
+						V3 term, direction; float pdf; bool transRay;
+						DrawImportance(a, c, s, j, false, anyTrans, term, pdf, transRay, direction);
+					}
+				}
+				EmitImportance(a, c, s, i, last, anyTrans, c.rayBase + c.nHemi + i, auxBase + c.rayBase + c.nHemi + i);
+			}
+		}
+	};
+
 	// ---- classify: fold one ray's closest hit into its RayAux, spawn the child activation of an importance hit --------
 	struct ClassifyKernel
 	{
@@ -488,16 +599,21 @@ namespace spt
 		SPT_KERNEL_BODY void operator()(uint32_t i) const
 		{
 			const uint32_t g = a.c->level[level].auxBase + i;
-			RayAux x = a.aux[g];
-			const uint32_t kind = x.tag & kRkMask;
+			// fast paths touch only the tag word and the hit's triangle id: most rays are final after one comparison
+			const uint32_t tag = a.aux[g].tag;
+			const uint32_t kind = tag & kRkMask;
 			if (kind == kRkInactive) return;
-			const Hit h = a.hits[i];
-			const uint32_t owner = a.auxOwner[g];
+			const uint32_t hitTri = a.hits[i].tri;
 			if (kind == kRkLight)
 			{
-				if (h.tri != kNoHit) a.aux[g].tag = x.tag | kRsBlocked;                  // :699
+				if (hitTri != kNoHit) a.aux[g].tag = tag | kRsBlocked;                   // :699
 				return;
 			}
+			if (hitTri == kNoHit && kind != kRkOwn) { a.aux[g].tag = tag | kRsMiss; return; }   // hemi: TraceSky returns att = 1 (:587-590); sample: :786-796
+			if (kind == kRkHemi && !a.hasSky) return;                                    // hit something opaque: TraceSky returns 0 (:597-600)
+			RayAux x = a.aux[g];
+			const Hit h = a.hits[i];
+			const uint32_t owner = f2u(x.b1);
 			if (kind == kRkOwn)
 			{
 				NodeRec* c = a.recs + owner;
@@ -519,13 +635,6 @@ namespace spt
 			}
 			// kRkSample (:786-833)
 			const V3 term = v3(x.a0, x.a1, x.a2);
-			if (h.tri == kNoHit)
-			{
-				const V3 value = glm_clamp(term * a.ambient, 0.0f, 10.0f);               // :788
-				x.a0 = value.x; x.a1 = value.y; x.a2 = value.z; x.tag |= kRsMiss;
-				a.aux[g] = x;
-				return;
-			}
 			const NodeRec* o = a.recs + owner;
 			const uint32_t bounceLimit = o->bounces & 0xFFFFu, pMaxBounces = o->bounces >> 16;
 			if (bounceLimit == 0) { a.aux[g].tag = x.tag | kRsHit0; return; }            // :797, :835
@@ -625,7 +734,8 @@ namespace spt
 						for (uint32_t k = 0; k < nA; k++, g++)
 						{
 							const RayAux x = a.aux[g];
-							if ((x.tag & kRkMask) == kRkHemi) amb1 = amb1 + v3(x.a0, x.a1, x.a2);
+							if (x.tag & kRsSky2) amb1 = amb1 + v3(x.a0, x.a1, x.a2);                                          // a sky walk ended (:730-735)
+							else if (x.tag & kRsMiss) amb1 = amb1 + glm_clamp((v3(x.a0, x.a1, x.a2) * a.ambient * x.a3) / pdfHemisphere, 0.0f, 10.0f);   // att = 1
 						}
 					}
 					amb1 = amb1 / (float)nA;                                              // :739
@@ -634,8 +744,8 @@ namespace spt
 					{
 						const RayAux x = a.aux[g];
 						if (x.tag & kRsSkipped) continue;
-						const V3 value = v3(x.a0, x.a1, x.a2);
-						if (x.tag & kRsMiss) { amb2 = amb2 + value; avgPdf += x.a3; indirect = indirect + value; }         // :786-796
+						V3 value = v3(x.a0, x.a1, x.a2);
+						if (x.tag & kRsMiss) { value = glm_clamp(value * a.ambient, 0.0f, 10.0f); amb2 = amb2 + value; avgPdf += x.a3; indirect = indirect + value; }   // :786-796
 						else if (x.tag & kRsHit)                                                                          // :816-832
 						{
 							indirect = indirect + value;
@@ -684,7 +794,7 @@ namespace spt
 		BatchCounters* c; uint32_t count;
 		SPT_KERNEL_BODY void operator()(uint32_t) const
 		{
-			c->recAlloc = count; c->auxAlloc = 0; c->overflow = 0; c->skyCount[0] = c->skyCount[1] = 0; c->zero = 0; c->rays = 0;
+			c->recAlloc = count; c->auxAlloc = 0; c->overflow = 0; c->skyCount[0] = c->skyCount[1] = 0; c->zero = 0; c->fanThreads = 0; c->rays = 0;
 			c->level[0].recBegin = 0; c->level[0].recEnd = count; c->level[0].rayCount = 0; c->level[0].auxBase = 0;
 		}
 	};
@@ -698,6 +808,7 @@ namespace spt
 			c->level[level + 1] = nx;
 			c->auxAlloc = nx.auxBase;
 			c->rays += cur.rayCount;
+			c->fanThreads = 0;
 		}
 	};
 	struct SkySwapKernel         // after a sky iteration: queue q is consumed

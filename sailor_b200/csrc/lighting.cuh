@@ -2,9 +2,11 @@
 //
 // Restates LightingModel (reference Raytracing/LightingModel.cpp) expression by expression, in fp32, with the
 // reference's own constants (two different pi values are in play: glm::pi<float>() and Math::Pi = 3.1415926f),
-// clamps (max(r*r,1e-3), max(NdotH,1e-4) ...) and early-outs.  Transcendentals (powf/expf/logf/sinf/cosf) are the
-// CUDA libm ones, which differ from glibc in the last ulp or two; that is inside the converged-image tolerance and
-// checked per function by tests/test_lighting.py (SailorPt_EvalLighting).
+// clamps (max(r*r,1e-3), max(NdotH,1e-4) ...) and early-outs.  The integer powers the reference writes as pow(x, 5.0f),
+// pow(x, 2.0f), pow(x, 4.0f) are evaluated by multiplication (within 2 ulp of glibc's correctly rounded pow, closer to
+// it than CUDA's powf and an order of magnitude cheaper); expf/logf/sinf/cosf are the CUDA libm ones, which differ from
+// glibc in the last ulp or two.  All of that is inside the converged-image tolerance and is checked per function against
+// the reference's own LightingModel by SailorPt_EvalLighting (tests: check_lighting, rtol 2e-4).
 #pragma once
 #include "backend.h"
 
@@ -30,7 +32,8 @@ namespace spt
 
 	SPT_HD V3 FresnelSchlick(float cosTheta, V3 F0)                            // :42-45
 	{
-		return F0 + (1.0f - F0) * powf(1.0f - cosTheta, 5.0f);
+		const float x = 1.0f - cosTheta, x2 = x * x;
+		return F0 + (1.0f - F0) * (x2 * x2 * x);                                   // pow(1 - cosTheta, 5.0f)
 	}
 
 	SPT_HD float GeometrySchlickGGX(float NdotV, float roughness)             // :47-52
@@ -81,7 +84,9 @@ namespace spt
 	// shared tail of the four ImportanceSample* functions (:162-249)
 	SPT_HD V3 ToWorld(float sinTheta, float cosTheta, float phi, V3 n)
 	{
-		const V3 h = v3(sinTheta * cosf(phi), sinTheta * sinf(phi), cosTheta);
+		float sp, cp;
+		sincosf(phi, &sp, &cp);
+		const V3 h = v3(sinTheta * cp, sinTheta * sp, cosTheta);
 		const V3 up = fabsf(n.z) < 0.999f ? v3(0.0f, 0.0f, 1.0f) : v3(1.0f, 0.0f, 0.0f);
 		const V3 tangent = normalize(cross(up, n));
 		const V3 bitangent = cross(n, tangent);
@@ -134,7 +139,8 @@ namespace spt
 		const float a = std_max(roughness * roughness, 0.001f);
 		const float NdotH = std_max(dot(N, H), 0.001f);
 		const float VdotH = std_max(dot(V, H), 0.001f);
-		const float D = (a * a) / (kPiGlm * powf(NdotH * NdotH * (a * a - 1.0f) + 1.0f, 2.0f));
+		const float dd = NdotH * NdotH * (a * a - 1.0f) + 1.0f;
+		const float D = (a * a) / (kPiGlm * (dd * dd));                              // pow(., 2.0f)
 		return D * NdotH / (4.0f * VdotH);
 	}
 
@@ -146,7 +152,8 @@ namespace spt
 		const float tanThetaH = sqrtf(1.0f - NdotH * NdotH) / NdotH;
 		const float tanThetaHSquared = tanThetaH * tanThetaH;
 		const float alphaSquared = alpha * alpha;
-		const float D = expf(-tanThetaHSquared / alphaSquared) / (kPiGlm * alphaSquared * powf(NdotH, 4.0f));
+		const float n2 = NdotH * NdotH;
+		const float D = expf(-tanThetaHSquared / alphaSquared) / (kPiGlm * alphaSquared * (n2 * n2));   // pow(NdotH, 4.0f)
 		return D * NdotH / (4.0f * VdotH);
 	}
 

@@ -58,7 +58,7 @@ namespace spt
 		DevBuf<uint32_t> counter;             // persistent-kernel work counters
 		SailorPtStats stats{};
 
-		BvhView View() const { BvhView v; v.nodes = tnodes.p; v.tris = ttris.p; v.rootRef = rootRef; return v; }
+		BvhView View() const { BvhView v; v.nodes = tnodes.p; v.tris = ttris.p; v.rootRef = rootRef; v.numNodes = numInternal; v.numTris = numTris; return v; }
 
 		int Fail(int code) { return code; }
 		int CudaStatus() { return ctx.ok ? SAILOR_PT_OK : SAILOR_PT_ERR_CUDA; }
@@ -206,7 +206,7 @@ namespace spt
 			if (!ctx.ok) return CudaStatus();
 			launch_for(ctx, nodesUsed, LeafCountAtSlotKernel{ s.left, s.count, refIdx.p, leafOffsetByRef.p, leafCountAtSlot.p });
 			launch_for(ctx, nodesUsed, PackNodesKernel{ s.left, rank.p, refIdx.p, leafOffsetByRef.p, s.aabb, tnodes.p });
-			launch_for(ctx, N, PackTrisKernel{ vtx.p, mapping.p, leafCountAtSlot.p, ttris.p });
+			launch_for(ctx, N, PackTrisKernel{ vtx.p, mapping.p, leafCountAtSlot.p, ttris.p, N });
 			rootRef = numInternal ? 0u : kLeafBit;      // a root that never split is one leaf at slot 0
 			stats.secondsBvhBuild = ctx.TimerStop();
 			stats.secondsTotal = HostNow() - t0;

@@ -58,7 +58,7 @@ namespace spt
 	struct PrimaryPassSource
 	{
 		PrimaryArgs a;
-		__device__ __forceinline__ bool Load(uint32_t g, V3& o, V3& d, uint32_t& ignore, float& maxLen) const
+		__device__ __forceinline__ bool Load(uint32_t g, V3& o, V3& d, uint32_t& ignore, float& maxLen, bool& anyHit) const
 		{
 			uint32_t x, y, sample;
 			if (!DecodePrimary(a, g, x, y, sample)) return false;
@@ -66,7 +66,7 @@ namespace spt
 			Rng rng; rng.key = PrimaryRngKey(a.seed, pixel, a.msaa, sample); rng.counter = 0;
 			float ox = 0.5f, oy = 0.5f;                                               // PathTracer.cpp:460
 			if (sample != 0) { ox = rng.Float01(); oy = rng.Float01(); }
-			o = a.cam.pos; d = PrimaryDir(a.cam, x, y, ox, oy); ignore = kNoHit; maxLen = kFltMax;
+			o = a.cam.pos; d = PrimaryDir(a.cam, x, y, ox, oy); ignore = kNoHit; maxLen = kFltMax; anyHit = false;
 			return true;
 		}
 	};
@@ -151,7 +151,7 @@ namespace spt
 		const uint64_t raysPer = lvl0 > lvl1 ? lvl0 : lvl1;
 		const uint64_t auxPer = lvl0 + kDepthFactor * lvl1;
 		const uint64_t recPer = 2u + kDepthFactor * S;
-		const uint64_t bytesPer = raysPer * (sizeof(RayRec) + sizeof(Hit)) + auxPer * (sizeof(RayAux) + 4u) + recPer * sizeof(NodeRec);
+		const uint64_t bytesPer = raysPer * (sizeof(RayRec) + sizeof(Hit)) + auxPer * sizeof(RayAux) + recPer * sizeof(NodeRec);
 		uint64_t budget = 6144ull << 20;
 		if (const char* e = getenv("SAILOR_PT_BATCH_MB")) { const long v = atol(e); if (v > 0) budget = (uint64_t)v << 20; }
 		uint64_t B = budget / bytesPer;
@@ -232,11 +232,12 @@ namespace spt
 				a.ambient = pa.ambient; a.seed = p.seed;
 				a.hitQueue = queue; a.queueBegin = done; a.queueCount = plan.firstHits;
 				a.recs = EnsureBytes<NodeRec>(ctx, D.renderMem[0], plan.recCap); a.recCap = plan.recCap;
-				a.aux = EnsureBytes<RayAux>(ctx, D.renderMem[1], plan.auxCap); a.auxOwner = EnsureBytes<uint32_t>(ctx, D.renderMem[8], plan.auxCap); a.auxCap = plan.auxCap;
+				a.aux = EnsureBytes<RayAux>(ctx, D.renderMem[1], plan.auxCap); a.auxCap = plan.auxCap; a.hasSky = hasSky ? 1u : 0u;
 				a.rays = EnsureBytes<RayRec>(ctx, D.renderMem[2], plan.rayCap); a.hits = EnsureBytes<Hit>(ctx, D.renderMem[3], plan.rayCap); a.rayCap = plan.rayCap;
 				a.skyCap = hasSky ? plan.skyCap : 16u;
 				a.sky[0] = EnsureBytes<SkyState>(ctx, D.renderMem[9], (size_t)a.skyCap * 2); a.sky[1] = a.sky[0] + a.skyCap;
 				a.skyRays = EnsureBytes<RayRec>(ctx, D.renderMem[10], (size_t)a.skyCap * 2); a.skyHits = EnsureBytes<Hit>(ctx, D.renderMem[11], a.skyCap);
+				a.fanCap = plan.firstHits + 1024u; a.fan = EnsureBytes<ShadeCtx>(ctx, D.renderMem[8], a.fanCap);
 				a.c = counters; a.sampleBuf = sampleBuf;
 				if (!ctx.ok) return SAILOR_PT_ERR_CUDA;
 
@@ -248,6 +249,7 @@ namespace spt
 					// upper bounds for the grid: level 0 is exact, deeper levels are bounded by the arenas
 					const uint32_t maxRecs = level == 0 ? plan.firstHits : plan.recCap;
 					launch_for_range(ctx, &L->recBegin, &L->recEnd, plan.recCap, maxRecs, ExpandKernel{ a, level });
+					launch_for_range(ctx, &counters->zero, &counters->fanThreads, a.fanCap * 32u, a.fanCap * 32u, FanOutKernel{ a, level });
 					tt.Begin(ctx);
 					LaunchTraceRays(ctx, view, a.rays, a.hits, plan.rayCap, D.counter.p, &L->rayCount);
 					tt.End(ctx);
@@ -271,7 +273,7 @@ namespace spt
 					const LevelInfo* L = &counters->level[level];
 					launch_for_range(ctx, &L->recBegin, &L->recEnd, plan.recCap, level == 0 ? plan.firstHits : plan.recCap, GatherKernel{ a });
 				}
-				struct { uint32_t recAlloc, auxAlloc, overflow, sky0, sky1, zero, pad0, pad1; unsigned long long rays; } head;
+				struct { uint32_t recAlloc, auxAlloc, overflow, sky0, sky1, zero, fanThreads, pad1; unsigned long long rays; } head;
 				DevDownload(ctx, &head, counters, sizeof(head));          // synchronises
 				if (!ctx.ok) break;
 				if (head.overflow)

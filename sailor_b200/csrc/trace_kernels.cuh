@@ -28,9 +28,22 @@ namespace spt
 	static_assert(sizeof(RayRec) == 32 && sizeof(Hit) == 16, "ray queue layout");
 
 #if !defined(SPT_EMU)
-	constexpr int kTraceBlock = 128;
-	constexpr int kSmemStack = 24;
-	constexpr uint32_t kFetchMinIdle = 8;
+	// tuning knobs (tools/trace_variants.py builds variants with -D to measure them on the GPU)
+#ifndef SPT_TRACE_BLOCK
+#define SPT_TRACE_BLOCK 128
+#endif
+#ifndef SPT_SMEM_STACK
+#define SPT_SMEM_STACK 24
+#endif
+#ifndef SPT_FETCH_MIN_IDLE
+#define SPT_FETCH_MIN_IDLE 8
+#endif
+#ifndef SPT_VOTE_LEAF_BIAS
+#define SPT_VOTE_LEAF_BIAS 1
+#endif
+	constexpr int kTraceBlock = SPT_TRACE_BLOCK;
+	constexpr int kSmemStack = SPT_SMEM_STACK;
+	constexpr uint32_t kFetchMinIdle = SPT_FETCH_MIN_IDLE;
 
 	struct SmemStack     // used by the one-ray-per-thread helpers (TraceClosest); whole stack in shared memory
 	{
@@ -53,60 +66,67 @@ namespace spt
 
 	__device__ __forceinline__ bool FiniteF(float f) { return (__float_as_uint(f) & 0x7F800000u) != 0x7F800000u; }
 
-	// The warp loop.  Source: bool Load(uint32_t index, V3& o, V3& d, uint32_t& ignore, float& maxLen) (false = nothing to
+	// The warp loop.  Source: bool Load(uint32_t index, V3& o, V3& d, uint32_t& ignore, float& maxLen, bool& anyHit) (false = nothing to
 	// trace at this index).  Sink: void Retire(bool finished, uint32_t index, const Hit&) called by ALL lanes each iteration.
+	// Lane state is one word: kLaneIdle, an inner node index, or kLeafBit | triangle slot (the next triangle to test).
+#ifndef SPT_VOTE_INNER_BIAS
+#define SPT_VOTE_INNER_BIAS 1      // inner step when nInner * bias >= nLeaf
+#endif
+	constexpr uint32_t kLaneIdle = 0xFFFFFFFFu;
+
 	template<class Source, class Sink>
 	__device__ __forceinline__ void TraceWarpLoop(const BvhView& bvh, uint32_t n, uint32_t* __restrict__ counter, uint32_t* stackMem, Source& src, Sink& sink)
 	{
-		uint32_t* const sbase = stackMem + threadIdx.x;
+		// 32-bit shared-window address of this lane's stack column: [entry][thread], 4-byte entries
+		const uint32_t sAddr = (uint32_t)__cvta_generic_to_shared(stackMem) + threadIdx.x * 4u;
 		uint32_t ovf[kStackDepth - kSmemStack];
 		const uint32_t lane = threadIdx.x & 31;
-		enum : uint32_t { kIdle = 0, kInner = 1, kLeaf = 2 };
-		uint32_t mode = kIdle;
 		V3 o = v3(0.0f), d = v3(0.0f), rD = v3(0.0f);
 		float maxLen = 0.0f; uint32_t ignore = kNoHit, index = 0;
-		bool safe = false;
+		bool safe = false, anyHit = false;
 		Hit hit; hit.t = 0.0f; hit.u = 0.0f; hit.v = 0.0f; hit.tri = kNoHit;
-		uint32_t cur = 0, triLeft = 0;
+		uint32_t cur = kLaneIdle;
 		int sp = 0;
 		bool exhausted = false;
 
 		for (;;)
 		{
 			// ---- refill idle lanes -------------------------------------------------------------------------
-			const uint32_t idleMask = __ballot_sync(0xffffffffu, mode == kIdle);
-			if (idleMask == 0xffffffffu && exhausted) break;
-			if (!exhausted && (__popc(idleMask) >= (int)kFetchMinIdle))
+			const uint32_t idleMask = __ballot_sync(0xffffffffu, cur == kLaneIdle);
+			if (idleMask)
 			{
-				const uint32_t want = (uint32_t)__popc(idleMask);
-				uint32_t base = 0;
-				if (lane == 0) base = atomicAdd(counter, want);
-				base = __shfl_sync(0xffffffffu, base, 0);
-				if (base + want >= n) exhausted = true;
-				if (mode == kIdle)
+				if (!exhausted && (__popc(idleMask) >= (int)kFetchMinIdle))
 				{
-					const uint32_t i = base + (uint32_t)__popc(idleMask & ((1u << lane) - 1u));
-					if (i < n && src.Load(i, o, d, ignore, maxLen))
+					const uint32_t want = (uint32_t)__popc(idleMask);
+					uint32_t base = 0;
+					if (lane == 0) base = atomicAdd(counter, want);
+					base = __shfl_sync(0xffffffffu, base, 0);
+					if (base + want >= n) exhausted = true;
+					if (cur == kLaneIdle)
 					{
-						index = i;
-						rD = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);          // Ray::SetDirection (Bounds.h:44-48)
-						safe = FiniteF(rD.x) && FiniteF(rD.y) && FiniteF(rD.z) && FiniteF(o.x) && FiniteF(o.y) && FiniteF(o.z);
-						hit.t = u2f(0x7F800000u); hit.u = 0.0f; hit.v = 0.0f; hit.tri = kNoHit;
-						sp = 0;
-						cur = bvh.rootRef;
-						if (cur & kLeafBit) { mode = kLeaf; cur &= ~kLeafBit; triLeft = 0xFFFFFFFFu; } else mode = kInner;
+						const uint32_t i = base + (uint32_t)__popc(idleMask & ((1u << lane) - 1u));
+						if (i < n && src.Load(i, o, d, ignore, maxLen, anyHit))
+						{
+							index = i;
+							rD = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);          // Ray::SetDirection (Bounds.h:44-48)
+							safe = FiniteF(rD.x) && FiniteF(rD.y) && FiniteF(rD.z) && FiniteF(o.x) && FiniteF(o.y) && FiniteF(o.z);
+							hit.t = u2f(0x7F800000u); hit.u = 0.0f; hit.v = 0.0f; hit.tri = kNoHit;
+							sp = 0;
+							cur = bvh.rootRef;
+						}
 					}
+					continue;
 				}
-				continue;
+				if (idleMask == 0xffffffffu) break;          // queue exhausted and every lane retired
 			}
 			// ---- vote: the step most busy lanes need --------------------------------------------------------
-			const uint32_t innerMask = __ballot_sync(0xffffffffu, mode == kInner);
-			const uint32_t leafMask = __ballot_sync(0xffffffffu, mode == kLeaf);
-			bool finished = false;
-			uint32_t next = 0; bool havePopOrNext = false;      // next node reference for this lane after the step
-			if (__popc(innerMask) >= __popc(leafMask))
+			const bool isLeaf = (cur & kLeafBit) && cur != kLaneIdle;
+			const uint32_t leafMask = __ballot_sync(0xffffffffu, isLeaf);
+			const int nLeaf = __popc(leafMask), nInner = 32 - __popc(idleMask) - nLeaf;
+			bool pop = false;
+			if (nInner * SPT_VOTE_INNER_BIAS >= nLeaf * SPT_VOTE_LEAF_BIAS)
 			{
-				if (mode == kInner)
+				if (!(cur & kLeafBit))
 				{
 					const TNode* nd = bvh.nodes + cur;
 					const V4 q0 = ld4(&nd->q0), q1 = ld4(&nd->q1), q2 = ld4(&nd->q2);
@@ -124,21 +144,25 @@ namespace spt
 						d2 = SlabTest(o, rD, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, maxLen);
 					}
 					if (d1 > d2) { const float tf = d1; d1 = d2; d2 = tf; const uint32_t tc = c1; c1 = c2; c2 = tc; }   // BVH.cpp:163-167
-					if (d1 == kFltMax) havePopOrNext = false;               // both missed: pop
+					if (d1 == kFltMax) pop = true;                              // both children missed
 					else
 					{
-						next = c1; havePopOrNext = true;
-						if (d2 != kFltMax) { if (sp < kSmemStack) sbase[sp * kTraceBlock] = c2; else ovf[sp - kSmemStack] = c2; sp++; }
+						cur = c1;
+						if (d2 != kFltMax)
+						{
+							if (sp < kSmemStack) asm volatile("st.shared.u32 [%0], %1;" :: "r"(sAddr + (uint32_t)sp * (kTraceBlock * 4u)), "r"(c2) : "memory");
+							else ovf[sp - kSmemStack] = c2;
+							sp++;
+						}
 					}
 				}
 			}
 			else
 			{
-				if (mode == kLeaf)
+				if (isLeaf)
 				{
-					const TTri* T = bvh.tris + cur;
+					const TTri* T = bvh.tris + (cur & ~kLeafBit);
 					const V4 a = ld4(&T->a), b = ld4(&T->b), c = ld4(&T->c);
-					if (triLeft == 0xFFFFFFFFu) triLeft = f2u(c.z);           // the leaf's size sits in its first record
 					const uint32_t triId = f2u(c.y);
 					if (ignore != triId)                                       // BVH.cpp:136-139
 					{
@@ -147,30 +171,23 @@ namespace spt
 						{
 							hit.t = t; hit.u = u; hit.v = v; hit.tri = triId;
 							maxLen = std_min(maxLen, t);
+							if (anyHit) { sp = 0; pop = true; }                     // hit-or-miss query: done
 						}
 					}
-					cur++; triLeft--;
-					if (triLeft != 0) { next = cur | kLeafBit; havePopOrNext = true; }
+					if (f2u(c.w)) pop = true;                                   // last triangle of its leaf
+					else cur++;
 				}
 			}
-			// ---- move on: descend / next triangle / pop / finish --------------------------------------------
-			const bool stepped = ((__popc(innerMask) >= __popc(leafMask)) ? (mode == kInner) : (mode == kLeaf));
-			if (stepped)
+			// ---- pop / retire -------------------------------------------------------------------------------
+			bool finished = false;
+			if (pop)
 			{
-				if (!havePopOrNext)
+				if (sp == 0) { finished = true; cur = kLaneIdle; }
+				else
 				{
-					if (sp == 0) { finished = true; mode = kIdle; }
-					else { sp--; next = sp < kSmemStack ? sbase[sp * kTraceBlock] : ovf[sp - kSmemStack]; havePopOrNext = true; }
-				}
-				if (havePopOrNext)
-				{
-					if (next & kLeafBit)
-					{
-						const bool sameLeaf = mode == kLeaf && triLeft != 0 && (next & ~kLeafBit) == cur;
-						if (!sameLeaf) triLeft = 0xFFFFFFFFu;
-						mode = kLeaf; cur = next & ~kLeafBit;
-					}
-					else { mode = kInner; cur = next; }
+					sp--;
+					if (sp < kSmemStack) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cur) : "r"(sAddr + (uint32_t)sp * (kTraceBlock * 4u)) : "memory");
+					else cur = ovf[sp - kSmemStack];
 				}
 			}
 			sink.Retire(finished, index, hit);
@@ -181,12 +198,13 @@ namespace spt
 	struct QueueSource
 	{
 		const RayRec* rays;
-		__device__ __forceinline__ bool Load(uint32_t i, V3& o, V3& d, uint32_t& ignore, float& maxLen) const
+		__device__ __forceinline__ bool Load(uint32_t i, V3& o, V3& d, uint32_t& ignore, float& maxLen, bool& anyHit) const
 		{
 			const float4 r0 = __ldg(reinterpret_cast<const float4*>(rays + i));
 			const float4 r1 = __ldg(reinterpret_cast<const float4*>(rays + i) + 1);
-			if (r1.w < 0.0f) return false;     // inactive queue entry
-			o = v3(r0.x, r0.y, r0.z); ignore = __float_as_uint(r0.w); d = v3(r1.x, r1.y, r1.z); maxLen = r1.w;
+			if (r1.w == -1.0f) return false;   // inactive queue entry
+			o = v3(r0.x, r0.y, r0.z); ignore = __float_as_uint(r0.w); d = v3(r1.x, r1.y, r1.z);
+			anyHit = r1.w < 0.0f; maxLen = fabsf(r1.w);
 			return true;
 		}
 	};
@@ -209,6 +227,98 @@ namespace spt
 		TraceWarpLoop(bvh, n, counter, stackMem, src, sink);
 	}
 
+	// ---- small scenes: the whole traversal layout lives in shared memory --------------------------------------------
+	// A scene of a few hundred triangles (BASELINE config C1/C2 is a 12-triangle cube) has no memory problem to solve: the
+	// node and triangle records are copied into shared memory once per CTA and every thread walks its own ray with the
+	// reference's loop (TraceClosest's order), grid-stride over the queue.  Nothing is voted or refilled because a ray
+	// lives for a handful of steps.
+	constexpr uint32_t kSmallSceneBytes = 40u * 1024u;
+	constexpr int kSmallBlock = 256;
+
+	__global__ void __launch_bounds__(kSmallBlock) k_trace_rays_small(const TNode* __restrict__ gNodes, uint32_t numNodes, const TTri* __restrict__ gTris, uint32_t numTris,
+		uint32_t rootRef, const RayRec* __restrict__ rays, Hit* __restrict__ hits, uint32_t n, const uint32_t* __restrict__ nPtr)
+	{
+		extern __shared__ __align__(16) unsigned char smallMem[];
+		V4* sNodes = reinterpret_cast<V4*>(smallMem);                         // 4 x V4 per node
+		V4* sTris = sNodes + (size_t)numNodes * 4;                            // 3 x V4 per triangle
+		{
+			const V4* gn = reinterpret_cast<const V4*>(gNodes); const V4* gt = reinterpret_cast<const V4*>(gTris);
+			for (uint32_t i = threadIdx.x; i < numNodes * 4u; i += kSmallBlock) sNodes[i] = ld4(gn + i);
+			for (uint32_t i = threadIdx.x; i < numTris * 3u; i += kSmallBlock) sTris[i] = ld4(gt + i);
+		}
+		__syncthreads();
+		if (nPtr) { const uint32_t m = *nPtr; if (m < n) n = m; }
+		uint32_t stack[kStackDepth];
+		for (uint32_t i = blockIdx.x * kSmallBlock + threadIdx.x; i < n; i += gridDim.x * kSmallBlock)
+		{
+			const float4 r0 = __ldg(reinterpret_cast<const float4*>(rays + i));
+			const float4 r1 = __ldg(reinterpret_cast<const float4*>(rays + i) + 1);
+			if (r1.w == -1.0f) continue;                                       // inactive queue entry
+			const V3 o = v3(r0.x, r0.y, r0.z), d = v3(r1.x, r1.y, r1.z);
+			const uint32_t ignore = __float_as_uint(r0.w);
+			const bool anyHit = r1.w < 0.0f;
+			float maxLen = fabsf(r1.w);
+			const V3 rD = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);            // Ray::SetDirection (Bounds.h:44-48)
+			const bool safe = FiniteF(rD.x) && FiniteF(rD.y) && FiniteF(rD.z) && FiniteF(o.x) && FiniteF(o.y) && FiniteF(o.z);
+			Hit hit; hit.t = u2f(0x7F800000u); hit.u = 0.0f; hit.v = 0.0f; hit.tri = kNoHit;
+			uint32_t cur = rootRef; int sp = 0;
+			for (;;)                                                           // BVH.cpp:128-189
+			{
+				if (cur & kLeafBit)
+				{
+					const V4* T = sTris + (size_t)(cur & ~kLeafBit) * 3;
+					bool done = false;
+					for (;;)
+					{
+						const V4 a = T[0], b = T[1], c = T[2];
+						const uint32_t triId = f2u(c.y);
+						if (ignore != triId)
+						{
+							float t, u, v;
+							if (TriTest(o, d, v3(a.x, a.y, a.z), v3(a.w, b.x, b.y), v3(b.z, b.w, c.x), maxLen, t, u, v))
+							{
+								hit.t = t; hit.u = u; hit.v = v; hit.tri = triId;
+								maxLen = std_min(maxLen, t);
+								if (anyHit) { done = true; break; }
+							}
+						}
+						if (f2u(c.w)) break;
+						T += 3;
+					}
+					if (done || sp == 0) break;
+					cur = stack[--sp];
+					continue;
+				}
+				const V4* nd = sNodes + (size_t)cur * 4;
+				const V4 q0 = nd[0], q1 = nd[1], q2 = nd[2], q3 = nd[3];
+				uint32_t c1 = f2u(q3.x), c2 = f2u(q3.y);
+				float d1, d2;
+				if (safe)
+				{
+					d1 = SlabTestFast(o, rD, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, maxLen);
+					d2 = SlabTestFast(o, rD, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, maxLen);
+				}
+				else
+				{
+					d1 = SlabTest(o, rD, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, maxLen);
+					d2 = SlabTest(o, rD, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, maxLen);
+				}
+				if (d1 > d2) { const float tf = d1; d1 = d2; d2 = tf; const uint32_t tc = c1; c1 = c2; c2 = tc; }
+				if (d1 == kFltMax)
+				{
+					if (sp == 0) break;
+					cur = stack[--sp];
+				}
+				else
+				{
+					cur = c1;
+					if (d2 != kFltMax) stack[sp++] = c2;
+				}
+			}
+			*reinterpret_cast<float4*>(hits + i) = make_float4(hit.t, hit.u, hit.v, __uint_as_float(hit.tri));
+		}
+	}
+
 	// primary rays of sample 0 generated in-kernel (no ray queue traffic): work index -> 8x4 pixel tile + lane
 	struct PrimarySource
 	{
@@ -218,11 +328,11 @@ namespace spt
 			const uint32_t tile = i >> 5, l = i & 31u;
 			x = (tile % tilesX) * 8u + (l & 7u); y = (tile / tilesX) * 4u + (l >> 3);
 		}
-		__device__ __forceinline__ bool Load(uint32_t i, V3& o, V3& d, uint32_t& ignore, float& maxLen) const
+		__device__ __forceinline__ bool Load(uint32_t i, V3& o, V3& d, uint32_t& ignore, float& maxLen, bool& anyHit) const
 		{
 			uint32_t x, y; Pixel(i, x, y);
 			if (x >= cam.width || y >= cam.height) return false;
-			o = cam.pos; d = PrimaryDir(cam, x, y, 0.5f, 0.5f); ignore = kNoHit; maxLen = kFltMax;
+			o = cam.pos; d = PrimaryDir(cam, x, y, 0.5f, 0.5f); ignore = kNoHit; maxLen = kFltMax; anyHit = false;
 			return true;
 		}
 	};
@@ -263,6 +373,19 @@ namespace spt
 	inline void LaunchTraceRays(Ctx& ctx, const BvhView& bvh, const RayRec* rays, Hit* hits, uint32_t n, uint32_t* counter, const uint32_t* nPtr = nullptr)
 	{
 		if (!n || !ctx.ok) return;
+		const size_t smallBytes = (size_t)bvh.numNodes * sizeof(TNode) + (size_t)bvh.numTris * sizeof(TTri);
+		if (smallBytes <= kSmallSceneBytes)
+		{
+			static bool attr = false;
+			if (!attr) { cudaFuncSetAttribute(k_trace_rays_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSceneBytes); attr = true; }
+			uint32_t blocks = (n + kSmallBlock - 1) / kSmallBlock;
+			const uint32_t lim = (uint32_t)RangeGridBlocks();
+			if (blocks > lim) blocks = lim;
+			k_trace_rays_small<<<blocks, kSmallBlock, smallBytes, ctx.stream>>>(bvh.nodes, bvh.numNodes, bvh.tris, bvh.numTris, bvh.rootRef, rays, hits, n, nPtr);
+			ctx.kernelLaunches++;
+			SPT_CUDA_CHECK(ctx, cudaGetLastError());
+			return;
+		}
 		DevMemset(ctx, counter, 0, sizeof(uint32_t));
 		k_trace_rays<<<TraceGridSize(), kTraceBlock, 0, ctx.stream>>>(bvh, rays, hits, n, nPtr, counter);
 		ctx.kernelLaunches++;
@@ -283,7 +406,7 @@ namespace spt
 		LocalStack st;
 		if (nPtr && *nPtr < n) n = *nPtr;
 		for (uint32_t i = 0; i < n; i++)
-			if (!(rays[i].tmax < 0.0f)) TraceClosest(bvh, v3(rays[i].ox, rays[i].oy, rays[i].oz), v3(rays[i].dx, rays[i].dy, rays[i].dz), rays[i].ignoreTri, rays[i].tmax, st, hits[i]);
+			if (rays[i].tmax != -1.0f) TraceClosest(bvh, v3(rays[i].ox, rays[i].oy, rays[i].oz), v3(rays[i].dx, rays[i].dy, rays[i].dz), rays[i].ignoreTri, fabsf(rays[i].tmax), st, hits[i]);
 		ctx.kernelLaunches++;
 	}
 	inline void LaunchTracePrimary(Ctx& ctx, const BvhView& bvh, const CameraGpu& cam, Hit* hits, uint32_t*)

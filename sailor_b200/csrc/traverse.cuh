@@ -20,14 +20,14 @@
 namespace spt
 {
 	struct alignas(16) TNode { V4 q0, q1, q2; uint32_t left, right, pad0, pad1; };
-	struct alignas(16) TTri { V4 a, b, c; };   // a=(v0, e1.x) b=(e1.y,e1.z,e2.x,e2.y) c=(e2.z, bits(triId), bits(leafCount), 0)
+	struct alignas(16) TTri { V4 a, b, c; };   // a=(v0, e1.x) b=(e1.y,e1.z,e2.x,e2.y) c=(e2.z, bits(triId), bits(leafCount), bits(lastInLeaf))
 	static_assert(sizeof(TNode) == 64 && sizeof(TTri) == 48, "traversal layout");
 
 	constexpr uint32_t kLeafBit = 0x80000000u;
 	constexpr uint32_t kNoHit = 0xFFFFFFFFu;
 	constexpr int kStackDepth = 64;               // BVH.cpp:126
 
-	struct BvhView { const TNode* nodes; const TTri* tris; uint32_t rootRef; };
+	struct BvhView { const TNode* nodes; const TTri* tris; uint32_t rootRef; uint32_t numNodes, numTris; };
 	struct Hit { float t, u, v; uint32_t tri; };
 
 	// Math::IntersectRayAABB (Bounds.cpp:582-604). _mm_max_ps/_mm_min_ps return the SECOND operand on NaN.
@@ -164,7 +164,7 @@ namespace spt
 
 	struct PackTrisKernel    // one thread per triangle slot in leaf order
 	{
-		const V4* vtx; const uint32_t* mapping; const uint32_t* leafCountAtSlot; TTri* out;
+		const V4* vtx; const uint32_t* mapping; const uint32_t* leafCountAtSlot; TTri* out; uint32_t numTris;
 		SPT_KERNEL_BODY void operator()(uint32_t slot) const
 		{
 			const uint32_t tri = mapping[slot];
@@ -172,7 +172,9 @@ namespace spt
 			const V3 e1 = v3(v1.x - v0.x, v1.y - v0.y, v1.z - v0.z), e2 = v3(v2.x - v0.x, v2.y - v0.y, v2.z - v0.z);
 			TTri t;
 			t.a = v4(v0.x, v0.y, v0.z, e1.x); t.b = v4(e1.y, e1.z, e2.x, e2.y);
-			t.c = v4(e2.z, u2f(tri), u2f(leafCountAtSlot[slot]), 0.0f);
+			// c.z: size of the leaf (at its first slot, else 0); c.w: 1 on the last triangle of a leaf (the next slot starts a leaf)
+			const uint32_t last = (slot + 1u == numTris || leafCountAtSlot[slot + 1u] != 0u) ? 1u : 0u;
+			t.c = v4(e2.z, u2f(tri), u2f(leafCountAtSlot[slot]), u2f(last));
 			out[slot] = t;
 		}
 	};
