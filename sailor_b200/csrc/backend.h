@@ -122,8 +122,9 @@ namespace spt
 	// The wavefront levels are sized by device-side counters; reading them here would cost a host round trip per level,
 	// so the grid is fixed (a few CTAs per SM, grid-stride) and the kernel fetches its own range.
 #if !defined(SPT_EMU)
-	template<class F>
-	__global__ void __launch_bounds__(256) k_for_range(const uint32_t* __restrict__ begin, const uint32_t* __restrict__ end, uint32_t cap, F f)
+	// MinBlocks: occupancy hint (caps registers per thread) for the register-hungry shading functors
+	template<class F, int MinBlocks>
+	__global__ void __launch_bounds__(256, MinBlocks) k_for_range(const uint32_t* __restrict__ begin, const uint32_t* __restrict__ end, uint32_t cap, F f)
 	{
 		const uint32_t b = *begin;
 		uint32_t e = *end; if (e > cap) e = cap;
@@ -132,19 +133,19 @@ namespace spt
 
 	int RangeGridBlocks();    // SMs x 8
 
-	template<class F>
+	template<int MinBlocks = 1, class F>
 	inline void launch_for_range(Ctx& ctx, const uint32_t* dBegin, const uint32_t* dEnd, uint32_t cap, uint32_t maxCount, const F& f)
 	{
 		if (!maxCount || !ctx.ok) return;
 		uint32_t blocks = (maxCount + 255u) / 256u;
 		const uint32_t lim = (uint32_t)RangeGridBlocks();
 		if (blocks > lim) blocks = lim;
-		k_for_range<F><<<blocks, 256, 0, ctx.stream>>>(dBegin, dEnd, cap, f);
+		k_for_range<F, MinBlocks><<<blocks, 256, 0, ctx.stream>>>(dBegin, dEnd, cap, f);
 		ctx.kernelLaunches++;
 		SPT_CUDA_CHECK(ctx, cudaGetLastError());
 	}
 #else
-	template<class F>
+	template<int MinBlocks = 1, class F>
 	inline void launch_for_range(Ctx& ctx, const uint32_t* dBegin, const uint32_t* dEnd, uint32_t cap, uint32_t, const F& f)
 	{
 		if (!ctx.ok) return;

@@ -77,15 +77,13 @@ namespace spt
 	};
 	static_assert(sizeof(NodeRec) == 128, "NodeRec layout");
 
-	// ray kinds (RayAux::tag low 3 bits) and state bits
+	// ray kinds (RayAux::tag low 3 bits) and state bits.  Whether a ray hit anything is NOT in the tag: the trace kernel writes
+	// one status byte per ray (IntegratorArgs::status), so rays that only need hit-or-miss are never touched again until gather.
 	enum : uint32_t
 	{
 		kRkInactive = 0, kRkLight = 1, kRkHemi = 2, kRkSample = 3, kRkOwn = 4, kRkMask = 7u,
-		kRsBlocked = 8u,        // light: shadow ray hit something
 		kRsTransRay = 16u,      // sample: bTransmissionRay
-		kRsMiss = 32u,          // sample / hemi: the ray missed; gather evaluates clamp(term*ambient) / the unattenuated sky term itself
 		kRsHit = 64u,           // sample: hit with bounceLimit > 0 -> a = clamp(term*att*L) (written by the child's gather, or by classify when no child runs)
-		kRsHit0 = 128u,         // sample: hit with bounceLimit == 0 (:835 only)
 		kRsSky2 = 256u,         // sample: TraceSky behind the hit returned non-zero -> b = att (:825-831); hemi: a = final contribution of a sky walk
 		kRsSkipped = 512u,      // sample: rejection budget exhausted
 	};
@@ -121,7 +119,7 @@ namespace spt
 		uint32_t skyCount[2];      // ping-pong sky queues
 		uint32_t zero;             // always 0 (range begin)
 		uint32_t fanThreads;       // 32 x activations handed to FanOutKernel at the current level
-		uint32_t pad;
+		uint32_t slowCount;        // rays of the current level whose closest hit needs ClassifyKernel
 		unsigned long long rays;   // closest-hit queries of the batch
 		LevelInfo level[66];
 	};
@@ -138,7 +136,8 @@ namespace spt
 		const PrimaryHitRec* hitQueue; uint32_t queueBegin, queueCount;     // first hits [queueBegin, queueBegin+queueCount) are level 0
 		NodeRec* recs; uint32_t recCap;
 		RayAux* aux; uint32_t auxCap; uint32_t hasSky;                       // hasSky: the scene has thick transmissive materials (TraceSky can continue)
-		RayRec* rays; Hit* hits; uint32_t rayCap;                             // ray queue of the current level
+		RayRec* rays; Hit* hits; uint32_t rayCap;                             // ray queue of the current level (hits: only rays on the slow list)
+		uint8_t* status; uint32_t* slowList;                                  // per RayAux: 1 = the ray hit something (written by the trace kernel); level-local indices of rays for ClassifyKernel
 		SkyState* sky[2]; RayRec* skyRays; Hit* skyHits; uint32_t skyCap;
 		ShadeCtx* fan; uint32_t fanCap;                                       // activations whose samples are produced by FanOutKernel
 		BatchCounters* c;
@@ -409,10 +408,10 @@ namespace spt
 			NodeRec c;
 			c.rayO = o; c.parent = self; c.rayD = d; c.parentAux = kNone;
 			c.t = 0.0f; c.u = 0.0f; c.v = 0.0f; c.tri = kNoHit;
-			c.inAcc = inAcc; c.envIor = envIor; c.bounces = bounceLimit | (pMaxBounces << 16); c.flags = 0;
+			c.inAcc = inAcc; c.envIor = envIor; c.bounces = bounceLimit | (pMaxBounces << 16); c.flags = kNfDone;   // a miss is final (:873-876); a hit clears kNfDone (ClassifyKernel)
 			c.rngKey = ChildRngKey(n.rngKey, slot); c.auxBase = 0; c.child = kNone;
 			c.pNumSamples = pNumSamples; c.pNumAmbient = pNumAmbient; c.nA = 0; c.nS = 0;
-			c.emissive = v3(0.0f); c.alpha = 1.0f; c.result = v3(0.0f); c.nLights = 0;
+			c.emissive = v3(0.0f); c.alpha = 1.0f; c.result = a.ambient; c.nLights = 0;
 			a.recs[ci] = c;
 			return ci;
 		}
@@ -593,32 +592,22 @@ namespace spt
 	};
 
 	// ---- classify: fold one ray's closest hit into its RayAux, spawn the child activation of an importance hit --------
-	struct ClassifyKernel
+	struct ClassifyKernel            // one thread per entry of the level's slow list
 	{
 		IntegratorArgs a; uint32_t level;
-		SPT_KERNEL_BODY void operator()(uint32_t i) const
+		SPT_KERNEL_BODY void operator()(uint32_t k) const
 		{
+			const uint32_t i = a.slowList[k];
 			const uint32_t g = a.c->level[level].auxBase + i;
-			// fast paths touch only the tag word and the hit's triangle id: most rays are final after one comparison
-			const uint32_t tag = a.aux[g].tag;
-			const uint32_t kind = tag & kRkMask;
-			if (kind == kRkInactive) return;
-			const uint32_t hitTri = a.hits[i].tri;
-			if (kind == kRkLight)
-			{
-				if (hitTri != kNoHit) a.aux[g].tag = tag | kRsBlocked;                   // :699
-				return;
-			}
-			if (hitTri == kNoHit && kind != kRkOwn) { a.aux[g].tag = tag | kRsMiss; return; }   // hemi: TraceSky returns att = 1 (:587-590); sample: :786-796
-			if (kind == kRkHemi && !a.hasSky) return;                                    // hit something opaque: TraceSky returns 0 (:597-600)
 			RayAux x = a.aux[g];
+			const uint32_t kind = x.tag & kRkMask;
 			const Hit h = a.hits[i];
+			if (kind == kRkInactive || kind == kRkLight || h.tri == kNoHit) return;      // cannot be on the list
 			const uint32_t owner = f2u(x.b1);
 			if (kind == kRkOwn)
 			{
-				NodeRec* c = a.recs + owner;
-				if (h.tri == kNoHit) { c->result = a.ambient; c->flags |= kNfDone; }     // :873-876
-				else { c->t = h.t; c->u = h.u; c->v = h.v; c->tri = h.tri; }
+				NodeRec* c = a.recs + owner;                                              // the child activation has its closest hit now
+				c->t = h.t; c->u = h.u; c->v = h.v; c->tri = h.tri; c->flags &= ~kNfDone;
 				return;
 			}
 			const RayRec ray = a.rays[i];
@@ -637,7 +626,7 @@ namespace spt
 			const V3 term = v3(x.a0, x.a1, x.a2);
 			const NodeRec* o = a.recs + owner;
 			const uint32_t bounceLimit = o->bounces & 0xFFFFu, pMaxBounces = o->bounces >> 16;
-			if (bounceLimit == 0) { a.aux[g].tag = x.tag | kRsHit0; return; }            // :797, :835
+			if (bounceLimit == 0) return;                                                // :797, :835 (such rays are boolean and never get here)
 			const uint32_t oflags = o->flags;
 			V3 att = v3(1.0f);
 			if ((oflags & kNfOpposite) && (x.tag & kRsTransRay) && (oflags & kNfThick))  // :801-807
@@ -721,9 +710,8 @@ namespace spt
 				bool blocked = false;                                                     // stale hitLight (:694)
 				for (uint32_t j = 0; j < nLights; j++, g++)
 				{
-					const RayAux x = a.aux[g];
-					if (x.tag & kRsBlocked) blocked = true;
-					if (!blocked) res = res + v3(x.a0, x.a1, x.a2);
+					if (a.status[g]) blocked = true;                                       // :699
+					if (!blocked) { const RayAux x = a.aux[g]; res = res + v3(x.a0, x.a1, x.a2); }
 				}
 				if (flags & kNfAmbientOn)
 				{
@@ -734,8 +722,9 @@ namespace spt
 						for (uint32_t k = 0; k < nA; k++, g++)
 						{
 							const RayAux x = a.aux[g];
+							if ((x.tag & kRkMask) != kRkHemi) continue;                                                       // dead ray (maxBounces == 0)
 							if (x.tag & kRsSky2) amb1 = amb1 + v3(x.a0, x.a1, x.a2);                                          // a sky walk ended (:730-735)
-							else if (x.tag & kRsMiss) amb1 = amb1 + glm_clamp((v3(x.a0, x.a1, x.a2) * a.ambient * x.a3) / pdfHemisphere, 0.0f, 10.0f);   // att = 1
+							else if (!a.status[g]) amb1 = amb1 + glm_clamp((v3(x.a0, x.a1, x.a2) * a.ambient * x.a3) / pdfHemisphere, 0.0f, 10.0f);   // miss: att = 1 (:587-590)
 						}
 					}
 					amb1 = amb1 / (float)nA;                                              // :739
@@ -745,12 +734,18 @@ namespace spt
 						const RayAux x = a.aux[g];
 						if (x.tag & kRsSkipped) continue;
 						V3 value = v3(x.a0, x.a1, x.a2);
-						if (x.tag & kRsMiss) { value = glm_clamp(value * a.ambient, 0.0f, 10.0f); amb2 = amb2 + value; avgPdf += x.a3; indirect = indirect + value; }   // :786-796
-						else if (x.tag & kRsHit)                                                                          // :816-832
+						if (!a.status[g])                                                                                 // miss (:786-796)
+						{
+							value = glm_clamp(value * a.ambient, 0.0f, 10.0f);
+							amb2 = amb2 + value; avgPdf += x.a3; indirect = indirect + value;
+						}
+						else if (x.tag & kRsHit)                                                                          // :816-832, value = clamp(term*att*L)
 						{
 							indirect = indirect + value;
 							if (x.tag & kRsSky2) { amb2 = amb2 + value * v3(x.b0, x.b1, x.b2); avgPdf += x.a3; }
 						}
+						else if ((rec->bounces & 0xFFFFu) > 0)                                                            // boolean ray below the 0.01 cut: raytraced = 0 (:809,:816)
+							indirect = indirect + glm_clamp(value * v3(0.0f), 0.0f, 10.0f);
 						cnt += 1.0f;                                                                                      // :835
 					}
 					amb2 = amb2 / cnt; avgPdf = avgPdf / cnt;                             // :838-839
@@ -794,7 +789,7 @@ namespace spt
 		BatchCounters* c; uint32_t count;
 		SPT_KERNEL_BODY void operator()(uint32_t) const
 		{
-			c->recAlloc = count; c->auxAlloc = 0; c->overflow = 0; c->skyCount[0] = c->skyCount[1] = 0; c->zero = 0; c->fanThreads = 0; c->rays = 0;
+			c->recAlloc = count; c->auxAlloc = 0; c->overflow = 0; c->skyCount[0] = c->skyCount[1] = 0; c->zero = 0; c->fanThreads = 0; c->slowCount = 0; c->rays = 0;
 			c->level[0].recBegin = 0; c->level[0].recEnd = count; c->level[0].rayCount = 0; c->level[0].auxBase = 0;
 		}
 	};
@@ -808,7 +803,7 @@ namespace spt
 			c->level[level + 1] = nx;
 			c->auxAlloc = nx.auxBase;
 			c->rays += cur.rayCount;
-			c->fanThreads = 0;
+			c->fanThreads = 0; c->slowCount = 0;
 		}
 	};
 	struct SkySwapKernel         // after a sky iteration: queue q is consumed

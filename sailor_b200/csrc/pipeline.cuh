@@ -47,9 +47,9 @@ namespace spt
 		DevBuf<float> residentLin; DevBuf<uint8_t> residentSrgb; uint32_t residentW = 0, residentH = 0;
 
 		// wavefront working set, kept across renders (only ever grows): 0 activation records, 1 RayAux arena, 2 rays,
-		// 3 hits, 4 per-sample results, 5 primary-hit queue, 6 batch counters, 7 blue-noise table, 8 RayAux owners,
-		// 9 sky states, 10 sky rays, 11 sky hits
-		DevBuf<unsigned char> renderMem[12];
+		// 3 hits, 4 per-sample results, 5 primary-hit queue, 6 batch counters, 7 blue-noise table, 8 fan-out contexts,
+		// 9 sky states, 10 sky rays, 11 sky hits, 12 ray status bytes, 13 slow list
+		DevBuf<unsigned char> renderMem[14];
 		SpanTimer traceTimer;
 		// BVH build scratch, kept across builds
 		DevBuf<uint32_t> buildU32[24];

@@ -13,6 +13,10 @@
 #pragma once
 #include "integrator.cuh"
 
+#ifndef SPT_FAN_MIN_BLOCKS
+#define SPT_FAN_MIN_BLOCKS 3
+#endif
+
 namespace spt
 {
 	struct PrimaryArgs
@@ -73,7 +77,7 @@ namespace spt
 	struct PrimaryPassSink
 	{
 		PrimaryArgs a;
-		__device__ __forceinline__ void Retire(bool finished, uint32_t g, const Hit& h) const
+		__device__ __forceinline__ void Retire(bool finished, uint32_t g, const Hit& h, bool) const
 		{
 			const bool hit = finished && h.tri != kNoHit;
 			uint32_t x = 0, y = 0, sample = 0;
@@ -151,7 +155,7 @@ namespace spt
 		const uint64_t raysPer = lvl0 > lvl1 ? lvl0 : lvl1;
 		const uint64_t auxPer = lvl0 + kDepthFactor * lvl1;
 		const uint64_t recPer = 2u + kDepthFactor * S;
-		const uint64_t bytesPer = raysPer * (sizeof(RayRec) + sizeof(Hit)) + auxPer * sizeof(RayAux) + recPer * sizeof(NodeRec);
+		const uint64_t bytesPer = raysPer * (sizeof(RayRec) + sizeof(Hit) + 4u) + auxPer * (sizeof(RayAux) + 1u) + recPer * sizeof(NodeRec);
 		uint64_t budget = 6144ull << 20;
 		if (const char* e = getenv("SAILOR_PT_BATCH_MB")) { const long v = atol(e); if (v > 0) budget = (uint64_t)v << 20; }
 		uint64_t B = budget / bytesPer;
@@ -237,6 +241,7 @@ namespace spt
 				a.skyCap = hasSky ? plan.skyCap : 16u;
 				a.sky[0] = EnsureBytes<SkyState>(ctx, D.renderMem[9], (size_t)a.skyCap * 2); a.sky[1] = a.sky[0] + a.skyCap;
 				a.skyRays = EnsureBytes<RayRec>(ctx, D.renderMem[10], (size_t)a.skyCap * 2); a.skyHits = EnsureBytes<Hit>(ctx, D.renderMem[11], a.skyCap);
+				a.status = EnsureBytes<uint8_t>(ctx, D.renderMem[12], plan.auxCap); a.slowList = EnsureBytes<uint32_t>(ctx, D.renderMem[13], plan.rayCap);
 				a.fanCap = plan.firstHits + 1024u; a.fan = EnsureBytes<ShadeCtx>(ctx, D.renderMem[8], a.fanCap);
 				a.c = counters; a.sampleBuf = sampleBuf;
 				if (!ctx.ok) return SAILOR_PT_ERR_CUDA;
@@ -249,11 +254,11 @@ namespace spt
 					// upper bounds for the grid: level 0 is exact, deeper levels are bounded by the arenas
 					const uint32_t maxRecs = level == 0 ? plan.firstHits : plan.recCap;
 					launch_for_range(ctx, &L->recBegin, &L->recEnd, plan.recCap, maxRecs, ExpandKernel{ a, level });
-					launch_for_range(ctx, &counters->zero, &counters->fanThreads, a.fanCap * 32u, a.fanCap * 32u, FanOutKernel{ a, level });
+					launch_for_range<SPT_FAN_MIN_BLOCKS>(ctx, &counters->zero, &counters->fanThreads, a.fanCap * 32u, a.fanCap * 32u, FanOutKernel{ a, level });
 					tt.Begin(ctx);
-					LaunchTraceRays(ctx, view, a.rays, a.hits, plan.rayCap, D.counter.p, &L->rayCount);
+					LaunchTraceLevel(ctx, view, a.rays, a.hits, plan.rayCap, D.counter.p, &L->rayCount, WavefrontOut{ a.status, &L->auxBase, a.slowList, &counters->slowCount });
 					tt.End(ctx);
-					launch_for_range(ctx, &counters->zero, &L->rayCount, plan.rayCap, plan.rayCap, ClassifyKernel{ a, level });
+					launch_for_range(ctx, &counters->zero, &counters->slowCount, plan.rayCap, plan.rayCap, ClassifyKernel{ a, level });
 					if (hasSky)
 					{
 						uint32_t q = 0;
@@ -273,7 +278,7 @@ namespace spt
 					const LevelInfo* L = &counters->level[level];
 					launch_for_range(ctx, &L->recBegin, &L->recEnd, plan.recCap, level == 0 ? plan.firstHits : plan.recCap, GatherKernel{ a });
 				}
-				struct { uint32_t recAlloc, auxAlloc, overflow, sky0, sky1, zero, fanThreads, pad1; unsigned long long rays; } head;
+				struct { uint32_t recAlloc, auxAlloc, overflow, sky0, sky1, zero, fanThreads, slowCount; unsigned long long rays; } head;
 				DevDownload(ctx, &head, counters, sizeof(head));          // synchronises
 				if (!ctx.ok) break;
 				if (head.overflow)

@@ -4,7 +4,7 @@
 // Every lane owns one ray and is in one of three modes: idle, at an INNER node, or inside a LEAF (one triangle per
 // step).  Each iteration the warp votes (ballot) and executes the step the majority of its busy lanes needs, so an
 // instruction is never issued for a handful of lanes while the rest wait in the other branch; lanes that finished
-// are refilled from the global queue as soon as a quarter of the warp is idle (one atomicAdd per refill), so the
+// are refilled from the global queue as soon as half of the warp is idle (one atomicAdd per refill), so the
 // warp does not drain to its slowest ray.  Per lane the order of box and triangle tests is exactly the
 // reference's (BVH.cpp:122-191) whatever the warp does, so hit ids and barycentrics stay bit-identical.
 //
@@ -36,7 +36,7 @@ namespace spt
 #define SPT_SMEM_STACK 24
 #endif
 #ifndef SPT_FETCH_MIN_IDLE
-#define SPT_FETCH_MIN_IDLE 8
+#define SPT_FETCH_MIN_IDLE 16
 #endif
 #ifndef SPT_VOTE_LEAF_BIAS
 #define SPT_VOTE_LEAF_BIAS 1
@@ -67,7 +67,7 @@ namespace spt
 	__device__ __forceinline__ bool FiniteF(float f) { return (__float_as_uint(f) & 0x7F800000u) != 0x7F800000u; }
 
 	// The warp loop.  Source: bool Load(uint32_t index, V3& o, V3& d, uint32_t& ignore, float& maxLen, bool& anyHit) (false = nothing to
-	// trace at this index).  Sink: void Retire(bool finished, uint32_t index, const Hit&) called by ALL lanes each iteration.
+	// trace at this index).  Sink: void Retire(bool finished, uint32_t index, const Hit&, bool anyHit) called by ALL lanes each iteration.
 	// Lane state is one word: kLaneIdle, an inner node index, or kLeafBit | triangle slot (the next triangle to test).
 #ifndef SPT_VOTE_INNER_BIAS
 #define SPT_VOTE_INNER_BIAS 1      // inner step when nInner * bias >= nLeaf
@@ -190,7 +190,7 @@ namespace spt
 					else cur = ovf[sp - kSmemStack];
 				}
 			}
-			sink.Retire(finished, index, hit);
+			sink.Retire(finished, index, hit, anyHit);
 		}
 	}
 
@@ -211,9 +211,36 @@ namespace spt
 	struct QueueSink
 	{
 		Hit* hits;
-		__device__ __forceinline__ void Retire(bool finished, uint32_t i, const Hit& h) const
+		__device__ __forceinline__ void Retire(bool finished, uint32_t i, const Hit& h, bool) const
 		{
 			if (finished) *reinterpret_cast<float4*>(hits + i) = make_float4(h.t, h.u, h.v, __uint_as_float(h.tri));
+		}
+	};
+	// Wavefront levels: every ray leaves ONE status byte (hit or miss).  Only closest-hit queries that hit something (a child
+	// activation or a TraceSky walk may start there) also leave their hit record and a slow-list entry for ClassifyKernel.
+	struct WavefrontOut { uint8_t* status; const uint32_t* auxBase; uint32_t* slowList; uint32_t* slowCount; };
+	struct WavefrontSink
+	{
+		Hit* hits; uint8_t* status; uint32_t* slowList; uint32_t* slowCount;     // status already offset by the level's auxBase
+		__device__ __forceinline__ void Retire(bool finished, uint32_t i, const Hit& h, bool anyHit) const
+		{
+			const bool hitSomething = h.tri != kNoHit;
+			if (finished) status[i] = hitSomething ? 1 : 0;
+			const bool slow = finished && hitSomething && !anyHit;
+			const uint32_t m = __ballot_sync(0xffffffffu, slow);
+			if (m)
+			{
+				const uint32_t lane = threadIdx.x & 31;
+				const int leader = __ffs(m) - 1;
+				uint32_t base = 0;
+				if ((int)lane == leader) base = atomicAdd(slowCount, (uint32_t)__popc(m));
+				base = __shfl_sync(0xffffffffu, base, leader);
+				if (slow)
+				{
+					*reinterpret_cast<float4*>(hits + i) = make_float4(h.t, h.u, h.v, __uint_as_float(h.tri));
+					slowList[base + (uint32_t)__popc(m & ((1u << lane) - 1u))] = i;
+				}
+			}
 		}
 	};
 
@@ -227,6 +254,15 @@ namespace spt
 		TraceWarpLoop(bvh, n, counter, stackMem, src, sink);
 	}
 
+	__global__ void __launch_bounds__(kTraceBlock) k_trace_level(BvhView bvh, const RayRec* __restrict__ rays, Hit* __restrict__ hits,
+		uint32_t n, const uint32_t* __restrict__ nPtr, uint32_t* __restrict__ counter, WavefrontOut out)
+	{
+		__shared__ uint32_t stackMem[kSmemStack * kTraceBlock];
+		{ const uint32_t m = *nPtr; if (m < n) n = m; }
+		QueueSource src{ rays }; WavefrontSink sink{ hits, out.status + *out.auxBase, out.slowList, out.slowCount };
+		TraceWarpLoop(bvh, n, counter, stackMem, src, sink);
+	}
+
 	// ---- small scenes: the whole traversal layout lives in shared memory --------------------------------------------
 	// A scene of a few hundred triangles (BASELINE config C1/C2 is a 12-triangle cube) has no memory problem to solve: the
 	// node and triangle records are copied into shared memory once per CTA and every thread walks its own ray with the
@@ -235,8 +271,9 @@ namespace spt
 	constexpr uint32_t kSmallSceneBytes = 40u * 1024u;
 	constexpr int kSmallBlock = 256;
 
+	template<bool kWavefront>
 	__global__ void __launch_bounds__(kSmallBlock) k_trace_rays_small(const TNode* __restrict__ gNodes, uint32_t numNodes, const TTri* __restrict__ gTris, uint32_t numTris,
-		uint32_t rootRef, const RayRec* __restrict__ rays, Hit* __restrict__ hits, uint32_t n, const uint32_t* __restrict__ nPtr)
+		uint32_t rootRef, const RayRec* __restrict__ rays, Hit* __restrict__ hits, uint32_t n, const uint32_t* __restrict__ nPtr, WavefrontOut out)
 	{
 		extern __shared__ __align__(16) unsigned char smallMem[];
 		V4* sNodes = reinterpret_cast<V4*>(smallMem);                         // 4 x V4 per node
@@ -315,7 +352,17 @@ namespace spt
 					if (d2 != kFltMax) stack[sp++] = c2;
 				}
 			}
-			*reinterpret_cast<float4*>(hits + i) = make_float4(hit.t, hit.u, hit.v, __uint_as_float(hit.tri));
+			if (!kWavefront) *reinterpret_cast<float4*>(hits + i) = make_float4(hit.t, hit.u, hit.v, __uint_as_float(hit.tri));
+			else
+			{
+				const bool hitSomething = hit.tri != kNoHit;
+				out.status[*out.auxBase + i] = hitSomething ? 1 : 0;
+				if (hitSomething && !anyHit)
+				{
+					*reinterpret_cast<float4*>(hits + i) = make_float4(hit.t, hit.u, hit.v, __uint_as_float(hit.tri));
+					out.slowList[atomicAdd(out.slowCount, 1u)] = i;
+				}
+			}
 		}
 	}
 
@@ -339,7 +386,7 @@ namespace spt
 	struct PrimarySink
 	{
 		Hit* hits; PrimarySource src;
-		__device__ __forceinline__ void Retire(bool finished, uint32_t i, const Hit& h) const
+		__device__ __forceinline__ void Retire(bool finished, uint32_t i, const Hit& h, bool) const
 		{
 			if (!finished) return;
 			uint32_t x, y; src.Pixel(i, x, y);
@@ -370,24 +417,55 @@ namespace spt
 		return grid;
 	}
 
+	inline bool SmallScene(const BvhView& bvh, size_t& bytes)
+	{
+		bytes = (size_t)bvh.numNodes * sizeof(TNode) + (size_t)bvh.numTris * sizeof(TTri);
+		if (bytes > kSmallSceneBytes) return false;
+		static bool attr = false;
+		if (!attr)
+		{
+			cudaFuncSetAttribute(k_trace_rays_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSceneBytes);
+			cudaFuncSetAttribute(k_trace_rays_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSceneBytes);
+			attr = true;
+		}
+		return true;
+	}
+	inline uint32_t SmallGrid(uint32_t n)
+	{
+		uint32_t blocks = (n + kSmallBlock - 1) / kSmallBlock;
+		const uint32_t lim = (uint32_t)RangeGridBlocks();
+		return blocks > lim ? lim : blocks;
+	}
+
 	inline void LaunchTraceRays(Ctx& ctx, const BvhView& bvh, const RayRec* rays, Hit* hits, uint32_t n, uint32_t* counter, const uint32_t* nPtr = nullptr)
 	{
 		if (!n || !ctx.ok) return;
-		const size_t smallBytes = (size_t)bvh.numNodes * sizeof(TNode) + (size_t)bvh.numTris * sizeof(TTri);
-		if (smallBytes <= kSmallSceneBytes)
+		size_t smallBytes;
+		if (SmallScene(bvh, smallBytes))
 		{
-			static bool attr = false;
-			if (!attr) { cudaFuncSetAttribute(k_trace_rays_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSceneBytes); attr = true; }
-			uint32_t blocks = (n + kSmallBlock - 1) / kSmallBlock;
-			const uint32_t lim = (uint32_t)RangeGridBlocks();
-			if (blocks > lim) blocks = lim;
-			k_trace_rays_small<<<blocks, kSmallBlock, smallBytes, ctx.stream>>>(bvh.nodes, bvh.numNodes, bvh.tris, bvh.numTris, bvh.rootRef, rays, hits, n, nPtr);
+			k_trace_rays_small<false><<<SmallGrid(n), kSmallBlock, smallBytes, ctx.stream>>>(bvh.nodes, bvh.numNodes, bvh.tris, bvh.numTris, bvh.rootRef, rays, hits, n, nPtr, WavefrontOut{});
 			ctx.kernelLaunches++;
 			SPT_CUDA_CHECK(ctx, cudaGetLastError());
 			return;
 		}
 		DevMemset(ctx, counter, 0, sizeof(uint32_t));
 		k_trace_rays<<<TraceGridSize(), kTraceBlock, 0, ctx.stream>>>(bvh, rays, hits, n, nPtr, counter);
+		ctx.kernelLaunches++;
+		SPT_CUDA_CHECK(ctx, cudaGetLastError());
+	}
+
+	// one level of the wavefront: queue length in device memory, status bytes + slow list out
+	inline void LaunchTraceLevel(Ctx& ctx, const BvhView& bvh, const RayRec* rays, Hit* hits, uint32_t cap, uint32_t* counter, const uint32_t* nPtr, const WavefrontOut& out)
+	{
+		if (!cap || !ctx.ok) return;
+		size_t smallBytes;
+		if (SmallScene(bvh, smallBytes))
+			k_trace_rays_small<true><<<SmallGrid(cap), kSmallBlock, smallBytes, ctx.stream>>>(bvh.nodes, bvh.numNodes, bvh.tris, bvh.numTris, bvh.rootRef, rays, hits, cap, nPtr, out);
+		else
+		{
+			DevMemset(ctx, counter, 0, sizeof(uint32_t));
+			k_trace_level<<<TraceGridSize(), kTraceBlock, 0, ctx.stream>>>(bvh, rays, hits, cap, nPtr, counter, out);
+		}
 		ctx.kernelLaunches++;
 		SPT_CUDA_CHECK(ctx, cudaGetLastError());
 	}
@@ -407,6 +485,21 @@ namespace spt
 		if (nPtr && *nPtr < n) n = *nPtr;
 		for (uint32_t i = 0; i < n; i++)
 			if (rays[i].tmax != -1.0f) TraceClosest(bvh, v3(rays[i].ox, rays[i].oy, rays[i].oz), v3(rays[i].dx, rays[i].dy, rays[i].dz), rays[i].ignoreTri, fabsf(rays[i].tmax), st, hits[i]);
+		ctx.kernelLaunches++;
+	}
+	struct WavefrontOut { uint8_t* status; const uint32_t* auxBase; uint32_t* slowList; uint32_t* slowCount; };
+	inline void LaunchTraceLevel(Ctx& ctx, const BvhView& bvh, const RayRec* rays, Hit* hits, uint32_t cap, uint32_t*, const uint32_t* nPtr, const WavefrontOut& out)
+	{
+		LocalStack st;
+		const uint32_t n = *nPtr < cap ? *nPtr : cap;
+		for (uint32_t i = 0; i < n; i++)
+		{
+			if (rays[i].tmax == -1.0f) continue;
+			Hit h;
+			TraceClosest(bvh, v3(rays[i].ox, rays[i].oy, rays[i].oz), v3(rays[i].dx, rays[i].dy, rays[i].dz), rays[i].ignoreTri, fabsf(rays[i].tmax), st, h);
+			out.status[*out.auxBase + i] = h.tri != kNoHit ? 1 : 0;
+			if (h.tri != kNoHit && !(rays[i].tmax < 0.0f)) { hits[i] = h; out.slowList[(*out.slowCount)++] = i; }
+		}
 		ctx.kernelLaunches++;
 	}
 	inline void LaunchTracePrimary(Ctx& ctx, const BvhView& bvh, const CameraGpu& cam, Hit* hits, uint32_t*)

@@ -11,15 +11,13 @@ VDIR = os.path.join(ROOT, "sailor_b200", "variants")
 
 VARIANTS = {
     "base": [],
-    "idle4": ["SPT_FETCH_MIN_IDLE=4"],
-    "idle12": ["SPT_FETCH_MIN_IDLE=12"],
     "idle16": ["SPT_FETCH_MIN_IDLE=16"],
-    "inner2": ["SPT_VOTE_INNER_BIAS=2"],
-    "leaf2": ["SPT_VOTE_LEAF_BIAS=2"],
-    "stack16": ["SPT_SMEM_STACK=16"],
-    "stack32": ["SPT_SMEM_STACK=32"],
-    "block64": ["SPT_TRACE_BLOCK=64"],
-    "block256": ["SPT_TRACE_BLOCK=256"],
+    "idle20": ["SPT_FETCH_MIN_IDLE=20"],
+    "idle24": ["SPT_FETCH_MIN_IDLE=24"],
+    "idle32": ["SPT_FETCH_MIN_IDLE=32"],
+    "fan1": ["SPT_FAN_MIN_BLOCKS=1"],
+    "fan2": ["SPT_FAN_MIN_BLOCKS=2"],
+    "fan4": ["SPT_FAN_MIN_BLOCKS=4"],
 }
 
 if sys.argv[1] == "build":
