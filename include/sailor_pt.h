@@ -100,6 +100,12 @@ typedef struct SailorPtStats {
 	uint32_t reserved;
 	uint64_t h2dBytes;        /* product: bytes copied host->device by the last call */
 	uint64_t d2hBytes;        /* product: bytes copied device->host by the last call */
+	/* product, render calls: device time per wavefront stage (CUDA events on the launch stream); secondsShade is their sum + the rest */
+	double secondsExpand;     /* ExpandKernel: shade an activation, emit its few rays */
+	double secondsFanOut;     /* FanOutKernel: hemisphere + importance samples of first hits */
+	double secondsClassify;   /* ClassifyKernel + TraceSky continuation kernels */
+	double secondsGather;     /* GatherKernel + resolve */
+	uint64_t fanOutSamples;   /* rays emitted by FanOutKernel */
 } SailorPtStats;
 
 /* ---- the reference entry points (PathTracer.h:34-36) ---- */
@@ -153,6 +159,10 @@ SAILOR_PT_API int32_t SailorPt_ReadResident(SailorPtScene* scene, float* linearR
 /* Product only: copy the resident linear accumulator (width*height*3 floats) into a caller-owned DEVICE buffer
  * (e.g. a torch tensor handed to NCCL). */
 SAILOR_PT_API int32_t SailorPt_CopyResidentToDevice(SailorPtScene* scene, void* dstDevice, uint64_t bytes);
+
+/* Product only: run the output stage on the resident accumulator; when srcDevice != NULL that DEVICE buffer (width*height*3
+ * floats, e.g. the NCCL-reduced frame) first replaces the resident accumulator.  The sRGB8 image stays resident. */
+SAILOR_PT_API int32_t SailorPt_OutputStageResident(SailorPtScene* scene, const void* srcDevice, uint64_t bytes);
 
 /* Output stage alone (PathTracer.cpp:535-565 + Core/Utils.cpp:48-57). */
 SAILOR_PT_API int32_t SailorPt_OutputStage(uint32_t width, uint32_t height, const float* linearRGB, uint8_t* srgb8);

@@ -37,6 +37,8 @@ class SailorPtStats(C.Structure):
         ("secondsTraverse", C.c_double), ("secondsShade", C.c_double), ("secondsOutput", C.c_double),
         ("traverseLaunches", C.c_uint32), ("kernelLaunches", C.c_uint32), ("threads", C.c_uint32),
         ("reserved", C.c_uint32), ("h2dBytes", C.c_uint64), ("d2hBytes", C.c_uint64),
+        ("secondsExpand", C.c_double), ("secondsFanOut", C.c_double), ("secondsClassify", C.c_double), ("secondsGather", C.c_double),
+        ("fanOutSamples", C.c_uint64),
     ]
 
     def as_dict(self):
@@ -52,7 +54,7 @@ SYMBOLS = [
     "SailorPt_SceneCounts", "SailorPt_SceneGetTriangles", "SailorPt_BuildBVH", "SailorPt_GetBVH",
     "SailorPt_GetCamera", "SailorPt_IntersectRays", "SailorPt_PrimaryHits", "SailorPt_Render",
     "SailorPt_OutputStage", "SailorPt_SampleTexture", "SailorPt_EvalLighting", "SailorPt_GetStats",
-    "SailorPt_LastError", "SailorPt_Backend", "SailorPt_RenderResident", "SailorPt_ReadResident", "SailorPt_CopyResidentToDevice", "SailorPt_SetDevice",
+    "SailorPt_LastError", "SailorPt_Backend", "SailorPt_RenderResident", "SailorPt_ReadResident", "SailorPt_CopyResidentToDevice", "SailorPt_SetDevice", "SailorPt_OutputStageResident",
 ]
 
 
@@ -135,6 +137,7 @@ class Library:
         lib.SailorPt_EvalLighting.argtypes = [C.c_uint32, P(C.c_float), P(C.c_float)]
         lib.SailorPt_GetStats.argtypes = [P(SailorPtStats)]
         lib.SailorPt_SetDevice.argtypes = [C.c_int32]
+        lib.SailorPt_OutputStageResident.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         lib.SailorPt_LastError.restype = C.c_char_p
         lib.SailorPt_Backend.restype = C.c_char_p
         for s in SYMBOLS:
@@ -266,11 +269,18 @@ class Scene:
         self.L.check(self.L.lib.SailorPt_PrimaryHits(self.h, C.byref(cp), hits.ctypes.data), "SailorPt_PrimaryHits")
         return hits.reshape(h, w)
 
-    def render(self, params: Params, want_srgb=True):
+    def render(self, params: Params, want_srgb=True, out=None):
+        """out=(linear float32 [h,w,3], srgb uint8 [h,w,3] or None): caller-owned host buffers to fill (a host that renders
+        frame after frame reuses them); by default fresh arrays are allocated."""
         w, h, _ = self.camera(params)
         cp = params.to_c()
-        lin = np.empty((h, w, 3), np.float32)
-        srgb = np.empty((h, w, 3), np.uint8) if want_srgb else None
+        if out is not None:
+            lin, srgb = out
+            assert lin.shape == (h, w, 3) and lin.dtype == np.float32 and lin.flags.c_contiguous
+            assert srgb is None or (srgb.shape == (h, w, 3) and srgb.dtype == np.uint8 and srgb.flags.c_contiguous)
+        else:
+            lin = np.empty((h, w, 3), np.float32)
+            srgb = np.empty((h, w, 3), np.uint8) if want_srgb else None
         self.L.check(self.L.lib.SailorPt_Render(self.h, C.byref(cp), _ptr(lin, C.c_float), _ptr(srgb, C.c_uint8)), "SailorPt_Render")
         return lin, srgb
 
@@ -287,6 +297,9 @@ class Scene:
 
     def copy_resident_to_device(self, device_ptr, nbytes):
         self.L.check(self.L.lib.SailorPt_CopyResidentToDevice(self.h, C.c_void_p(device_ptr), nbytes), "SailorPt_CopyResidentToDevice")
+
+    def output_stage_resident(self, device_ptr=None, nbytes=0):
+        self.L.check(self.L.lib.SailorPt_OutputStageResident(self.h, C.c_void_p(device_ptr) if device_ptr else None, nbytes), "SailorPt_OutputStageResident")
 
     def sample_texture(self, index, uv):
         uv = np.ascontiguousarray(uv, dtype=np.float32)

@@ -144,6 +144,7 @@ void SailorPt_SceneFree(SailorPtScene* s)
 	if (!s) return;
 	s->dev.ctx.Sync();
 	s->dev.traceTimer.Destroy();
+	for (SpanTimer& t : s->dev.stageTimer) t.Destroy();
 	Ctx keep = s->dev.ctx;
 	delete s;
 	keep.Destroy();
@@ -319,7 +320,8 @@ int32_t SailorPt_RenderResident(SailorPtScene* s, const SailorPtParams* p, uint3
 	g_stats = SailorPtStats{};
 	g_stats.secondsFlatten = D.ctx.Between(Ctx::kMarkCall0, Ctx::kMarkCall1);         // whole call on the launch stream (CUDA events); field reused: no flatten here
 	g_stats.rays = rs.rays; g_stats.primarySamples = rs.primarySamples; g_stats.secondsTraverse = rs.secondsTraverse;
-	g_stats.secondsShade = rs.secondsShade; g_stats.secondsOutput = tOut; g_stats.secondsBvhBuild = tBuild; g_stats.traverseLaunches = rs.traverseLaunches;
+	g_stats.secondsShade = rs.secondsShade; g_stats.secondsExpand = rs.secondsStage[0]; g_stats.secondsFanOut = rs.secondsStage[1]; g_stats.secondsClassify = rs.secondsStage[2];
+	g_stats.secondsGather = rs.secondsStage[3]; g_stats.fanOutSamples = rs.fanOutSamples; g_stats.secondsOutput = tOut; g_stats.secondsBvhBuild = tBuild; g_stats.traverseLaunches = rs.traverseLaunches;
 	g_stats.kernelLaunches = D.ctx.kernelLaunches; g_stats.h2dBytes = D.ctx.h2dBytes; g_stats.d2hBytes = D.ctx.d2hBytes;
 	g_stats.secondsTotal = HostNow() - t0;
 	return FromCtx(D, SAILOR_PT_OK);
@@ -343,6 +345,25 @@ int32_t SailorPt_CopyResidentToDevice(SailorPtScene* s, void* dstDevice, uint64_
 	if (bytes != (uint64_t)D.residentW * D.residentH * 3 * sizeof(float)) return SAILOR_PT_ERR_ARG;
 	DevCopy(D.ctx, dstDevice, D.residentLin.p, (size_t)bytes);
 	D.ctx.Sync();
+	return FromCtx(D, SAILOR_PT_OK);
+}
+
+int32_t SailorPt_OutputStageResident(SailorPtScene* s, const void* srcDevice, uint64_t bytes)
+{
+	if (!s || !s->dev.residentW) return SAILOR_PT_ERR_ARG;
+	SceneDevice& D = s->dev;
+	const size_t n = (size_t)D.residentW * D.residentH;
+	if (srcDevice)
+	{
+		if (bytes != (uint64_t)n * 3 * sizeof(float)) return SAILOR_PT_ERR_ARG;
+		DevCopy(D.ctx, D.residentLin.p, srcDevice, (size_t)bytes);
+	}
+	D.residentSrgb.Ensure(D.ctx, n * 3);
+	D.ctx.kernelLaunches = 0;
+	D.ctx.TimerStart();
+	RunOutputStage(D.ctx, D.residentW, D.residentH, D.residentLin.p, D.residentSrgb.p);
+	g_stats.secondsOutput = D.ctx.TimerStop();
+	g_stats.kernelLaunches = D.ctx.kernelLaunches;
 	return FromCtx(D, SAILOR_PT_OK);
 }
 

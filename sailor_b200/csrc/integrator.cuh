@@ -46,11 +46,11 @@ namespace spt
 	struct alignas(16) PrimaryHitRec { uint32_t pixel, sample, pad0, pad1; float t, u, v; uint32_t tri; };
 	static_assert(sizeof(PrimaryHitRec) == 32, "PrimaryHitRec layout");
 
-	struct RenderStats { uint64_t rays, primarySamples; double secondsTraverse, secondsShade; uint32_t traverseLaunches; };
+	struct RenderStats { uint64_t rays, primarySamples, fanOutSamples; double secondsTraverse, secondsShade, secondsStage[4]; uint32_t traverseLaunches; };
 
 	constexpr uint32_t kNone = 0xFFFFFFFFu;
 #ifndef SPT_FAN_OUT_MIN
-#define SPT_FAN_OUT_MIN 16
+#define SPT_FAN_OUT_MIN 8
 #endif
 	constexpr uint32_t kFanOutMinSamples = SPT_FAN_OUT_MIN;   // activations with at least this many hemisphere + importance samples get a warp
 
@@ -118,9 +118,11 @@ namespace spt
 		uint32_t overflow;         // any arena ran out: the batch is invalid, the host retries with a smaller one
 		uint32_t skyCount[2];      // ping-pong sky queues
 		uint32_t zero;             // always 0 (range begin)
-		uint32_t fanThreads;       // 32 x activations handed to FanOutKernel at the current level
+		uint32_t fanEntries;       // activations handed to FanOutKernel at the current level
 		uint32_t slowCount;        // rays of the current level whose closest hit needs ClassifyKernel
+		uint32_t fanThreads[2];    // 8 x slots of the hemisphere / importance fan-out passes
 		unsigned long long rays;   // closest-hit queries of the batch
+		unsigned long long fanSamples;   // rays emitted by FanOutKernel
 		LevelInfo level[66];
 	};
 
@@ -139,7 +141,7 @@ namespace spt
 		RayRec* rays; Hit* hits; uint32_t rayCap;                             // ray queue of the current level (hits: only rays on the slow list)
 		uint8_t* status; uint32_t* slowList;                                  // per RayAux: 1 = the ray hit something (written by the trace kernel); level-local indices of rays for ClassifyKernel
 		SkyState* sky[2]; RayRec* skyRays; Hit* skyHits; uint32_t skyCap;
-		ShadeCtx* fan; uint32_t fanCap;                                       // activations whose samples are produced by FanOutKernel
+		ShadeCtx* fan; uint32_t fanCap; uint32_t* fanSlots[2];                // activations whose samples are produced by FanOutKernel; 8-lane slot tables (4 x fanCap each)
 		BatchCounters* c;
 		float* sampleBuf;                       // 3 floats per (pixel in band, sample in range)
 	};
@@ -528,9 +530,21 @@ namespace spt
 				bool fanned = false;
 				if (nHemi + nS >= kFanOutMinSamples)
 				{
-					// many samples (first hits): hand them to a warp (FanOutKernel); this thread only reserves the rays
-					const uint32_t e = atomic_add_u32(&a.c->fanThreads, 32u) / 32u;
-					if (e < a.fanCap) { a.fan[e] = c; fanned = true; }
+					// many samples (first hits): hand them to FanOutKernel in slots of 8 lanes; this thread only reserves the rays
+					const uint32_t e = atomic_add_u32(&a.c->fanEntries, 1u);
+					if (e < a.fanCap)
+					{
+						a.fan[e] = c; fanned = true;
+						atomic_add_u64(&a.c->fanSamples, (unsigned long long)(nHemi + nS));
+						const uint32_t cnt[2] = { nHemi, nS };
+						for (uint32_t pass = 0; pass < 2; pass++)
+						{
+							uint32_t slots = (cnt[pass] + 7u) / 8u; if (slots > 4u) slots = 4u;
+							if (!slots) continue;
+							const uint32_t base = atomic_add_u32(&a.c->fanThreads[pass], 8u * slots) / 8u;
+							for (uint32_t k = 0; k < slots; k++) a.fanSlots[pass][base + k] = e | (k << 24) | ((slots - 1u) << 27);
+						}
+					}
 				}
 				if (!fanned)
 				{
@@ -560,20 +574,27 @@ namespace spt
 		}
 	};
 
-	// ---- fan-out: one warp per activation with many samples; lane l produces samples l, l+32, ... ------------------------
+	// ---- fan-out: activations with many samples get 1-4 slots of 8 lanes per pass; lane l produces samples l, l+stride, ... ----
+	// Two passes (hemisphere rays, importance rays) so that the lanes of a warp run the same code; rays of one activation are
+	// written by consecutive lanes (coalesced).
 	struct FanOutKernel
 	{
-		IntegratorArgs a; uint32_t level;
-		SPT_KERNEL_BODY void operator()(uint32_t w) const                             // w = entry * 32 + lane
+		IntegratorArgs a; uint32_t level; uint32_t pass;
+		SPT_KERNEL_BODY void operator()(uint32_t w) const                             // w = slot * 8 + lane
 		{
-			const uint32_t e = w >> 5, lane = w & 31u;
-			if (e >= a.fanCap) return;
+			const uint32_t packed = a.fanSlots[pass][w >> 3];
+			const uint32_t e = packed & 0xFFFFFFu, slot = (packed >> 24) & 7u, stride = (((packed >> 27) & 7u) + 1u) * 8u;
+			const uint32_t lane = slot * 8u + (w & 7u);
 			const ShadeCtx c = a.fan[e];
 			const SampledData s = SampledOf(c);
 			const uint32_t auxBase = a.c->level[level].auxBase;
-			for (uint32_t k = lane; k < c.nHemi; k += 32u) EmitHemisphere(a, c, s, k, c.rayBase + k, auxBase + c.rayBase + k);
+			if (pass == 0)
+			{
+				for (uint32_t k = lane; k < c.nHemi; k += stride) EmitHemisphere(a, c, s, k, c.rayBase + k, auxBase + c.rayBase + k);
+				return;
+			}
 			const bool thick = (c.flags & kNfThick) != 0;
-			for (uint32_t i = lane; i < c.nS; i += 32u)
+			for (uint32_t i = lane; i < c.nS; i += stride)
 			{
 				bool anyTrans = false;
 				const bool last = thick && i == c.nS - 1u;
@@ -719,6 +740,7 @@ namespace spt
 					V3 amb1 = v3(0.0f);
 					if (!(flags & kNfThick))
 					{
+#pragma unroll 4
 						for (uint32_t k = 0; k < nA; k++, g++)
 						{
 							const RayAux x = a.aux[g];
@@ -729,6 +751,7 @@ namespace spt
 					}
 					amb1 = amb1 / (float)nA;                                              // :739
 					V3 amb2 = v3(0.0f), indirect = v3(0.0f); float avgPdf = 0.0f, cnt = 0.0f;
+#pragma unroll 4
 					for (uint32_t i = 0; i < nS; i++, g++)
 					{
 						const RayAux x = a.aux[g];
@@ -789,7 +812,7 @@ namespace spt
 		BatchCounters* c; uint32_t count;
 		SPT_KERNEL_BODY void operator()(uint32_t) const
 		{
-			c->recAlloc = count; c->auxAlloc = 0; c->overflow = 0; c->skyCount[0] = c->skyCount[1] = 0; c->zero = 0; c->fanThreads = 0; c->slowCount = 0; c->rays = 0;
+			c->recAlloc = count; c->auxAlloc = 0; c->overflow = 0; c->skyCount[0] = c->skyCount[1] = 0; c->zero = 0; c->fanEntries = 0; c->fanThreads[0] = c->fanThreads[1] = 0; c->slowCount = 0; c->rays = 0; c->fanSamples = 0;
 			c->level[0].recBegin = 0; c->level[0].recEnd = count; c->level[0].rayCount = 0; c->level[0].auxBase = 0;
 		}
 	};
@@ -803,7 +826,7 @@ namespace spt
 			c->level[level + 1] = nx;
 			c->auxAlloc = nx.auxBase;
 			c->rays += cur.rayCount;
-			c->fanThreads = 0; c->slowCount = 0;
+			c->fanEntries = 0; c->fanThreads[0] = c->fanThreads[1] = 0; c->slowCount = 0;
 		}
 	};
 	struct SkySwapKernel         // after a sky iteration: queue q is consumed

@@ -13,6 +13,9 @@
 #pragma once
 #include "integrator.cuh"
 
+#ifndef SPT_EXPAND_MIN_BLOCKS
+#define SPT_EXPAND_MIN_BLOCKS 2
+#endif
 #ifndef SPT_FAN_MIN_BLOCKS
 #define SPT_FAN_MIN_BLOCKS 3
 #endif
@@ -204,6 +207,7 @@ namespace spt
 		rs = RenderStats{};
 		const BvhView view = D.View();
 		SpanTimer& tt = D.traceTimer;
+		SpanTimer* st = D.stageTimer;
 
 		ctx.Mark(0);
 		// ---- primary pass ----
@@ -243,6 +247,7 @@ namespace spt
 				a.skyRays = EnsureBytes<RayRec>(ctx, D.renderMem[10], (size_t)a.skyCap * 2); a.skyHits = EnsureBytes<Hit>(ctx, D.renderMem[11], a.skyCap);
 				a.status = EnsureBytes<uint8_t>(ctx, D.renderMem[12], plan.auxCap); a.slowList = EnsureBytes<uint32_t>(ctx, D.renderMem[13], plan.rayCap);
 				a.fanCap = plan.firstHits + 1024u; a.fan = EnsureBytes<ShadeCtx>(ctx, D.renderMem[8], a.fanCap);
+				a.fanSlots[0] = EnsureBytes<uint32_t>(ctx, D.renderMem[14], (size_t)a.fanCap * 8u); a.fanSlots[1] = a.fanSlots[0] + (size_t)a.fanCap * 4u;
 				a.c = counters; a.sampleBuf = sampleBuf;
 				if (!ctx.ok) return SAILOR_PT_ERR_CUDA;
 
@@ -253,12 +258,19 @@ namespace spt
 					const LevelInfo* L = &counters->level[level];
 					// upper bounds for the grid: level 0 is exact, deeper levels are bounded by the arenas
 					const uint32_t maxRecs = level == 0 ? plan.firstHits : plan.recCap;
-					launch_for_range(ctx, &L->recBegin, &L->recEnd, plan.recCap, maxRecs, ExpandKernel{ a, level });
-					launch_for_range<SPT_FAN_MIN_BLOCKS>(ctx, &counters->zero, &counters->fanThreads, a.fanCap * 32u, a.fanCap * 32u, FanOutKernel{ a, level });
+					st[0].Begin(ctx);
+					launch_for_range<SPT_EXPAND_MIN_BLOCKS>(ctx, &L->recBegin, &L->recEnd, plan.recCap, maxRecs, ExpandKernel{ a, level });
+					st[0].End(ctx);
+					st[1].Begin(ctx);
+					launch_for_range<SPT_FAN_MIN_BLOCKS>(ctx, &counters->zero, &counters->fanThreads[0], a.fanCap * 32u, a.fanCap * 32u, FanOutKernel{ a, level, 0u });
+					launch_for_range<SPT_FAN_MIN_BLOCKS>(ctx, &counters->zero, &counters->fanThreads[1], a.fanCap * 32u, a.fanCap * 32u, FanOutKernel{ a, level, 1u });
+					st[1].End(ctx);
 					tt.Begin(ctx);
 					LaunchTraceLevel(ctx, view, a.rays, a.hits, plan.rayCap, D.counter.p, &L->rayCount, WavefrontOut{ a.status, &L->auxBase, a.slowList, &counters->slowCount });
 					tt.End(ctx);
+					st[2].Begin(ctx);
 					launch_for_range(ctx, &counters->zero, &counters->slowCount, plan.rayCap, plan.rayCap, ClassifyKernel{ a, level });
+					st[2].End(ctx);
 					if (hasSky)
 					{
 						uint32_t q = 0;
@@ -267,18 +279,22 @@ namespace spt
 							tt.Begin(ctx);
 							LaunchTraceRays(ctx, view, a.skyRays + (q ? a.skyCap : 0u), a.skyHits, a.skyCap, D.counter.p, &counters->skyCount[q]);
 							tt.End(ctx);
+							st[2].Begin(ctx);
 							launch_for_range(ctx, &counters->zero, &counters->skyCount[q], a.skyCap, a.skyCap, SkyKernel{ a, q });
 							launch_for(ctx, 1, SkySwapKernel{ counters, q });
+							st[2].End(ctx);
 						}
 					}
 					launch_for(ctx, 1, NextLevelKernel{ counters, level, plan.recCap });
 				}
+				st[3].Begin(ctx);
 				for (uint32_t level = levels; level-- > 0;)
 				{
 					const LevelInfo* L = &counters->level[level];
 					launch_for_range(ctx, &L->recBegin, &L->recEnd, plan.recCap, level == 0 ? plan.firstHits : plan.recCap, GatherKernel{ a });
 				}
-				struct { uint32_t recAlloc, auxAlloc, overflow, sky0, sky1, zero, fanThreads, slowCount; unsigned long long rays; } head;
+				st[3].End(ctx);
+				struct { uint32_t recAlloc, auxAlloc, overflow, sky0, sky1, zero, fanEntries, slowCount, fan0, fan1; unsigned long long rays, fanSamples; } head;
 				DevDownload(ctx, &head, counters, sizeof(head));          // synchronises
 				if (!ctx.ok) break;
 				if (head.overflow)
@@ -287,7 +303,7 @@ namespace spt
 					shrink++;
 					continue;                                                // redo this batch smaller (results are keyed per activation, not per batch)
 				}
-				rs.rays += head.rays;
+				rs.rays += head.rays; rs.fanOutSamples += head.fanSamples;
 				done += plan.firstHits;
 			}
 		}
@@ -296,6 +312,7 @@ namespace spt
 		ctx.Sync();
 		rs.traverseLaunches = tt.Spans();
 		rs.secondsTraverse = tt.Collect(ctx);
+		for (int k = 0; k < 4; k++) rs.secondsStage[k] = st[k].Collect(ctx);
 		rs.secondsShade = ctx.Between(0, 1) - rs.secondsTraverse;      // everything of the frame that is not a trace launch
 		return ctx.ok ? SAILOR_PT_OK : SAILOR_PT_ERR_CUDA;
 	}

@@ -41,6 +41,12 @@ namespace spt
 #ifndef SPT_VOTE_LEAF_BIAS
 #define SPT_VOTE_LEAF_BIAS 1
 #endif
+#ifndef SPT_INNER_REPS
+#define SPT_INNER_REPS 4
+#endif
+#ifndef SPT_LEAF_REPS
+#define SPT_LEAF_REPS 2
+#endif
 	constexpr int kTraceBlock = SPT_TRACE_BLOCK;
 	constexpr int kSmemStack = SPT_SMEM_STACK;
 	constexpr uint32_t kFetchMinIdle = SPT_FETCH_MIN_IDLE;
@@ -123,71 +129,85 @@ namespace spt
 			const bool isLeaf = (cur & kLeafBit) && cur != kLaneIdle;
 			const uint32_t leafMask = __ballot_sync(0xffffffffu, isLeaf);
 			const int nLeaf = __popc(leafMask), nInner = 32 - __popc(idleMask) - nLeaf;
-			bool pop = false;
+			// The chosen step is repeated a few times per vote (lanes that left the mode sit out): the vote, the refill check
+			// and the retire cost ~45 warp-wide instructions, a step ~80.
+			bool finished = false;
 			if (nInner * SPT_VOTE_INNER_BIAS >= nLeaf * SPT_VOTE_LEAF_BIAS)
 			{
-				if (!(cur & kLeafBit))
+#pragma unroll 1
+				for (int rep = 0; rep < SPT_INNER_REPS; rep++)
 				{
-					const TNode* nd = bvh.nodes + cur;
-					const V4 q0 = ld4(&nd->q0), q1 = ld4(&nd->q1), q2 = ld4(&nd->q2);
-					const auto q3 = ld4u(&nd->left);
-					uint32_t c1 = q3.x, c2 = q3.y;
-					float d1, d2;
-					if (safe)
+					if (!(cur & kLeafBit))
 					{
-						d1 = SlabTestFast(o, rD, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, maxLen);
-						d2 = SlabTestFast(o, rD, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, maxLen);
-					}
-					else
-					{
-						d1 = SlabTest(o, rD, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, maxLen);
-						d2 = SlabTest(o, rD, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, maxLen);
-					}
-					if (d1 > d2) { const float tf = d1; d1 = d2; d2 = tf; const uint32_t tc = c1; c1 = c2; c2 = tc; }   // BVH.cpp:163-167
-					if (d1 == kFltMax) pop = true;                              // both children missed
-					else
-					{
-						cur = c1;
-						if (d2 != kFltMax)
+						const TNode* nd = bvh.nodes + cur;
+						const V4 q0 = ld4(&nd->q0), q1 = ld4(&nd->q1), q2 = ld4(&nd->q2);
+						const auto q3 = ld4u(&nd->left);
+						uint32_t c1 = q3.x, c2 = q3.y;
+						float d1, d2;
+						if (safe)
 						{
-							if (sp < kSmemStack) asm volatile("st.shared.u32 [%0], %1;" :: "r"(sAddr + (uint32_t)sp * (kTraceBlock * 4u)), "r"(c2) : "memory");
-							else ovf[sp - kSmemStack] = c2;
-							sp++;
+							d1 = SlabTestFast(o, rD, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, maxLen);
+							d2 = SlabTestFast(o, rD, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, maxLen);
+						}
+						else
+						{
+							d1 = SlabTest(o, rD, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, maxLen);
+							d2 = SlabTest(o, rD, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, maxLen);
+						}
+						if (d1 > d2) { const float tf = d1; d1 = d2; d2 = tf; const uint32_t tc = c1; c1 = c2; c2 = tc; }   // BVH.cpp:163-167
+						if (d1 == kFltMax)                                          // both children missed: pop
+						{
+							if (sp == 0) { finished = true; cur = kLaneIdle; }
+							else
+							{
+								sp--;
+								if (sp < kSmemStack) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cur) : "r"(sAddr + (uint32_t)sp * (kTraceBlock * 4u)) : "memory");
+								else cur = ovf[sp - kSmemStack];
+							}
+						}
+						else
+						{
+							cur = c1;
+							if (d2 != kFltMax)
+							{
+								if (sp < kSmemStack) asm volatile("st.shared.u32 [%0], %1;" :: "r"(sAddr + (uint32_t)sp * (kTraceBlock * 4u)), "r"(c2) : "memory");
+								else ovf[sp - kSmemStack] = c2;
+								sp++;
+							}
 						}
 					}
 				}
 			}
 			else
 			{
-				if (isLeaf)
+#pragma unroll 1
+				for (int rep = 0; rep < SPT_LEAF_REPS; rep++)
 				{
-					const TTri* T = bvh.tris + (cur & ~kLeafBit);
-					const V4 a = ld4(&T->a), b = ld4(&T->b), c = ld4(&T->c);
-					const uint32_t triId = f2u(c.y);
-					if (ignore != triId)                                       // BVH.cpp:136-139
+					if ((cur & kLeafBit) && cur != kLaneIdle)
 					{
-						float t, u, v;
-						if (TriTest(o, d, v3(a.x, a.y, a.z), v3(a.w, b.x, b.y), v3(b.z, b.w, c.x), maxLen, t, u, v))
+						const TTri* T = bvh.tris + (cur & ~kLeafBit);
+						const V4 a = ld4(&T->a), b = ld4(&T->b), c = ld4(&T->c);
+						const uint32_t triId = f2u(c.y);
+						bool pop = f2u(c.w) != 0u;                                  // last triangle of its leaf
+						if (ignore != triId)                                       // BVH.cpp:136-139
 						{
-							hit.t = t; hit.u = u; hit.v = v; hit.tri = triId;
-							maxLen = std_min(maxLen, t);
-							if (anyHit) { sp = 0; pop = true; }                     // hit-or-miss query: done
+							float t, u, v;
+							if (TriTest(o, d, v3(a.x, a.y, a.z), v3(a.w, b.x, b.y), v3(b.z, b.w, c.x), maxLen, t, u, v))
+							{
+								hit.t = t; hit.u = u; hit.v = v; hit.tri = triId;
+								maxLen = std_min(maxLen, t);
+								if (anyHit) { sp = 0; pop = true; }                 // hit-or-miss query: done
+							}
+						}
+						if (!pop) cur++;
+						else if (sp == 0) { finished = true; cur = kLaneIdle; }
+						else
+						{
+							sp--;
+							if (sp < kSmemStack) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cur) : "r"(sAddr + (uint32_t)sp * (kTraceBlock * 4u)) : "memory");
+							else cur = ovf[sp - kSmemStack];
 						}
 					}
-					if (f2u(c.w)) pop = true;                                   // last triangle of its leaf
-					else cur++;
-				}
-			}
-			// ---- pop / retire -------------------------------------------------------------------------------
-			bool finished = false;
-			if (pop)
-			{
-				if (sp == 0) { finished = true; cur = kLaneIdle; }
-				else
-				{
-					sp--;
-					if (sp < kSmemStack) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cur) : "r"(sAddr + (uint32_t)sp * (kTraceBlock * 4u)) : "memory");
-					else cur = ovf[sp - kSmemStack];
 				}
 			}
 			sink.Retire(finished, index, hit, anyHit);

@@ -42,7 +42,7 @@ def test_struct_layouts_match_the_header():
     # 3 pointers + 5 u32 + 3 f32 + u32 + (pad) u64 + 4 u32
     assert C.sizeof(SailorPtParams) == 88
     assert SailorPtParams.seed.offset == 64 and SailorPtParams.rowBegin.offset == 72
-    assert C.sizeof(SailorPtStats) == 112
+    assert C.sizeof(SailorPtStats) == 152
 
 
 def test_product_fails_loudly_without_a_cuda_device(scene_dir):

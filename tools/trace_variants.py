@@ -11,13 +11,9 @@ VDIR = os.path.join(ROOT, "sailor_b200", "variants")
 
 VARIANTS = {
     "base": [],
-    "idle16": ["SPT_FETCH_MIN_IDLE=16"],
-    "idle20": ["SPT_FETCH_MIN_IDLE=20"],
-    "idle24": ["SPT_FETCH_MIN_IDLE=24"],
-    "idle32": ["SPT_FETCH_MIN_IDLE=32"],
-    "fan1": ["SPT_FAN_MIN_BLOCKS=1"],
-    "fan2": ["SPT_FAN_MIN_BLOCKS=2"],
-    "fan4": ["SPT_FAN_MIN_BLOCKS=4"],
+    "exp2": ["SPT_EXPAND_MIN_BLOCKS=2"],
+    "exp3": ["SPT_EXPAND_MIN_BLOCKS=3"],
+    "exp4": ["SPT_EXPAND_MIN_BLOCKS=4"],
 }
 
 if sys.argv[1] == "build":
