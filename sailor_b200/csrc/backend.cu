@@ -116,6 +116,19 @@ namespace spt
 		g_allocStream[p] = ctx.stream;
 		return p;
 	}
+	size_t DevMemAvailable()
+	{
+		size_t freeB = 0, totalB = 0;
+		if (cudaMemGetInfo(&freeB, &totalB) != cudaSuccess) { cudaGetLastError(); return 0; }
+		// memory this process freed earlier sits in the stream-ordered pool (release threshold lifted) and is reusable
+		int dev = 0; cudaMemPool_t pool = nullptr; uint64_t reserved = 0, used = 0;
+		if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess &&
+			cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+			cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+			freeB += (size_t)(reserved - used);
+		else cudaGetLastError();
+		return freeB;
+	}
 	void DevFreeBytes(void* p)
 	{
 		if (!p) return;
@@ -373,6 +386,7 @@ namespace spt
 	double Ctx::TimerStop() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - g_t0).count(); }
 	void* DevAllocBytes(Ctx&, size_t bytes) { return malloc(bytes ? bytes : 1); }
 	void DevFreeBytes(void* p) { free(p); }
+	size_t DevMemAvailable() { return (size_t)4 << 30; }
 	void DevUpload(Ctx& ctx, void* dst, const void* src, size_t bytes) { ctx.h2dBytes += bytes; memcpy(dst, src, bytes); }
 	void DevDownload(Ctx& ctx, void* dst, const void* src, size_t bytes) { ctx.d2hBytes += bytes; memcpy(dst, src, bytes); }
 	void DevMemset(Ctx&, void* dst, int byte, size_t bytes) { memset(dst, byte, bytes); }

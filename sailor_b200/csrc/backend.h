@@ -51,6 +51,7 @@ namespace spt
 #endif
 
 	void* DevAllocBytes(Ctx& ctx, size_t bytes);
+	size_t DevMemAvailable();          // bytes a new allocation can still get (free device memory + what the pool holds back); emu: 4 GiB
 	void DevFreeBytes(void* p);
 	void DevUpload(Ctx& ctx, void* dst, const void* src, size_t bytes);
 	void DevDownload(Ctx& ctx, void* dst, const void* src, size_t bytes);   // synchronises

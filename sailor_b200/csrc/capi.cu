@@ -77,6 +77,16 @@ int32_t SailorPt_SetDevice(int32_t device)
 	return SAILOR_PT_OK;
 #endif
 }
+#if defined(SPT_TRACE_STATS) && !defined(SPT_EMU)
+// tuning builds only (tools/trace_variants.py): read and clear the lane-state counters of the traversal warp loop
+extern "C" SAILOR_PT_API int32_t SailorPt_DebugTraceStats(unsigned long long* out)
+{
+	if (cudaMemcpyFromSymbol(out, spt::g_traceStats, sizeof(unsigned long long) * 16) != cudaSuccess) return SAILOR_PT_ERR_CUDA;
+	static const unsigned long long zero[16] = {};
+	cudaMemcpyToSymbol(spt::g_traceStats, zero, sizeof(zero));
+	return SAILOR_PT_OK;
+}
+#endif
 int32_t SailorPt_GetStats(SailorPtStats* s) { if (!s) return SAILOR_PT_ERR_ARG; *s = g_stats; return SAILOR_PT_OK; }
 
 int32_t SailorPt_ParseCommandLineArgs(SailorPtParams* res, const char** args, int32_t num)

@@ -150,7 +150,19 @@ namespace spt
 	// (BatchCounters::overflow) and the batch is redone at half the size, so the factors only affect speed.
 	struct BatchPlan { uint32_t firstHits, rayCap, auxCap, recCap, skyCap; };
 
-	inline BatchPlan PlanBatch(uint64_t hitCount, uint32_t D, uint32_t A, uint32_t S, uint32_t maxBounces, bool ambientOn, uint32_t shrink)
+	// Working-set budget of one batch of first hits: 16 GiB of the B200's 180 GB, never more than a third of what the device
+	// can still give (`held` = bytes the scene's arenas already own, which the batch reuses).  Decided once per frame.
+	inline uint64_t BatchBudget(uint64_t held)
+	{
+		uint64_t budget = 16384ull << 20;
+		const uint64_t avail = ((uint64_t)DevMemAvailable() + held) / 3u;
+		if (avail && budget > avail) budget = avail;
+		if (budget < (256ull << 20)) budget = 256ull << 20;
+		if (const char* e = getenv("SAILOR_PT_BATCH_MB")) { const long v = atol(e); if (v > 0) budget = (uint64_t)v << 20; }
+		return budget;
+	}
+
+	inline BatchPlan PlanBatch(uint64_t budget, uint64_t hitCount, uint32_t D, uint32_t A, uint32_t S, uint32_t maxBounces, bool ambientOn, uint32_t shrink)
 	{
 		const uint64_t kDepthFactor = maxBounces < 3u ? maxBounces : 3u;
 		if (!ambientOn) { A = 0; S = 0; }
@@ -159,8 +171,6 @@ namespace spt
 		const uint64_t auxPer = lvl0 + kDepthFactor * lvl1;
 		const uint64_t recPer = 2u + kDepthFactor * S;
 		const uint64_t bytesPer = raysPer * (sizeof(RayRec) + sizeof(Hit) + 4u) + auxPer * (sizeof(RayAux) + 1u) + recPer * sizeof(NodeRec);
-		uint64_t budget = 6144ull << 20;
-		if (const char* e = getenv("SAILOR_PT_BATCH_MB")) { const long v = atol(e); if (v > 0) budget = (uint64_t)v << 20; }
 		uint64_t B = budget / bytesPer;
 		B >>= shrink;
 		if (B < 1024u) B = 1024u;
@@ -229,9 +239,14 @@ namespace spt
 			const uint32_t levels = p.maxBounces + 1u;
 			uint32_t shrink = 0;
 			uint32_t done = 0;
+			uint64_t held = 0;
+			for (const int k : { 0, 1, 2, 3, 8, 9, 10, 11, 12, 13, 14 }) held += D.renderMem[k].n;
+			const uint64_t budget = BatchBudget(held);
+			const bool hostTrace = getenv("SAILOR_PT_TRACE_HOST") != nullptr;
+			const double tFrame0 = HostNow();
 			while (done < hitCount && ctx.ok)
 			{
-				const BatchPlan plan = PlanBatch(hitCount - done, numLights, p.numAmbientSamples, p.numSamples, p.maxBounces, ambientOn, shrink);
+				const BatchPlan plan = PlanBatch(budget, hitCount - done, numLights, p.numAmbientSamples, p.numSamples, p.maxBounces, ambientOn, shrink);
 				IntegratorArgs a;
 				a.shade = D.shade.p; a.centroid = D.centroid.p; a.materials = D.materials.p; a.tex.texels = D.texels.p; a.tex.textures = D.textures.p;
 				a.lights = D.lights.p; a.numLights = numLights; a.blueNoise = blue;
@@ -250,9 +265,12 @@ namespace spt
 				a.fanSlots[0] = EnsureBytes<uint32_t>(ctx, D.renderMem[14], (size_t)a.fanCap * 8u); a.fanSlots[1] = a.fanSlots[0] + (size_t)a.fanCap * 4u;
 				a.c = counters; a.sampleBuf = sampleBuf;
 				if (!ctx.ok) return SAILOR_PT_ERR_CUDA;
+				if (hostTrace) fprintf(stderr, "[sailor_pt] t=%.3f ms batch: first hits %u of %u (done %u), budget %.1f GiB, rayCap %u auxCap %u recCap %u shrink %u\n",
+					(HostNow() - tFrame0) * 1e3, plan.firstHits, hitCount, done, (double)budget / (1 << 30), plan.rayCap, plan.auxCap, plan.recCap, shrink);
 
 				launch_for(ctx, 1, BeginBatchKernel{ counters, plan.firstHits });
 				launch_for(ctx, plan.firstHits, SeedKernel{ a });
+				uint32_t usedLevels = levels;
 				for (uint32_t level = 0; level < levels; level++)
 				{
 					const LevelInfo* L = &counters->level[level];
@@ -286,9 +304,19 @@ namespace spt
 						}
 					}
 					launch_for(ctx, 1, NextLevelKernel{ counters, level, plan.recCap });
+					// A level without activations ends the batch (paths that left the scene, the 0.01 throughput cut): one 8-byte read
+					// per level instead of six launches for every remaining level (a convex object's batch stops after level 1).
+					if (level + 1u < levels)
+					{
+						uint32_t nextRange[2] = { 0u, 0u };
+						DevDownload(ctx, nextRange, &counters->level[level + 1u].recBegin, sizeof(nextRange));      // synchronises
+						if (!ctx.ok) break;
+						if (hostTrace) fprintf(stderr, "[sailor_pt] t=%.3f ms   level %u done, next level has %u activations\n", (HostNow() - tFrame0) * 1e3, level, nextRange[1] - nextRange[0]);
+						if (nextRange[1] <= nextRange[0]) { usedLevels = level + 1u; break; }
+					}
 				}
 				st[3].Begin(ctx);
-				for (uint32_t level = levels; level-- > 0;)
+				for (uint32_t level = usedLevels; level-- > 0;)
 				{
 					const LevelInfo* L = &counters->level[level];
 					launch_for_range(ctx, &L->recBegin, &L->recEnd, plan.recCap, level == 0 ? plan.firstHits : plan.recCap, GatherKernel{ a });

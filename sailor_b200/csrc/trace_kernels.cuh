@@ -80,6 +80,15 @@ namespace spt
 #endif
 	constexpr uint32_t kLaneIdle = 0xFFFFFFFFu;
 
+#if defined(SPT_TRACE_STATS)
+	// tuning aid (tools/trace_variants.py "stats" variant): lane-state sums over every vote of every warp
+	// 0 votes, 1 idle lanes, 2 leaf lanes, 3 inner lanes, 4 inner reps, 5 lanes active in inner reps, 6 leaf reps, 7 lanes active in leaf reps, 8 refills, 9 lanes refilled
+	__device__ unsigned long long g_traceStats[16];
+#define SPT_STAT(i, v) do { if (lane == 0) st_[i] += (v); } while (0)
+#else
+#define SPT_STAT(i, v) do { } while (0)
+#endif
+
 	template<class Source, class Sink>
 	__device__ __forceinline__ void TraceWarpLoop(const BvhView& bvh, uint32_t n, uint32_t* __restrict__ counter, uint32_t* stackMem, Source& src, Sink& sink)
 	{
@@ -94,6 +103,9 @@ namespace spt
 		uint32_t cur = kLaneIdle;
 		int sp = 0;
 		bool exhausted = false;
+#if defined(SPT_TRACE_STATS)
+		unsigned long long st_[10] = {};
+#endif
 
 		for (;;)
 		{
@@ -108,6 +120,7 @@ namespace spt
 					if (lane == 0) base = atomicAdd(counter, want);
 					base = __shfl_sync(0xffffffffu, base, 0);
 					if (base + want >= n) exhausted = true;
+					SPT_STAT(8, 1); SPT_STAT(9, want);
 					if (cur == kLaneIdle)
 					{
 						const uint32_t i = base + (uint32_t)__popc(idleMask & ((1u << lane) - 1u));
@@ -123,7 +136,13 @@ namespace spt
 					}
 					continue;
 				}
-				if (idleMask == 0xffffffffu) break;          // queue exhausted and every lane retired
+				if (idleMask == 0xffffffffu)                  // queue exhausted and every lane retired
+				{
+#if defined(SPT_TRACE_STATS)
+					if (lane == 0) for (int k = 0; k < 10; k++) atomicAdd(&g_traceStats[k], st_[k]);
+#endif
+					break;
+				}
 			}
 			// ---- vote: the step most busy lanes need --------------------------------------------------------
 			const bool isLeaf = (cur & kLeafBit) && cur != kLaneIdle;
@@ -132,11 +151,15 @@ namespace spt
 			// The chosen step is repeated a few times per vote (lanes that left the mode sit out): the vote, the refill check
 			// and the retire cost ~45 warp-wide instructions, a step ~80.
 			bool finished = false;
+			SPT_STAT(0, 1); SPT_STAT(1, __popc(idleMask)); SPT_STAT(2, nLeaf); SPT_STAT(3, nInner);
 			if (nInner * SPT_VOTE_INNER_BIAS >= nLeaf * SPT_VOTE_LEAF_BIAS)
 			{
 #pragma unroll 1
 				for (int rep = 0; rep < SPT_INNER_REPS; rep++)
 				{
+#if defined(SPT_TRACE_STATS)
+					{ const uint32_t am = __ballot_sync(0xffffffffu, !(cur & kLeafBit)); SPT_STAT(4, 1); SPT_STAT(5, __popc(am)); }
+#endif
 					if (!(cur & kLeafBit))
 					{
 						const TNode* nd = bvh.nodes + cur;
@@ -176,6 +199,9 @@ namespace spt
 							}
 						}
 					}
+#if defined(SPT_DYN_REPS)
+					if (__popc(__ballot_sync(0xffffffffu, !(cur & kLeafBit))) * 2 < nInner) break;   // most lanes left the mode: vote again
+#endif
 				}
 			}
 			else
@@ -183,6 +209,9 @@ namespace spt
 #pragma unroll 1
 				for (int rep = 0; rep < SPT_LEAF_REPS; rep++)
 				{
+#if defined(SPT_TRACE_STATS)
+					{ const uint32_t am = __ballot_sync(0xffffffffu, (cur & kLeafBit) && cur != kLaneIdle); SPT_STAT(6, 1); SPT_STAT(7, __popc(am)); }
+#endif
 					if ((cur & kLeafBit) && cur != kLaneIdle)
 					{
 						const TTri* T = bvh.tris + (cur & ~kLeafBit);
@@ -208,6 +237,9 @@ namespace spt
 							else cur = ovf[sp - kSmemStack];
 						}
 					}
+#if defined(SPT_DYN_REPS)
+					if (__popc(__ballot_sync(0xffffffffu, (cur & kLeafBit) && cur != kLaneIdle)) * 2 < nLeaf) break;
+#endif
 				}
 			}
 			sink.Retire(finished, index, hit, anyHit);

@@ -50,25 +50,20 @@ namespace spt
 		const float det = dot(e1, p);
 		float u, v;
 		V3 perp;
-		if (det > 0.0f)
+		// The two signed branches of the GLM routine (Bounds.h:207-243) compute the same u, perp and v and differ only in the
+		// comparisons, so they are evaluated once and the reference's comparisons are selected by the sign of det (NaNs
+		// behave as in the reference: every comparison with a NaN is false).  A warp whose lanes see both signs issues the
+		// arithmetic once: -7 % traversal time on the 1M-triangle scene (profiles/r01b_SUMMARY.md).
 		{
 			const V3 dist = o - v0;
 			u = dot(dist, p);
-			if (u < 0.0f || u > det) return false;
 			perp = cross(dist, e1);
 			v = dot(d, perp);
-			if ((v < 0.0f) || ((u + v) > det)) return false;
+			const float uv = u + v;
+			const bool pos = (det > 0.0f) & !((u < 0.0f) | (u > det)) & !((v < 0.0f) | (uv > det));
+			const bool neg = (det < 0.0f) & !((u > 0.0f) | (u < det)) & !((v > 0.0f) | (uv < det));
+			if (!(pos | neg)) return false;
 		}
-		else if (det < 0.0f)
-		{
-			const V3 dist = o - v0;
-			u = dot(dist, p);
-			if ((u > 0.0f) || (u < det)) return false;
-			perp = cross(dist, e1);
-			v = dot(d, perp);
-			if ((v > 0.0f) || (u + v < det)) return false;
-		}
-		else return false;
 		const float invDet = 1.0f / det;
 		const float t = dot(e2, perp) * invDet;
 		u *= invDet; v *= invDet;

@@ -26,6 +26,7 @@ def build():
         return lib
     cmd = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-DSPT_EMU", "-fvisibility=hidden",
            "-I", os.path.join(ROOT, "include"), "-o", lib]
+    cmd += ["-D" + d for d in os.environ.get("SPT_EMU_DEFINES", "").split()]      # tuning variants are checked on the host first
     for s in srcs:
         cmd += (["-x", "c++", s] if s.endswith(".cu") else ["-x", "c++", s])
     cmd += ["-lz"]

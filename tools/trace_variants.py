@@ -11,9 +11,14 @@ VDIR = os.path.join(ROOT, "sailor_b200", "variants")
 
 VARIANTS = {
     "base": [],
-    "exp2": ["SPT_EXPAND_MIN_BLOCKS=2"],
-    "exp3": ["SPT_EXPAND_MIN_BLOCKS=3"],
-    "exp4": ["SPT_EXPAND_MIN_BLOCKS=4"],
+    "stats": ["SPT_TRACE_STATS"],
+    "tri": ["SPT_TRI_UNIFIED"],
+    "idle8": ["SPT_FETCH_MIN_IDLE=8"],
+    "idle4": ["SPT_FETCH_MIN_IDLE=4"],
+    "dyn": ["SPT_DYN_REPS", "SPT_INNER_REPS=8", "SPT_LEAF_REPS=4"],
+    "dyn_tri_idle8": ["SPT_DYN_REPS", "SPT_INNER_REPS=8", "SPT_LEAF_REPS=4", "SPT_TRI_UNIFIED", "SPT_FETCH_MIN_IDLE=8"],
+    "reps21": ["SPT_INNER_REPS=2", "SPT_LEAF_REPS=1"],
+    "reps63": ["SPT_INNER_REPS=6", "SPT_LEAF_REPS=3"],
 }
 
 if sys.argv[1] == "build":
@@ -51,5 +56,15 @@ else:
                     s.render_resident(p, rebuild_bvh=False, output_stage=False); st = L.stats(); tr.append((st["secondsTraverse"], st["secondsFlatten"], st["rays"]))
                 best = min(tr)
                 row[tag + "_trace_ms"] = round(best[0] * 1e3, 2); row[tag + "_step_ms"] = round(best[1] * 1e3, 2); row[tag + "_trace_Grays"] = round(best[2] / best[0] / 1e9, 3)
+        if hasattr(L.lib, "SailorPt_DebugTraceStats"):
+            import ctypes
+            buf = (ctypes.c_ulonglong * 16)()
+            L.lib.SailorPt_DebugTraceStats(buf)          # clear
+            with L.load_scene(hf) as s:
+                s.build_bvh(); s.render_resident(bench.make_params(bench.WORKLOADS["c3"], seed=1), rebuild_bvh=False, output_stage=False)
+            L.lib.SailorPt_DebugTraceStats(buf)
+            v = list(buf)
+            row["stats"] = dict(votes=v[0], idle_per_vote=v[1] / v[0], leaf_per_vote=v[2] / v[0], inner_per_vote=v[3] / v[0], inner_reps=v[4], lanes_per_inner_rep=v[5] / max(v[4], 1),
+                                leaf_reps=v[6], lanes_per_leaf_rep=v[7] / max(v[6], 1), refills=v[8], lanes_per_refill=v[9] / max(v[8], 1))
         res[f] = row
         print(f, json.dumps(row), flush=True)
