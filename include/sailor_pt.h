@@ -126,6 +126,18 @@ SAILOR_PT_API void SailorPt_SceneFree(SailorPtScene* scene);
 SAILOR_PT_API int32_t SailorPt_SceneCounts(const SailorPtScene* scene, uint32_t counts[6]);
 /* triangles: numTriangles*SAILOR_PT_TRI_FLOATS floats; materialIndex: numTriangles bytes (either may be NULL). */
 SAILOR_PT_API int32_t SailorPt_SceneGetTriangles(const SailorPtScene* scene, float* triangles, uint8_t* materialIndex);
+/* Material import (PathTracer.cpp:164-360 -> Raytracing::Material, MaterialUtils.h:138-177): the fields the live integrator
+ * reads, SAILOR_PT_MATERIAL_WORDS 32-bit words per material:
+ *   [0..8]  m_uvTransform (glm::mat3, column-major)   [9..12] m_baseColorFactor   [13..15] m_emissiveFactor
+ *   [16..18] m_attenuationColor   [19] m_metallicFactor   [20] m_roughnessFactor   [21] m_indexOfRefraction
+ *   [22] m_transmissionFactor   [23] m_alphaCutoff   [24] m_thicknessFactor   [25] m_attenuationDistance
+ *   then as uint32: [26] m_blendMode (0 opaque, 1 blend, 2 mask), [27] m_baseColorIndex, [28] m_normalIndex,
+ *   [29] m_metallicRoughnessIndex, [30] m_emissiveIndex, [31] m_transmissionIndex (255 = no texture, the reference's u8(-1)). */
+#define SAILOR_PT_MATERIAL_WORDS 32
+SAILOR_PT_API int32_t SailorPt_SceneGetMaterials(const SailorPtScene* scene, uint32_t* words);
+/* Directional lights (PathTracer.cpp:362-381 -> DirectionalLight, LightingModel.h:10-14): 6 floats per light,
+ * m_direction then m_intensity (= color * intensity / 683). */
+SAILOR_PT_API int32_t SailorPt_SceneGetLights(const SailorPtScene* scene, float* directionAndIntensity);
 
 /* BVH::BuildBVH (BVH.cpp:280-338).  Idempotent. */
 SAILOR_PT_API int32_t SailorPt_BuildBVH(SailorPtScene* scene);

@@ -672,6 +672,37 @@ int32_t SailorPt_SceneCounts(const SailorPtScene* s, uint32_t c[6])
 	return SAILOR_PT_OK;
 }
 
+int32_t SailorPt_SceneGetMaterials(const SailorPtScene* s, uint32_t* words)
+{
+	if (!s || !words) return SAILOR_PT_ERR_ARG;
+	for (size_t i = 0; i < s->tracer.m_materials.Num(); i++)
+	{
+		const Material& m = s->tracer.m_materials[i];          // MaterialUtils.h:138-177
+		uint32_t* w = words + i * SAILOR_PT_MATERIAL_WORDS;
+		float f[26];
+		for (int c = 0; c < 3; c++) for (int r = 0; r < 3; r++) f[c * 3 + r] = m.m_uvTransform[c][r];
+		for (int k = 0; k < 4; k++) f[9 + k] = m.m_baseColorFactor[k];
+		for (int k = 0; k < 3; k++) { f[13 + k] = m.m_emissiveFactor[k]; f[16 + k] = m.m_attenuationColor[k]; }
+		f[19] = m.m_metallicFactor; f[20] = m.m_roughnessFactor; f[21] = m.m_indexOfRefraction; f[22] = m.m_transmissionFactor;
+		f[23] = m.m_alphaCutoff; f[24] = m.m_thicknessFactor; f[25] = m.m_attenuationDistance;
+		memcpy(w, f, sizeof(f));
+		w[26] = (uint32_t)m.m_blendMode; w[27] = m.m_baseColorIndex; w[28] = m.m_normalIndex; w[29] = m.m_metallicRoughnessIndex;
+		w[30] = m.m_emissiveIndex; w[31] = m.m_transmissionIndex;
+	}
+	return SAILOR_PT_OK;
+}
+
+int32_t SailorPt_SceneGetLights(const SailorPtScene* s, float* out)
+{
+	if (!s || !out) return SAILOR_PT_ERR_ARG;
+	for (size_t i = 0; i < s->tracer.m_directionalLights.Num(); i++)
+	{
+		const DirectionalLight& l = s->tracer.m_directionalLights[i];   // LightingModel.h:10-14
+		for (int k = 0; k < 3; k++) { out[i * 6 + k] = l.m_direction[k]; out[i * 6 + 3 + k] = l.m_intensity[k]; }
+	}
+	return SAILOR_PT_OK;
+}
+
 int32_t SailorPt_SceneGetTriangles(const SailorPtScene* s, float* tris, uint8_t* mat)
 {
 	if (!s) return SAILOR_PT_ERR_ARG;

@@ -14,6 +14,7 @@ import os
 
 import numpy as np
 
+MATERIAL_WORDS = 32
 TRI_FLOATS = 51
 
 OK = 0
@@ -51,7 +52,7 @@ HIT_DTYPE = np.dtype([("t", "<f4"), ("baryU", "<f4"), ("baryV", "<f4"), ("triId"
 # every symbol include/sailor_pt.h declares (tests check the built libraries export all of them)
 SYMBOLS = [
     "SailorPt_ParseCommandLineArgs", "SailorPt_Run", "SailorPt_SceneLoad", "SailorPt_SceneFree",
-    "SailorPt_SceneCounts", "SailorPt_SceneGetTriangles", "SailorPt_BuildBVH", "SailorPt_GetBVH",
+    "SailorPt_SceneCounts", "SailorPt_SceneGetTriangles", "SailorPt_SceneGetMaterials", "SailorPt_SceneGetLights", "SailorPt_BuildBVH", "SailorPt_GetBVH",
     "SailorPt_GetCamera", "SailorPt_IntersectRays", "SailorPt_PrimaryHits", "SailorPt_Render",
     "SailorPt_OutputStage", "SailorPt_SampleTexture", "SailorPt_EvalLighting", "SailorPt_GetStats",
     "SailorPt_LastError", "SailorPt_Backend", "SailorPt_RenderResident", "SailorPt_ReadResident", "SailorPt_CopyResidentToDevice", "SailorPt_SetDevice", "SailorPt_OutputStageResident",
@@ -123,6 +124,8 @@ class Library:
         lib.SailorPt_SceneFree.restype = None
         lib.SailorPt_SceneCounts.argtypes = [C.c_void_p, P(C.c_uint32)]
         lib.SailorPt_SceneGetTriangles.argtypes = [C.c_void_p, P(C.c_float), P(C.c_uint8)]
+        lib.SailorPt_SceneGetMaterials.argtypes = [C.c_void_p, P(C.c_uint32)]
+        lib.SailorPt_SceneGetLights.argtypes = [C.c_void_p, P(C.c_float)]
         lib.SailorPt_BuildBVH.argtypes = [C.c_void_p]
         lib.SailorPt_GetBVH.argtypes = [C.c_void_p, C.c_void_p, P(C.c_uint32)]
         lib.SailorPt_GetCamera.argtypes = [C.c_void_p, P(SailorPtParams), P(C.c_uint32), P(C.c_uint32), P(C.c_float)]
@@ -232,6 +235,20 @@ class Scene:
         mat = np.empty(n, np.uint8)
         self.L.check(self.L.lib.SailorPt_SceneGetTriangles(self.h, _ptr(tris, C.c_float), _ptr(mat, C.c_uint8)), "SailorPt_SceneGetTriangles")
         return tris, mat
+
+    def materials(self):
+        """(n, 32) uint32 words per material: 26 float fields then blend mode and texture slots (include/sailor_pt.h)."""
+        words = np.zeros((self.counts()["materials"], MATERIAL_WORDS), np.uint32)
+        if len(words):
+            self.L.check(self.L.lib.SailorPt_SceneGetMaterials(self.h, _ptr(words, C.c_uint32)), "SailorPt_SceneGetMaterials")
+        return words
+
+    def lights(self):
+        """(n, 6) float32: direction, intensity of every directional light."""
+        out = np.zeros((self.counts()["lights"], 6), np.float32)
+        if len(out):
+            self.L.check(self.L.lib.SailorPt_SceneGetLights(self.h, _ptr(out, C.c_float)), "SailorPt_SceneGetLights")
+        return out
 
     def build_bvh(self):
         self.L.check(self.L.lib.SailorPt_BuildBVH(self.h), "SailorPt_BuildBVH")

@@ -168,6 +168,32 @@ int32_t SailorPt_SceneCounts(const SailorPtScene* s, uint32_t c[6])
 	return SAILOR_PT_OK;
 }
 
+int32_t SailorPt_SceneGetMaterials(const SailorPtScene* s, uint32_t* words)
+{
+	if (!s || !words) return SAILOR_PT_ERR_ARG;
+	for (size_t i = 0; i < s->dev.host.materials.size(); i++)
+	{
+		const MaterialGpu& m = s->dev.host.materials[i];
+		uint32_t* w = words + i * SAILOR_PT_MATERIAL_WORDS;
+		float f[26];
+		for (int c = 0; c < 3; c++) for (int r = 0; r < 3; r++) f[c * 3 + r] = m.uvTransform[c * 4 + r];
+		for (int k = 0; k < 4; k++) f[9 + k] = m.baseColor[k];
+		for (int k = 0; k < 3; k++) { f[13 + k] = m.emissive[k]; f[16 + k] = m.attenuationColor[k]; }
+		f[19] = m.metallic; f[20] = m.roughness; f[21] = m.ior; f[22] = m.transmission; f[23] = m.alphaCutoff; f[24] = m.thickness; f[25] = m.attenuationDistance;
+		memcpy(w, f, sizeof(f));
+		w[26] = m.blendMode; w[27] = m.texBase; w[28] = m.texNormal; w[29] = m.texMetallicRoughness; w[30] = m.texEmissive; w[31] = m.texTransmission;
+	}
+	return SAILOR_PT_OK;
+}
+
+int32_t SailorPt_SceneGetLights(const SailorPtScene* s, float* out)
+{
+	if (!s || !out) return SAILOR_PT_ERR_ARG;
+	for (size_t i = 0; i < s->dev.host.lights.size(); i++)
+		for (int k = 0; k < 3; k++) { out[i * 6 + k] = s->dev.host.lights[i].direction[k]; out[i * 6 + 3 + k] = s->dev.host.lights[i].intensity[k]; }
+	return SAILOR_PT_OK;
+}
+
 int32_t SailorPt_SceneGetTriangles(const SailorPtScene* cs, float* tris, uint8_t* mat)
 {
 	if (!cs) return SAILOR_PT_ERR_ARG;

@@ -11,6 +11,13 @@
                         metallic-roughness / emissive textures (procedural PNGs), KHR_texture_transform, an alpha-BLEND
                         quad, a MASK quad, a thick transmissive (volume) box, a mirror, emissive quads, two directional
                         lights, a named camera.
+* gallery()           — SURVEY §8(d) config C4: an 8 x 8 floor of PBR tiles, every tile with its OWN material (baseColor +
+                        normal + occlusion/roughness/metallic textures, procedural, seed 1) and a box of that material on
+                        it, 32 emissive quads (each with its own emissive texture) hovering above, four directional
+                        lights, one camera: 96 materials, 224 textures (the reference's u8 slots allow 255).
+* instanced_heightfield() — config C5: ONE heightfield mesh (LCG seed 2) instanced by `instances` nodes with their own
+                        translation / rotation / scale (node-level instancing is what glTF offers); 10 instances of
+                        n=707 -> 9,996,980 triangles.
 All files are GLB with embedded buffers, written into a caller-supplied directory.
 """
 import json
@@ -96,16 +103,18 @@ class GlbBuilder:
         return path
 
 
-def png_bytes(img: np.ndarray) -> bytes:
+def png_bytes(img: np.ndarray, level=6) -> bytes:
     """8-bit RGB / RGBA PNG (filter 0)."""
     img = np.ascontiguousarray(img, np.uint8)
     h, w, c = img.shape
-    raw = b"".join(b"\0" + img[y].tobytes() for y in range(h))
+    rows = np.zeros((h, 1 + w * c), np.uint8)
+    rows[:, 1:] = img.reshape(h, w * c)
+    raw = rows.tobytes()
 
     def chunk(t, d):
         return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xFFFFFFFF)
     return (b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 2 if c == 3 else 6, 0, 0, 0)) +
-            chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b""))
+            chunk(b"IDAT", zlib.compress(raw, level)) + chunk(b"IEND", b""))
 
 
 def quat_from_to_neg_z(direction):
@@ -315,6 +324,99 @@ def pbr_scene(path, tex_size=64):
     return g.write(path)
 
 
+def _gallery_texture(size, seed, kind):
+    """Procedural tile textures, different for every seed (periods and phases drawn from RandomState(seed))."""
+    r = np.random.RandomState(seed)
+    y, x = np.mgrid[0:size, 0:size].astype(np.float32) / np.float32(size)
+    f = r.randint(2, 9, 4).astype(np.float32); ph = r.uniform(0, 6.28, 4).astype(np.float32); col = r.uniform(0.15, 1.0, (2, 3)).astype(np.float32)
+    a = 0.5 + 0.5 * np.sin(6.2831853 * f[0] * x + ph[0]) * np.sin(6.2831853 * f[1] * y + ph[1])
+    b = ((np.floor(x * f[2] * 2) + np.floor(y * f[3] * 2)) % 2).astype(np.float32)
+    if kind == "base":
+        img = (col[0][None, None, :] * a[..., None] + col[1][None, None, :] * (1 - a[..., None])) * (0.6 + 0.4 * b[..., None]) * 255
+    elif kind == "normal":
+        nx = 0.3 * np.cos(6.2831853 * f[0] * x + ph[0]) * np.sin(6.2831853 * f[1] * y + ph[1]); ny = 0.3 * np.sin(6.2831853 * f[0] * x + ph[0]) * np.cos(6.2831853 * f[1] * y + ph[1])
+        img = np.stack([(nx + 1) * 127.5, (ny + 1) * 127.5, (np.sqrt(1 - nx * nx - ny * ny) + 1) * 127.5], -1)
+    elif kind == "orm":
+        img = np.stack([np.full_like(a, 255.0), 30 + 220 * a, 255 * b * (r.uniform() < 0.5)], -1)
+    else:  # emissive
+        img = col[0][None, None, :] * (b * a)[..., None] * 255
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def gallery(path, tiles=8, emitters=32, tex_size=1024, seed=1):
+    g = GlbBuilder()
+    g.j["extensionsUsed"] = ["KHR_lights_punctual", "KHR_materials_emissive_strength", "KHR_texture_transform"]
+    r = np.random.RandomState(seed)
+    cp, cn, ci = _cube_arrays(0.5)
+    cuv = np.tile(np.array([[0, 0], [1, 0], [0, 1], [1, 1]], np.float32), (6, 1))
+    box = None
+    span = 1.0 / tiles
+    for ty in range(tiles):
+        for tx in range(tiles):
+            k = ty * tiles + tx
+            tb = g.texture(png_bytes(_gallery_texture(tex_size, seed * 1000 + 3 * k, "base"), 1))
+            tn = g.texture(png_bytes(_gallery_texture(tex_size, seed * 1000 + 3 * k + 1, "normal"), 1))
+            to = g.texture(png_bytes(_gallery_texture(tex_size, seed * 1000 + 3 * k + 2, "orm"), 1), wrap=33071 if k % 2 else 10497)
+            base = {"index": tb}
+            if k % 4 == 1:
+                base["extensions"] = {"KHR_texture_transform": {"offset": [0.25, 0.5], "scale": [2.0, 2.0], "rotation": 0.1 * k}}
+            m = g.material(pbrMetallicRoughness={"baseColorTexture": base, "metallicRoughnessTexture": {"index": to},
+                                                 "metallicFactor": float(r.uniform(0.0, 1.0)), "roughnessFactor": float(r.uniform(0.2, 1.0))},
+                           normalTexture={"index": tn})
+            c = (-0.5 + (tx + 0.5) * span, 0.0, -0.5 + (ty + 0.5) * span)
+            p, n, uv, i = _quad(c, (span / 2, 0, 0), (0, 0, -span / 2))
+            g.node(mesh=g.mesh(p, i, m, nrm=n, uv=uv))
+            h = float(r.uniform(0.02, 0.09)); sx = float(r.uniform(0.25, 0.6)) * span
+            q = quat_from_to_neg_z((math.sin(0.7 * k), 0.0, -math.cos(0.7 * k)))
+            g.node(mesh=g.mesh(cp, ci, m, nrm=cn, uv=cuv), translation=[c[0], h / 2, c[2]], rotation=q, scale=[sx, h, sx])
+    for e in range(emitters):
+        te = g.texture(png_bytes(_gallery_texture(tex_size, seed * 1000 + 500 + e, "emissive"), 1))
+        m = g.material(pbrMetallicRoughness={"baseColorFactor": [0.05, 0.05, 0.05, 1.0], "metallicFactor": 0.0},
+                       emissiveFactor=[1.0, 1.0, 1.0], emissiveTexture={"index": te},
+                       extensions={"KHR_materials_emissive_strength": {"emissiveStrength": float(r.uniform(2.0, 8.0))}})
+        c = (float(r.uniform(-0.45, 0.45)), float(r.uniform(0.15, 0.3)), float(r.uniform(-0.45, 0.45)))
+        p, n, uv, i = _quad(c, (0.03, 0, 0), (0, 0, 0.03))           # facing down
+        g.node(mesh=g.mesh(p, i, m, nrm=n, uv=uv))
+    g.j["cameras"] = [{"type": "perspective", "perspective": {"yfov": 0.75, "aspectRatio": 16.0 / 9.0, "znear": 0.01, "zfar": 100.0}}]
+    g.node(camera=0, name="main", translation=[0.0, 0.55, 0.95], rotation=look_at_quat((0.0, -0.5, -0.9)))
+    dirs = [(0.3, -1.0, 0.2), (-0.5, -0.8, -0.1), (0.1, -0.6, -0.7), (-0.2, -1.0, 0.6)]
+    g.j["extensions"] = {"KHR_lights_punctual": {"lights": [
+        {"type": "directional", "color": [1.0, 0.96 - 0.1 * k, 0.9 - 0.15 * k], "intensity": 683.0 * (0.8 - 0.15 * k)} for k in range(len(dirs))]}}
+    for k, d in enumerate(dirs):
+        g.node(name="sun%d" % k, rotation=quat_from_to_neg_z(d), extensions={"KHR_lights_punctual": {"light": k}})
+    return g.write(path)
+
+
+def instanced_heightfield(path, n=707, instances=10, seed=2):
+    g = GlbBuilder()
+    nv = n + 1
+    u = lcg_uniform_fast(nv * nv, seed)
+    jj, ii = np.meshgrid(np.arange(nv), np.arange(nv), indexing="ij")
+    pos = np.stack([-0.5 + ii / n, 0.05 * u.reshape(nv, nv), -0.5 + jj / n], axis=-1).reshape(-1, 3).astype(np.float32)
+    q = (jj[:-1, :-1] * nv + ii[:-1, :-1]).reshape(-1)
+    idx = np.stack([q, q + nv, q + 1, q + 1, q + nv, q + nv + 1], axis=-1).reshape(-1).astype(np.uint32)
+    mats = [g.material(pbrMetallicRoughness={"baseColorFactor": [0.4 + 0.05 * k, 0.75 - 0.04 * k, 0.5, 1.0], "metallicFactor": 0.1 * (k % 3), "roughnessFactor": 0.5 + 0.05 * (k % 5)})
+            for k in range(min(instances, 4))]
+    # one set of accessors; one mesh object per material, all sharing them (instancing at the node level)
+    first = g.mesh(pos, idx, mats[0])
+    meshes = [first]
+    for m in mats[1:]:
+        prim = dict(g.j["meshes"][first]["primitives"][0]); prim["material"] = m
+        g.j["meshes"].append({"primitives": [prim]}); meshes.append(len(g.j["meshes"]) - 1)
+    cols = int(math.ceil(math.sqrt(instances)))
+    for k in range(instances):
+        cx, cz = k % cols, k // cols
+        ang = 0.35 * k
+        g.node(mesh=meshes[k % len(meshes)], translation=[(cx - (cols - 1) / 2) * 0.98, 0.01 * k, -(cz * 0.98)],
+               rotation=[0.0, math.sin(ang / 2), 0.0, math.cos(ang / 2)], scale=[1.0, 1.0 + 0.2 * (k % 3), 1.0])
+    g.j["cameras"] = [{"type": "perspective", "perspective": {"yfov": 0.8, "aspectRatio": 16.0 / 9.0, "znear": 0.01, "zfar": 100.0}}]
+    g.node(camera=0, name="main", translation=[0.0, 1.1, 1.6], rotation=look_at_quat((0.0, -0.5, -0.9)))
+    g.j["extensionsUsed"] = ["KHR_lights_punctual"]
+    g.j["extensions"] = {"KHR_lights_punctual": {"lights": [{"type": "directional", "color": [1.0, 1.0, 1.0], "intensity": 2049.0}]}}
+    g.node(name="sun", rotation=quat_from_to_neg_z((0.3, -1.0, 0.2)), extensions={"KHR_lights_punctual": {"light": 0}})
+    return g.write(path)
+
+
 def ensure(directory, name, **kw):
     """Create (once) and return the path of a named scene."""
     os.makedirs(directory, exist_ok=True)
@@ -328,4 +430,12 @@ def ensure(directory, name, **kw):
         n = kw.get("n", 64)
         p = os.path.join(directory, "heightfield_%d.glb" % n)
         return p if os.path.exists(p) else heightfield(p, n=n)
+    if name == "gallery":
+        ts, tiles, em = kw.get("tex_size", 1024), kw.get("tiles", 8), kw.get("emitters", 32)
+        p = os.path.join(directory, "gallery_%d_%d_%d.glb" % (tiles, em, ts))
+        return p if os.path.exists(p) else gallery(p, tiles=tiles, emitters=em, tex_size=ts)
+    if name == "instanced":
+        n, k = kw.get("n", 707), kw.get("instances", 10)
+        p = os.path.join(directory, "instanced_%d_x%d.glb" % (n, k))
+        return p if os.path.exists(p) else instanced_heightfield(p, n=n, instances=k)
     raise KeyError(name)
