@@ -176,6 +176,13 @@ SAILOR_PT_API int32_t SailorPt_CopyResidentToDevice(SailorPtScene* scene, void* 
  * floats, e.g. the NCCL-reduced frame) first replaces the resident accumulator.  The sRGB8 image stays resident. */
 SAILOR_PT_API int32_t SailorPt_OutputStageResident(SailorPtScene* scene, const void* srcDevice, uint64_t bytes);
 
+/* Product: page-lock a caller-owned HOST buffer (the result images a host reuses frame after frame) so that SailorPt_Render /
+ * SailorPt_ReadResident DMA straight into it instead of staging through the library's own pinned chunks and a host memcpy.
+ * The buffer must be unpinned before it is freed.  Results are identical either way.  The reference has no counterpart (its
+ * image lives in host memory, PathTracer.cpp:449-469); the oracle accepts and ignores both calls. */
+SAILOR_PT_API int32_t SailorPt_PinHostBuffer(void* hostBuffer, uint64_t bytes);
+SAILOR_PT_API int32_t SailorPt_UnpinHostBuffer(void* hostBuffer);
+
 /* Output stage alone (PathTracer.cpp:535-565 + Core/Utils.cpp:48-57). */
 SAILOR_PT_API int32_t SailorPt_OutputStage(uint32_t width, uint32_t height, const float* linearRGB, uint8_t* srgb8);
 

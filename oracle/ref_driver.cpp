@@ -626,6 +626,8 @@ extern "C" {
 const char* SailorPt_Backend(void) { return "reference-cpu"; }
 int32_t SailorPt_OutputStageResident(SailorPtScene*, const void*, uint64_t) { return SAILOR_PT_ERR_UNSUPPORTED; }
 int32_t SailorPt_SetDevice(int32_t device) { return device == 0 ? SAILOR_PT_OK : SAILOR_PT_ERR_ARG; }
+int32_t SailorPt_PinHostBuffer(void* hostBuffer, uint64_t bytes) { return (hostBuffer && bytes) ? SAILOR_PT_OK : SAILOR_PT_ERR_ARG; }   // host memory is the oracle's own memory
+int32_t SailorPt_UnpinHostBuffer(void* hostBuffer) { return hostBuffer ? SAILOR_PT_OK : SAILOR_PT_ERR_ARG; }
 const char* SailorPt_LastError(void) { return t_lastError.c_str(); }
 int32_t SailorPt_GetStats(SailorPtStats* s) { if (!s) return SAILOR_PT_ERR_ARG; *s = g_stats; return SAILOR_PT_OK; }
 

@@ -56,6 +56,7 @@ SYMBOLS = [
     "SailorPt_GetCamera", "SailorPt_IntersectRays", "SailorPt_PrimaryHits", "SailorPt_Render",
     "SailorPt_OutputStage", "SailorPt_SampleTexture", "SailorPt_EvalLighting", "SailorPt_GetStats",
     "SailorPt_LastError", "SailorPt_Backend", "SailorPt_RenderResident", "SailorPt_ReadResident", "SailorPt_CopyResidentToDevice", "SailorPt_SetDevice", "SailorPt_OutputStageResident",
+    "SailorPt_PinHostBuffer", "SailorPt_UnpinHostBuffer",
 ]
 
 
@@ -141,6 +142,8 @@ class Library:
         lib.SailorPt_GetStats.argtypes = [P(SailorPtStats)]
         lib.SailorPt_SetDevice.argtypes = [C.c_int32]
         lib.SailorPt_OutputStageResident.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        lib.SailorPt_PinHostBuffer.argtypes = [C.c_void_p, C.c_uint64]
+        lib.SailorPt_UnpinHostBuffer.argtypes = [C.c_void_p]
         lib.SailorPt_LastError.restype = C.c_char_p
         lib.SailorPt_Backend.restype = C.c_char_p
         for s in SYMBOLS:
@@ -158,6 +161,13 @@ class Library:
 
     def set_device(self, index):
         self.check(self.lib.SailorPt_SetDevice(index), "SailorPt_SetDevice")
+
+    def pin_host_buffer(self, array):
+        """Page-lock a numpy array the caller reuses for results (SailorPt_PinHostBuffer); unpin before dropping it."""
+        self.check(self.lib.SailorPt_PinHostBuffer(array.ctypes.data, array.nbytes), "SailorPt_PinHostBuffer")
+
+    def unpin_host_buffer(self, array):
+        self.check(self.lib.SailorPt_UnpinHostBuffer(array.ctypes.data), "SailorPt_UnpinHostBuffer")
 
     def stats(self):
         s = SailorPtStats()

@@ -213,11 +213,45 @@ namespace spt
 		CopyPool* g_copyPool = new CopyPool();      // leaked on purpose: helper threads may outlive static destruction
 	}
 
+	namespace
+	{
+		std::mutex g_pinMutex;
+		std::unordered_map<void*, size_t> g_pinned;
+		bool IsPinned(const void* p, size_t bytes)
+		{
+			std::lock_guard<std::mutex> lock(g_pinMutex);
+			for (const auto& kv : g_pinned)
+			{
+				const unsigned char* b = (const unsigned char*)kv.first;
+				if ((const unsigned char*)p >= b && (const unsigned char*)p + bytes <= b + kv.second) return true;
+			}
+			return false;
+		}
+	}
+	int HostPin(void* p, size_t bytes)
+	{
+		if (!p || !bytes) return -1;
+		std::lock_guard<std::mutex> lock(g_pinMutex);
+		if (g_pinned.count(p)) return g_pinned[p] >= bytes ? 0 : -1;
+		if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) != cudaSuccess) { cudaGetLastError(); return -1; }
+		g_pinned[p] = bytes;
+		return 0;
+	}
+	int HostUnpin(void* p)
+	{
+		std::lock_guard<std::mutex> lock(g_pinMutex);
+		auto it = g_pinned.find(p);
+		if (it == g_pinned.end()) return -1;
+		g_pinned.erase(it);
+		if (cudaHostUnregister(p) != cudaSuccess) { cudaGetLastError(); return -1; }
+		return 0;
+	}
+
 	void DevDownload(Ctx& ctx, void* dst, const void* src, size_t bytes)
 	{
 		if (!ctx.ok) return;
 		ctx.d2hBytes += bytes;
-		if (bytes >= (1u << 20))
+		if (bytes >= (1u << 20) && !IsPinned(dst, bytes))
 		{
 			std::lock_guard<std::mutex> lock(g_stageMutex);
 			if (EnsureStage())
@@ -389,6 +423,8 @@ namespace spt
 	size_t DevMemAvailable() { return (size_t)4 << 30; }
 	void DevUpload(Ctx& ctx, void* dst, const void* src, size_t bytes) { ctx.h2dBytes += bytes; memcpy(dst, src, bytes); }
 	void DevDownload(Ctx& ctx, void* dst, const void* src, size_t bytes) { ctx.d2hBytes += bytes; memcpy(dst, src, bytes); }
+	int HostPin(void* p, size_t bytes) { return (p && bytes) ? 0 : -1; }
+	int HostUnpin(void* p) { return p ? 0 : -1; }
 	void DevMemset(Ctx&, void* dst, int byte, size_t bytes) { memset(dst, byte, bytes); }
 	void DevCopy(Ctx&, void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
 	void ExclusiveScanU32(Ctx& ctx, const uint32_t* in, uint32_t* out, uint32_t n, DevBuf<uint32_t>&)

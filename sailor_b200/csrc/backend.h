@@ -17,6 +17,11 @@
 
 #if !defined(SPT_EMU)
 #include <cuda_runtime.h>
+#if defined(__CUDACC__)
+#include <cooperative_groups.h>
+#include <cooperative_groups/scan.h>
+#include <cooperative_groups/reduce.h>
+#endif
 #endif
 
 namespace spt
@@ -56,6 +61,9 @@ namespace spt
 	void DevUpload(Ctx& ctx, void* dst, const void* src, size_t bytes);
 	void DevDownload(Ctx& ctx, void* dst, const void* src, size_t bytes);   // synchronises
 	void DevMemset(Ctx& ctx, void* dst, int byte, size_t bytes);
+	// caller-owned host buffers page-locked through the C-ABI: DevDownload copies into them without staging
+	int HostPin(void* p, size_t bytes);       // 0 ok, -1 failed
+	int HostUnpin(void* p);
 	void DevCopy(Ctx& ctx, void* dst, const void* src, size_t bytes);
 
 	template<class T>
@@ -84,11 +92,47 @@ namespace spt
 	__device__ __forceinline__ uint32_t atomic_add_u32(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
 	__device__ __forceinline__ unsigned long long atomic_add_u64(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
 #define SPT_KERNEL_BODY __device__ __forceinline__
+#if defined(__CUDACC__)
+	// Warp-aggregated forms: the lanes that are active at the call each reserve v (or 1) consecutive units of *p, which must
+	// be the SAME address in every lane; one atomic per warp instead of one per lane, ranges handed out in lane order.
+	// The wavefront counters (ray queue length, record arena, fan-out tables) are bumped once per activation: per-lane
+	// atomics on four addresses were what bounded ExpandKernel (profiles/r01d_SUMMARY.md).
+	__device__ __forceinline__ uint32_t atomic_inc_u32_agg(uint32_t* p)
+	{
+		const uint32_t mask = __activemask(), lane = threadIdx.x & 31u;
+		const int leader = __ffs(mask) - 1;
+		uint32_t base = 0;
+		if ((int)lane == leader) base = atomicAdd(p, (uint32_t)__popc(mask));
+		base = __shfl_sync(mask, base, leader);
+		return base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+	}
+	__device__ __forceinline__ uint32_t atomic_add_u32_agg(uint32_t* p, uint32_t v)
+	{
+		namespace cg = cooperative_groups;
+		const cg::coalesced_group g = cg::coalesced_threads();
+		const uint32_t excl = cg::exclusive_scan(g, v);
+		const uint32_t last = g.size() - 1u;
+		uint32_t base = 0;
+		if (g.thread_rank() == last) base = atomicAdd(p, excl + v);
+		base = g.shfl(base, last);
+		return base + excl;
+	}
+	__device__ __forceinline__ void atomic_add_u64_agg(unsigned long long* p, unsigned long long v)
+	{
+		namespace cg = cooperative_groups;
+		const cg::coalesced_group g = cg::coalesced_threads();
+		const unsigned long long total = cg::reduce(g, v, cg::plus<unsigned long long>());
+		if (g.thread_rank() == 0) atomicAdd(p, total);
+	}
+#endif
 #else
 	inline void atomic_min_u32(uint32_t* p, uint32_t v) { if (v < *p) *p = v; }
 	inline void atomic_max_u32(uint32_t* p, uint32_t v) { if (v > *p) *p = v; }
 	inline uint32_t atomic_add_u32(uint32_t* p, uint32_t v) { const uint32_t o = *p; *p = o + v; return o; }
 	inline unsigned long long atomic_add_u64(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
+	inline uint32_t atomic_inc_u32_agg(uint32_t* p) { return atomic_add_u32(p, 1u); }
+	inline uint32_t atomic_add_u32_agg(uint32_t* p, uint32_t v) { return atomic_add_u32(p, v); }
+	inline void atomic_add_u64_agg(unsigned long long* p, unsigned long long v) { *p += v; }
 #define SPT_KERNEL_BODY inline
 #endif
 

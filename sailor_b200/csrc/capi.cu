@@ -77,6 +77,16 @@ int32_t SailorPt_SetDevice(int32_t device)
 	return SAILOR_PT_OK;
 #endif
 }
+int32_t SailorPt_PinHostBuffer(void* hostBuffer, uint64_t bytes)
+{
+	if (!hostBuffer || !bytes) return SetError(SAILOR_PT_ERR_ARG, "null buffer");
+	return spt::HostPin(hostBuffer, (size_t)bytes) == 0 ? SAILOR_PT_OK : SetError(SAILOR_PT_ERR_CUDA, "cudaHostRegister failed (or the buffer is already pinned with a smaller size)");
+}
+int32_t SailorPt_UnpinHostBuffer(void* hostBuffer)
+{
+	if (!hostBuffer) return SetError(SAILOR_PT_ERR_ARG, "null buffer");
+	return spt::HostUnpin(hostBuffer) == 0 ? SAILOR_PT_OK : SetError(SAILOR_PT_ERR_ARG, "buffer was not pinned");
+}
 #if defined(SPT_TRACE_STATS) && !defined(SPT_EMU)
 // tuning builds only (tools/trace_variants.py): read and clear the lane-state counters of the traversal warp loop
 extern "C" SAILOR_PT_API int32_t SailorPt_DebugTraceStats(unsigned long long* out)

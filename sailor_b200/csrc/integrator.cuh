@@ -200,7 +200,7 @@ namespace spt
 
 	SPT_KERNEL_BODY uint32_t AllocRecord(const IntegratorArgs& a)
 	{
-		const uint32_t i = atomic_add_u32(&a.c->recAlloc, 1u);
+		const uint32_t i = atomic_inc_u32_agg(&a.c->recAlloc);
 		if (i >= a.recCap) { a.c->overflow = 1u; return kNone; }
 		return i;
 	}
@@ -261,7 +261,7 @@ namespace spt
 
 	SPT_KERNEL_BODY void SkyPush(const IntegratorArgs& a, uint32_t q, const SkyState& s)
 	{
-		const uint32_t i = atomic_add_u32(&a.c->skyCount[q], 1u);
+		const uint32_t i = atomic_inc_u32_agg(&a.c->skyCount[q]);
 		if (i >= a.skyCap) { a.c->overflow = 1u; return; }
 		a.sky[q][i] = s;
 		WriteRay(a.skyRays + (q ? a.skyCap : 0u), i, s.start, s.dir, s.ignore, true);      // each queue owns one half of skyRays
@@ -478,7 +478,7 @@ namespace spt
 				const V3 nd = CalculateRefraction(n.rayD, N, n.envIor, 1.0f);
 				NodeRec* out = a.recs + ri;
 				if (eq0(nd) || bounceLimit == 0) { out->result = v3(0.0f); out->flags = n.flags | kNfDone; return; }
-				const uint32_t base = atomic_add_u32(&L->rayCount, 1u);
+				const uint32_t base = atomic_inc_u32_agg(&L->rayCount);
 				if (base >= a.rayCap || L->auxBase + base >= a.auxCap) { a.c->overflow = 1u; out->result = v3(0.0f); out->flags = n.flags | kNfDone; return; }
 				const V3 d = nd - offset;
 				const uint32_t ci = SpawnOwn(n, ri, hitPoint, d, bounceLimit - 1u, pMaxBounces, n.pNumSamples, n.pNumAmbient, n.inAcc, 1.0f, 0x40000000u);
@@ -500,7 +500,7 @@ namespace spt
 			uint32_t base = 0;
 			if (nRays)
 			{
-				base = atomic_add_u32(&L->rayCount, nRays);
+				base = atomic_add_u32_agg(&L->rayCount, nRays);
 				if (base + nRays > a.rayCap || L->auxBase + base + nRays > a.auxCap)
 				{
 					a.c->overflow = 1u; out->result = v3(0.0f); out->flags = n.flags | kNfDone; return;
@@ -531,17 +531,17 @@ namespace spt
 				if (nHemi + nS >= kFanOutMinSamples)
 				{
 					// many samples (first hits): hand them to FanOutKernel in slots of 8 lanes; this thread only reserves the rays
-					const uint32_t e = atomic_add_u32(&a.c->fanEntries, 1u);
+					const uint32_t e = atomic_inc_u32_agg(&a.c->fanEntries);
 					if (e < a.fanCap)
 					{
 						a.fan[e] = c; fanned = true;
-						atomic_add_u64(&a.c->fanSamples, (unsigned long long)(nHemi + nS));
+						atomic_add_u64_agg(&a.c->fanSamples, (unsigned long long)(nHemi + nS));
 						const uint32_t cnt[2] = { nHemi, nS };
 						for (uint32_t pass = 0; pass < 2; pass++)
 						{
 							uint32_t slots = (cnt[pass] + 7u) / 8u; if (slots > 4u) slots = 4u;
 							if (!slots) continue;
-							const uint32_t base = atomic_add_u32(&a.c->fanThreads[pass], 8u * slots) / 8u;
+							const uint32_t base = atomic_add_u32_agg(&a.c->fanThreads[pass], 8u * slots) / 8u;
 							for (uint32_t k = 0; k < slots; k++) a.fanSlots[pass][base + k] = e | (k << 24) | ((slots - 1u) << 27);
 						}
 					}
@@ -740,7 +740,7 @@ namespace spt
 					V3 amb1 = v3(0.0f);
 					if (!(flags & kNfThick))
 					{
-#pragma unroll 4
+#pragma unroll 8
 						for (uint32_t k = 0; k < nA; k++, g++)
 						{
 							const RayAux x = a.aux[g];
@@ -751,7 +751,7 @@ namespace spt
 					}
 					amb1 = amb1 / (float)nA;                                              // :739
 					V3 amb2 = v3(0.0f), indirect = v3(0.0f); float avgPdf = 0.0f, cnt = 0.0f;
-#pragma unroll 4
+#pragma unroll 8
 					for (uint32_t i = 0; i < nS; i++, g++)
 					{
 						const RayAux x = a.aux[g];

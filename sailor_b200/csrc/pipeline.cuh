@@ -9,6 +9,7 @@
 #include "flatten.cuh"
 #include "bvh_build.cuh"
 #include "trace_kernels.cuh"
+#include "bvh_build_small.cuh"
 #include "../../include/sailor_pt.h"
 
 #include <chrono>
@@ -156,6 +157,38 @@ namespace spt
 			s.bins = bins.p; s.splitFlag = splitFlag.p; s.splitScan = splitScan.p; s.binSlot = binSlot.p; s.binCounter = binCounter.p; s.n = N;
 
 			ctx.TimerStart();
+#if !defined(SPT_EMU)
+			if (N <= kSmallBuildMax && !getenv("SAILOR_PT_NO_SMALL_BUILD"))
+			{
+				// small scene: the whole build in one launch of one CTA (bvh_build_small.cuh), same functors, same bits
+				DevBuf<uint32_t>& internalCount = buildU32[21]; DevBuf<uint32_t>& refIdx = buildU32[22]; DevBuf<uint32_t>& rank = buildU32[23];
+				internalCount.Ensure(ctx, maxNodes); refIdx.Ensure(ctx, maxNodes); rank.Ensure(ctx, maxNodes);
+				flags.Ensure(ctx, maxNodes); scan.Ensure(ctx, (size_t)maxNodes + 1); buildF32[3].Ensure(ctx, N);
+				refNodes.Ensure(ctx, maxNodes); mapping.Ensure(ctx, N); tnodes.Ensure(ctx, N); ttris.Ensure(ctx, N);
+				if (!ctx.ok) return CudaStatus();
+				s.flags = flags.p; s.scan = scan.p;
+				SmallBuildOut o;
+				o.internalCount = internalCount.p; o.refIdx = refIdx.p; o.rank = rank.p; o.leafCountByRef = flags.p; o.leafOffsetByRef = scan.p; o.leafCountAtSlot = holes.p;
+				o.areaScratch = buildF32[3].p; o.refNodes = refNodes.p; o.mapping = mapping.p; o.tnodes = tnodes.p; o.ttris = ttris.p;
+				o.result = counter.p + 8; o.maxNodes = maxNodes;
+				k_build_small<<<1, kSmallBuildBlock, 0, ctx.stream>>>(s, o);
+				ctx.kernelLaunches++;
+				SPT_CUDA_CHECK(ctx, cudaGetLastError());
+				uint32_t res[4] = { 0u, 0u, 0u, 1u };
+				DevDownload(ctx, res, o.result, sizeof(res));
+				if (ctx.ok && res[3] == 0u)
+				{
+					nodesUsed = res[0]; numInternal = res[1]; numLevels = res[2];
+					rootRef = numInternal ? 0u : kLeafBit;
+					stats.secondsBvhBuild = ctx.TimerStop();
+					stats.secondsTotal = HostNow() - t0;
+					built = ctx.ok;
+					return CudaStatus();
+				}
+				if (!ctx.ok) return CudaStatus();
+				// deeper than kSmallBuildLevels (degenerate input): redo it with the multi-launch build below
+			}
+#endif
 			launch_for(ctx, N, InitSlotsKernel{ s });
 			const uint32_t rootInit[2] = { 0u, N };
 			DevUpload(ctx, first.p, &rootInit[0], 4); DevUpload(ctx, count.p, &rootInit[1], 4);   // BVH.cpp:291-293

@@ -17,7 +17,7 @@
 #define SPT_EXPAND_MIN_BLOCKS 2
 #endif
 #ifndef SPT_FAN_MIN_BLOCKS
-#define SPT_FAN_MIN_BLOCKS 3
+#define SPT_FAN_MIN_BLOCKS 4
 #endif
 
 namespace spt
@@ -114,7 +114,7 @@ namespace spt
 	{
 		__shared__ uint32_t stackMem[kSmemStack * kTraceBlock];
 		PrimaryPassSource src{ a }; PrimaryPassSink sink{ a };
-		TraceWarpLoop(a.bvh, a.total, counter, stackMem, src, sink);
+		TraceWarpLoop<false>(a.bvh, a.total, counter, stackMem, src, sink);
 	}
 
 	inline void LaunchPrimaryPass(Ctx& ctx, const PrimaryArgs& a, uint32_t* counter)
@@ -150,11 +150,12 @@ namespace spt
 	// (BatchCounters::overflow) and the batch is redone at half the size, so the factors only affect speed.
 	struct BatchPlan { uint32_t firstHits, rayCap, auxCap, recCap, skyCap; };
 
-	// Working-set budget of one batch of first hits: 16 GiB of the B200's 180 GB, never more than a third of what the device
+	// Working-set budget of one batch of first hits: 40 GiB of the B200's 180 GB (a whole C2 frame is then ONE batch: every batch
+	// boundary costs a host round trip, and a descheduled host thread shows up as an idle GPU), never more than a third of what the device
 	// can still give (`held` = bytes the scene's arenas already own, which the batch reuses).  Decided once per frame.
 	inline uint64_t BatchBudget(uint64_t held)
 	{
-		uint64_t budget = 16384ull << 20;
+		uint64_t budget = 40960ull << 20;
 		const uint64_t avail = ((uint64_t)DevMemAvailable() + held) / 3u;
 		if (avail && budget > avail) budget = avail;
 		if (budget < (256ull << 20)) budget = 256ull << 20;
@@ -228,6 +229,7 @@ namespace spt
 		LaunchPrimaryPass(ctx, pa, D.counter.p);
 		tt.End(ctx);
 		uint32_t hitCount = 0;
+		bool resolved = false;
 		DevDownload(ctx, &hitCount, hitCounter, 4);
 		rs.rays = realSamples; rs.primarySamples = realSamples;
 
@@ -322,6 +324,10 @@ namespace spt
 					launch_for_range(ctx, &L->recBegin, &L->recEnd, plan.recCap, level == 0 ? plan.firstHits : plan.recCap, GatherKernel{ a });
 				}
 				st[3].End(ctx);
+				// The batch's counters (overflow flag, ray count) are read back with a host round trip.  For the LAST batch of the frame
+				// the resolve kernel is queued first, so the GPU never idles on that read.
+				const bool lastBatch = (uint64_t)done + plan.firstHits >= hitCount;
+				if (lastBatch) launch_for(ctx, rows * cam.width, ResolveKernel{ sampleBuf, dImage, cam.width, cam.height, rowBegin, rowEnd, ns, p.msaa });
 				struct { uint32_t recAlloc, auxAlloc, overflow, sky0, sky1, zero, fanEntries, slowCount, fan0, fan1; unsigned long long rays, fanSamples; } head;
 				DevDownload(ctx, &head, counters, sizeof(head));          // synchronises
 				if (!ctx.ok) break;
@@ -329,13 +335,14 @@ namespace spt
 				{
 					if (plan.firstHits <= 1024u || shrink > 16u) { ctx.error = "wavefront arenas overflow even for the smallest batch"; return SAILOR_PT_ERR_LIMIT; }
 					shrink++;
-					continue;                                                // redo this batch smaller (results are keyed per activation, not per batch)
+					continue;                                                // redo this batch smaller (results are keyed per activation, not per batch); the resolve is redone too
 				}
 				rs.rays += head.rays; rs.fanOutSamples += head.fanSamples;
 				done += plan.firstHits;
+				resolved = lastBatch;
 			}
 		}
-		launch_for(ctx, rows * cam.width, ResolveKernel{ sampleBuf, dImage, cam.width, cam.height, rowBegin, rowEnd, ns, p.msaa });
+		if (!resolved) launch_for(ctx, rows * cam.width, ResolveKernel{ sampleBuf, dImage, cam.width, cam.height, rowBegin, rowEnd, ns, p.msaa });
 		ctx.Mark(1);
 		ctx.Sync();
 		rs.traverseLaunches = tt.Spans();

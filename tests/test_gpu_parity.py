@@ -110,6 +110,22 @@ def test_render_is_deterministic_and_partition_invariant(gpu, scene_dir):
         assert np.allclose(sum(parts), full, rtol=1e-6, atol=1e-7)
 
 
+def test_render_into_pinned_host_buffers_is_identical(gpu, scene_dir):
+    """SailorPt_PinHostBuffer only changes how the result travels (direct DMA instead of staged copies)."""
+    p = Params(height=540, width_override=960, num_samples=2, num_ambient_samples=2, max_bounces=2, msaa=1, ambient=(1, 1, 1), seed=4)
+    with gpu.load_scene(_scene(scene_dir, "cube", {})) as s:
+        lin0, srgb0 = s.render(p)
+        lin = np.zeros_like(lin0); srgb = np.zeros_like(srgb0)
+        gpu.pin_host_buffer(lin); gpu.pin_host_buffer(srgb)
+        try:
+            s.render(p, out=(lin, srgb))
+        finally:
+            gpu.unpin_host_buffer(lin); gpu.unpin_host_buffer(srgb)
+        assert lin0.nbytes > (1 << 20) and np.array_equal(lin, lin0) and np.array_equal(srgb, srgb0)
+    with pytest.raises(Exception):
+        gpu.unpin_host_buffer(lin)                      # not pinned any more
+
+
 def test_gpu_render_equals_host_compiled_kernel_bodies(gpu, emu, scene_dir):
     """Same RNG streams, same state machine: the CUDA render differs from the host-compiled bodies only through
     libm transcendentals, far below Monte-Carlo noise."""

@@ -19,6 +19,14 @@ VARIANTS = {
     "dyn_tri_idle8": ["SPT_DYN_REPS", "SPT_INNER_REPS=8", "SPT_LEAF_REPS=4", "SPT_TRI_UNIFIED", "SPT_FETCH_MIN_IDLE=8"],
     "reps21": ["SPT_INNER_REPS=2", "SPT_LEAF_REPS=1"],
     "reps63": ["SPT_INNER_REPS=6", "SPT_LEAF_REPS=3"],
+    "stack8": ["SPT_SMEM_STACK=8"],
+    "stack12": ["SPT_SMEM_STACK=12"],
+    "stack16": ["SPT_SMEM_STACK=16"],
+    "block64": ["SPT_TRACE_BLOCK=64"],
+    "block256": ["SPT_TRACE_BLOCK=256"],
+    "fan4": ["SPT_FAN_MIN_BLOCKS=4"],
+    "fan2": ["SPT_FAN_MIN_BLOCKS=2"],
+    "smallthread": ["SPT_SMALL_WARP=0"],
 }
 
 if sys.argv[1] == "build":
