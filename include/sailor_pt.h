@@ -176,6 +176,29 @@ SAILOR_PT_API int32_t SailorPt_CopyResidentToDevice(SailorPtScene* scene, void* 
  * floats, e.g. the NCCL-reduced frame) first replaces the resident accumulator.  The sRGB8 image stays resident. */
 SAILOR_PT_API int32_t SailorPt_OutputStageResident(SailorPtScene* scene, const void* srcDevice, uint64_t bytes);
 
+/* ---- the steps after the path; product only, the oracle returns SAILOR_PT_ERR_UNSUPPORTED ---- */
+
+/* Write a linear float image (width*height*3, rows as SailorPt_Render returns them) in the format the extension names:
+ * .pfm (Portable Float Map: the accumulator's exact bits), .hdr (Radiance RGBE), anything else = the reference's own output,
+ * i.e. output stage + sRGB8 PNG (PathTracer.cpp:535-565).  SailorPt_Run picks the format of params->output the same way. */
+SAILOR_PT_API int32_t SailorPt_WriteImage(const char* path, uint32_t width, uint32_t height, const float* linearRGB);
+
+/* Image difference report: metrics[0] mean relative error = mean|a-b| / mean|b| (the tolerance metric of the converged-image
+ * tests), [1] RMSE, [2] max |a-b|, [3] PSNR in dB against peak 1.0 (1e30 when identical). */
+SAILOR_PT_API int32_t SailorPt_CompareImages(uint32_t width, uint32_t height, const float* a, const float* b, double metrics[4]);
+
+/* Progressive render with checkpoint / resume.  The primary samples [0, params->msaa) of the frame (PathTracer.cpp:457-469,
+ * one Raytrace per pixel and sample, accumulator / msaa) are rendered in passes of `msaaPerPass` sample indices; the
+ * un-normalised sum stays on the device and every pass continues the same chain of additions, so the finished frame has
+ * the SAME BITS as SailorPt_Render.  maxPasses: stop after that many passes (0 = run to the end).  checkpointPath (may be
+ * NULL): the running sum + the parameters it depends on, written when the call returns (and after every pass with flag 2).
+ * flags: 1 = resume from checkpointPath when it exists (it must match scene, camera and parameters), 2 = checkpoint after
+ * every pass, 4 = also write params->output after every pass (preview).  linearRGB / srgb8 (either may be NULL) receive
+ * the estimate so far, normalised by the samples done; *msaaDone (may be NULL) the number of sample indices accumulated.
+ * When the frame is complete and params->output is set, the image file is written as SailorPt_Run would. */
+SAILOR_PT_API int32_t SailorPt_RenderProgressive(SailorPtScene* scene, const SailorPtParams* params, uint32_t msaaPerPass,
+	uint32_t maxPasses, const char* checkpointPath, uint32_t flags, float* linearRGB, uint8_t* srgb8, uint32_t* msaaDone);
+
 /* Product: page-lock a caller-owned HOST buffer (the result images a host reuses frame after frame) so that SailorPt_Render /
  * SailorPt_ReadResident DMA straight into it instead of staging through the library's own pinned chunks and a host memcpy.
  * The buffer must be unpinned before it is freed.  Results are identical either way.  The reference has no counterpart (its

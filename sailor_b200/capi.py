@@ -56,7 +56,7 @@ SYMBOLS = [
     "SailorPt_GetCamera", "SailorPt_IntersectRays", "SailorPt_PrimaryHits", "SailorPt_Render",
     "SailorPt_OutputStage", "SailorPt_SampleTexture", "SailorPt_EvalLighting", "SailorPt_GetStats",
     "SailorPt_LastError", "SailorPt_Backend", "SailorPt_RenderResident", "SailorPt_ReadResident", "SailorPt_CopyResidentToDevice", "SailorPt_SetDevice", "SailorPt_OutputStageResident",
-    "SailorPt_PinHostBuffer", "SailorPt_UnpinHostBuffer",
+    "SailorPt_PinHostBuffer", "SailorPt_UnpinHostBuffer", "SailorPt_WriteImage", "SailorPt_CompareImages", "SailorPt_RenderProgressive",
 ]
 
 
@@ -142,6 +142,9 @@ class Library:
         lib.SailorPt_GetStats.argtypes = [P(SailorPtStats)]
         lib.SailorPt_SetDevice.argtypes = [C.c_int32]
         lib.SailorPt_OutputStageResident.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        lib.SailorPt_WriteImage.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, P(C.c_float)]
+        lib.SailorPt_CompareImages.argtypes = [C.c_uint32, C.c_uint32, P(C.c_float), P(C.c_float), P(C.c_double)]
+        lib.SailorPt_RenderProgressive.argtypes = [C.c_void_p, P(SailorPtParams), C.c_uint32, C.c_uint32, C.c_char_p, C.c_uint32, P(C.c_float), P(C.c_uint8), P(C.c_uint32)]
         lib.SailorPt_PinHostBuffer.argtypes = [C.c_void_p, C.c_uint64]
         lib.SailorPt_UnpinHostBuffer.argtypes = [C.c_void_p]
         lib.SailorPt_LastError.restype = C.c_char_p
@@ -161,6 +164,19 @@ class Library:
 
     def set_device(self, index):
         self.check(self.lib.SailorPt_SetDevice(index), "SailorPt_SetDevice")
+
+    def write_image(self, path, linear):
+        """SailorPt_WriteImage: .pfm / .hdr linear dumps, anything else = output stage + PNG."""
+        lin = np.ascontiguousarray(linear, dtype=np.float32)
+        self.check(self.lib.SailorPt_WriteImage(str(path).encode(), lin.shape[1], lin.shape[0], _ptr(lin, C.c_float)), "SailorPt_WriteImage")
+
+    def compare_images(self, a, b):
+        """SailorPt_CompareImages -> dict(mean_rel_error, rmse, max_abs, psnr_db)."""
+        a = np.ascontiguousarray(a, dtype=np.float32); b = np.ascontiguousarray(b, dtype=np.float32)
+        assert a.shape == b.shape and a.ndim == 3 and a.shape[2] == 3
+        m = (C.c_double * 4)()
+        self.check(self.lib.SailorPt_CompareImages(a.shape[1], a.shape[0], _ptr(a, C.c_float), _ptr(b, C.c_float), m), "SailorPt_CompareImages")
+        return dict(mean_rel_error=m[0], rmse=m[1], max_abs=m[2], psnr_db=m[3])
 
     def pin_host_buffer(self, array):
         """Page-lock a numpy array the caller reuses for results (SailorPt_PinHostBuffer); unpin before dropping it."""
@@ -310,6 +326,19 @@ class Scene:
             srgb = np.empty((h, w, 3), np.uint8) if want_srgb else None
         self.L.check(self.L.lib.SailorPt_Render(self.h, C.byref(cp), _ptr(lin, C.c_float), _ptr(srgb, C.c_uint8)), "SailorPt_Render")
         return lin, srgb
+
+    def render_progressive(self, params: Params, msaa_per_pass, max_passes=0, checkpoint=None, resume=False, checkpoint_every_pass=False,
+                           preview=False, want_srgb=True):
+        """SailorPt_RenderProgressive -> (linear, srgb or None, primary-sample indices accumulated so far)."""
+        w, h, _ = self.camera(params)
+        cp = params.to_c()
+        lin = np.empty((h, w, 3), np.float32)
+        srgb = np.empty((h, w, 3), np.uint8) if want_srgb else None
+        done = C.c_uint32(0)
+        flags = (1 if resume else 0) | (2 if checkpoint_every_pass else 0) | (4 if preview else 0)
+        self.L.check(self.L.lib.SailorPt_RenderProgressive(self.h, C.byref(cp), msaa_per_pass, max_passes, str(checkpoint).encode() if checkpoint else None, flags,
+                                                          _ptr(lin, C.c_float), _ptr(srgb, C.c_uint8) if srgb is not None else None, C.byref(done)), "SailorPt_RenderProgressive")
+        return lin, srgb, done.value
 
     def render_resident(self, params: Params, rebuild_bvh=False, output_stage=True):
         cp = params.to_c()

@@ -55,6 +55,7 @@ namespace spt
 	}
 	void Ctx::Destroy()
 	{
+		if (pinned) { cudaFreeHost(pinned); pinned = nullptr; }
 		if (evA) cudaEventDestroy(evA);
 		if (evB) cudaEventDestroy(evB);
 		for (int i = 0; i < kMarkers; i++) { if (ev[i]) cudaEventDestroy(ev[i]); ev[i] = nullptr; }
@@ -74,6 +75,17 @@ namespace spt
 	}
 
 	void Ctx::Mark(int i) { if (ok) SPT_CUDA_CHECK(*this, cudaEventRecord(ev[i], stream)); }
+	void Ctx::WaitMark(int i) { if (ok) SPT_CUDA_CHECK(*this, cudaEventSynchronize(ev[i])); }
+	uint32_t* Ctx::Pinned()
+	{
+		if (!pinned && ok) { void* p = nullptr; SPT_CUDA_CHECK(*this, cudaHostAlloc(&p, 256 * sizeof(uint32_t), cudaHostAllocDefault)); pinned = (uint32_t*)p; }
+		return pinned;
+	}
+	void Ctx::ReadAsync(uint32_t* pinnedDst, const void* src, size_t bytes)
+	{
+		d2hBytes += bytes;
+		if (ok) SPT_CUDA_CHECK(*this, cudaMemcpyAsync(pinnedDst, src, bytes, cudaMemcpyDeviceToHost, stream));
+	}
 	double Ctx::Between(int i, int j)
 	{
 		float ms = 0.0f;
@@ -412,9 +424,12 @@ namespace spt
 	double SpanTimer::Collect(Ctx&) { const double s = acc; acc = 0.0; used = 0; return s; }
 	void SpanTimer::Destroy() {}
 	void Ctx::Mark(int i) { g_marks[i] = std::chrono::steady_clock::now(); }
+	void Ctx::WaitMark(int) {}
+	uint32_t* Ctx::Pinned() { if (!pinned) pinned = (uint32_t*)calloc(256, sizeof(uint32_t)); return pinned; }
+	void Ctx::ReadAsync(uint32_t* pinnedDst, const void* src, size_t bytes) { d2hBytes += bytes; memcpy(pinnedDst, src, bytes); }
 	double Ctx::Between(int i, int j) { return std::chrono::duration<double>(g_marks[j] - g_marks[i]).count(); }
 	int Ctx::Init() { ok = true; return SAILOR_PT_OK; }
-	void Ctx::Destroy() {}
+	void Ctx::Destroy() { free(pinned); pinned = nullptr; }
 	void Ctx::Sync() {}
 	void Ctx::TimerStart() { g_t0 = std::chrono::steady_clock::now(); }
 	double Ctx::TimerStop() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - g_t0).count(); }

@@ -49,6 +49,12 @@ namespace spt
 		double TimerStop();
 		void Mark(int i);                  // record marker i on the launch stream
 		double Between(int i, int j);      // seconds between two recorded markers (after a sync)
+		void WaitMark(int i);              // block the host until marker i has been reached
+		// small read-backs that must not drain the queue: copy into the context's pinned scratch (256 words) behind the work
+		// queued so far; the data is valid after WaitMark() of a marker recorded after the copy
+		uint32_t* pinned = nullptr;
+		uint32_t* Pinned();
+		void ReadAsync(uint32_t* pinnedDst, const void* src, size_t bytes);
 	};
 
 #if !defined(SPT_EMU)

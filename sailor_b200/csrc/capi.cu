@@ -424,6 +424,128 @@ int32_t SailorPt_Render(SailorPtScene* s, const SailorPtParams* p, float* linear
 	return rc;
 }
 
+int32_t SailorPt_WriteImage(const char* path, uint32_t width, uint32_t height, const float* linearRGB)
+{
+	if (!path || !path[0] || !linearRGB || !width || !height) return SAILOR_PT_ERR_ARG;
+	std::string err;
+	int rc;
+	switch (ImageFormatOf(path))
+	{
+	case ImageFormat::Pfm: rc = WritePfm(path, width, height, linearRGB, err); break;
+	case ImageFormat::Hdr: rc = WriteHdr(path, width, height, linearRGB, err); break;
+	default:
+	{
+		std::vector<uint8_t> srgb((size_t)width * height * 3);
+		rc = SailorPt_OutputStage(width, height, linearRGB, srgb.data());                  // PathTracer.cpp:535-565
+		if (rc == SAILOR_PT_OK) rc = EncodePngRgb8(path, width, height, srgb.data(), err);  // stbi_write_png (:560-564)
+	}
+	}
+	if (rc != SAILOR_PT_OK && !err.empty()) t_lastError = err;
+	return rc;
+}
+
+int32_t SailorPt_CompareImages(uint32_t width, uint32_t height, const float* a, const float* b, double metrics[4])
+{
+	if (!a || !b || !metrics || !width || !height) return SAILOR_PT_ERR_ARG;
+	CompareImages((size_t)width * height * 3, a, b, metrics);
+	return SAILOR_PT_OK;
+}
+
+int32_t SailorPt_RenderProgressive(SailorPtScene* s, const SailorPtParams* p, uint32_t msaaPerPass, uint32_t maxPasses, const char* checkpointPath,
+	uint32_t flags, float* linearRGB, uint8_t* srgb8, uint32_t* msaaDoneOut)
+{
+	if (!s || !p || !p->height || !p->msaa || !msaaPerPass) return SAILOR_PT_ERR_ARG;
+	if (p->msaaEnd) return SetError(SAILOR_PT_ERR_ARG, "a progressive render walks the primary-sample range itself: leave msaaBegin/msaaEnd 0");
+	int rc = SailorPt_BuildBVH(s);
+	if (rc != SAILOR_PT_OK) return rc;
+	SceneDevice& D = s->dev;
+	const double t0 = HostNow();
+	const CameraSetup c = CameraOf(D, p);
+	const size_t n = (size_t)c.width * c.height;
+	if (!n) return SAILOR_PT_ERR_ARG;
+	const uint32_t rowBegin = p->rowEnd ? p->rowBegin : 0u, rowEnd = p->rowEnd ? (p->rowEnd < c.height ? p->rowEnd : c.height) : c.height;
+	if (rowBegin >= rowEnd) return SetError(SAILOR_PT_ERR_ARG, "empty shard");
+	const size_t bandFloats = (size_t)(rowEnd - rowBegin) * c.width * 3;
+
+	CheckpointHeader hd; memset(&hd, 0, sizeof(hd));
+	hd.version = 1; hd.width = c.width; hd.height = c.height; hd.rowBegin = rowBegin; hd.rowEnd = rowEnd; hd.msaaTotal = p->msaa; hd.msaaDone = 0;
+	hd.numSamples = p->numSamples; hd.numAmbientSamples = p->numAmbientSamples; hd.maxBounces = p->maxBounces; hd.numTriangles = D.numTris; hd.seed = p->seed;
+	memcpy(hd.ambient, p->ambient, sizeof(hd.ambient));
+	memcpy(hd.camera, c.pos, 3 * sizeof(float)); memcpy(hd.camera + 3, c.pixel00Dir, 3 * sizeof(float)); memcpy(hd.camera + 6, c.deltaU, 3 * sizeof(float)); memcpy(hd.camera + 9, c.deltaV, 3 * sizeof(float));
+
+	DevBuf<float> running;
+	running.Alloc(D.ctx, bandFloats);
+	D.residentLin.Ensure(D.ctx, n * 3);
+	D.residentW = c.width; D.residentH = c.height;
+	if (!D.ctx.ok) return FromCtx(D, SAILOR_PT_ERR_CUDA);
+	D.residentLin.Zero(D.ctx, n * 3);
+	uint32_t done = 0;
+	if ((flags & 1u) && checkpointPath && checkpointPath[0])
+	{
+		CheckpointHeader got; std::vector<float> sum; std::string err;
+		const int rr = ReadCheckpoint(checkpointPath, got, sum, err);
+		if (rr == SAILOR_PT_OK)
+		{
+			CheckpointHeader want = hd; want.msaaDone = got.msaaDone;
+			if (memcmp(&want, &got, sizeof(want)) != 0) return SetError(SAILOR_PT_ERR_ARG, std::string("checkpoint was written for another scene, camera or parameter set: ") + checkpointPath);
+			running.Upload(D.ctx, sum.data(), bandFloats);
+			done = got.msaaDone;
+		}
+		else if (rr != SAILOR_PT_ERR_IO) return SetError(rr, err);          // a missing file means "start from scratch"; a damaged one is an error
+	}
+	uint64_t rays = 0, samples = 0; uint32_t launches = 0;
+	double tTrav = 0.0;
+	uint32_t passes = 0;
+	SailorPtParams q = *p;
+	while (done < p->msaa && (!maxPasses || passes < maxPasses))
+	{
+		q.msaaBegin = done; q.msaaEnd = done + msaaPerPass < p->msaa ? done + msaaPerPass : p->msaa;
+		D.ctx.kernelLaunches = 0;
+		RenderStats rs{};
+		ProgressiveArgs prog; prog.running = running.p; prog.runningValid = done > 0; prog.norm = q.msaaEnd;
+		rc = RenderFrame(D, ToGpuCamera(c), q, D.residentLin.p, rs, prog);
+		if (rc != SAILOR_PT_OK) return FromCtx(D, rc);
+		rays += rs.rays; samples += rs.primarySamples; launches += D.ctx.kernelLaunches; tTrav += rs.secondsTraverse;
+		done = q.msaaEnd; passes++;
+		const bool finalPass = done >= p->msaa || (maxPasses && passes >= maxPasses);
+		if (checkpointPath && checkpointPath[0] && ((flags & 2u) || finalPass))
+		{
+			std::vector<float> sum(bandFloats); std::string err;
+			running.Download(D.ctx, sum.data(), bandFloats);
+			if (!D.ctx.ok) return FromCtx(D, SAILOR_PT_ERR_CUDA);
+			hd.msaaDone = done;
+			rc = WriteCheckpoint(checkpointPath, hd, sum.data(), err);
+			if (rc != SAILOR_PT_OK) return SetError(rc, err);
+		}
+		if ((flags & 4u) && p->output && p->output[0] && !finalPass)         // preview of the estimate so far
+		{
+			std::vector<float> lin(n * 3);
+			D.residentLin.Download(D.ctx, lin.data(), n * 3);
+			if (!D.ctx.ok) return FromCtx(D, SAILOR_PT_ERR_CUDA);
+			rc = SailorPt_WriteImage(p->output, c.width, c.height, lin.data());
+			if (rc != SAILOR_PT_OK) return rc;
+		}
+	}
+	if (srgb8)
+	{
+		D.residentSrgb.Ensure(D.ctx, n * 3);
+		RunOutputStage(D.ctx, c.width, c.height, D.residentLin.p, D.residentSrgb.p);
+	}
+	if (passes == 0 && done > 0)
+	{
+		// nothing left to render (the checkpoint was complete): rebuild the image from the running sum
+		launch_for(D.ctx, (rowEnd - rowBegin) * c.width, ResolveKernel{ running.p, D.residentLin.p, c.width, c.height, rowBegin, rowEnd, 0u, done, running.p, 1u });
+		if (srgb8) RunOutputStage(D.ctx, c.width, c.height, D.residentLin.p, D.residentSrgb.p);
+	}
+	if (linearRGB) D.residentLin.Download(D.ctx, linearRGB, n * 3);
+	if (srgb8) D.residentSrgb.Download(D.ctx, srgb8, n * 3);
+	if (msaaDoneOut) *msaaDoneOut = done;
+	g_stats = SailorPtStats{};
+	g_stats.rays = rays; g_stats.primarySamples = samples; g_stats.kernelLaunches = launches; g_stats.secondsTraverse = tTrav; g_stats.secondsTotal = HostNow() - t0;
+	if (rc == SAILOR_PT_OK && done >= p->msaa && p->output && p->output[0] && linearRGB) rc = SailorPt_WriteImage(p->output, c.width, c.height, linearRGB);
+	return FromCtx(D, rc);
+}
+
 int32_t SailorPt_Run(const SailorPtParams* p)
 {
 	// PathTracer::Run (PathTracer.cpp:75-575)
@@ -441,7 +563,12 @@ int32_t SailorPt_Run(const SailorPtParams* p)
 		if (rc == SAILOR_PT_OK && p->output && p->output[0])
 		{
 			std::string err;
-			rc = EncodePngRgb8(p->output, w, h, srgb.data(), err);   // stbi_write_png (PathTracer.cpp:560-564)
+			switch (ImageFormatOf(p->output))
+			{
+			case ImageFormat::Pfm: rc = WritePfm(p->output, w, h, lin.data(), err); break;     // extension: the linear accumulator, exact bits
+			case ImageFormat::Hdr: rc = WriteHdr(p->output, w, h, lin.data(), err); break;
+			default: rc = EncodePngRgb8(p->output, w, h, srgb.data(), err);                    // stbi_write_png (PathTracer.cpp:560-564)
+			}
 			if (rc != SAILOR_PT_OK) t_lastError = err;
 		}
 	}

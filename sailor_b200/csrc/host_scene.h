@@ -77,6 +77,20 @@ namespace spt
 	int DecodePngRgba8(const uint8_t* data, size_t size, int32_t& w, int32_t& h, std::vector<uint8_t>& rgba, std::string& err);
 	int EncodePngRgb8(const char* path, uint32_t w, uint32_t h, const uint8_t* rgb, std::string& err);
 
+	// linear image dumps, comparison, progressive-render checkpoints (image_io.cpp)
+	enum class ImageFormat { Png, Pfm, Hdr };
+	ImageFormat ImageFormatOf(const char* path);                 // by extension; anything else is PNG (the reference's only format)
+	int WritePfm(const char* path, uint32_t w, uint32_t h, const float* rgb, std::string& err);
+	int WriteHdr(const char* path, uint32_t w, uint32_t h, const float* rgb, std::string& err);
+	void CompareImages(size_t count, const float* a, const float* b, double out[4]);
+	struct CheckpointHeader       // everything the running sum depends on; a resume must match all of it
+	{
+		uint32_t version, width, height, rowBegin, rowEnd, msaaTotal, msaaDone, numSamples, numAmbientSamples, maxBounces, numTriangles, pad;
+		uint64_t seed; float ambient[3]; float camera[12]; uint32_t pad2;
+	};
+	int WriteCheckpoint(const char* path, const CheckpointHeader& hd, const float* runningSum, std::string& err);
+	int ReadCheckpoint(const char* path, CheckpointHeader& hd, std::vector<float>& runningSum, std::string& err);
+
 	struct CameraSetup { uint32_t width, height; float pos[3], pixel00Dir[3], deltaU[3], deltaV[3]; };
 	struct SailorPtParamsView { const char* camera; uint32_t height; uint32_t widthOverride; };
 	// PathTracer.cpp:102-153 + 390-403 (host, glibc tan/atan like the reference)

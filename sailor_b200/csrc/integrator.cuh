@@ -836,15 +836,20 @@ namespace spt
 	};
 
 	// accumulator / msaa with the row flip of PathTracer.cpp:449,468-469
+	// Progressive renders (SailorPt_RenderProgressive) keep the UN-normalised sum in `running` between passes: a pass continues the
+	// same left-to-right chain of additions the one-shot render performs, so the final image has the same bits.
 	struct ResolveKernel
 	{
 		const float* sampleBuf; float* image; uint32_t width, height, rowBegin, rowEnd, numSamples, msaa;
+		float* running; uint32_t runningValid;      // running: optional [rows*width*3] sum carried across passes; valid = continue from it
 		SPT_KERNEL_BODY void operator()(uint32_t i) const
 		{
 			const uint32_t x = i % width, yb = i / width, y = rowBegin + yb;
 			V3 acc = v3(0.0f);
+			if (running && runningValid) acc = v3(running[(size_t)i * 3], running[(size_t)i * 3 + 1], running[(size_t)i * 3 + 2]);
 			const float* s = sampleBuf + (size_t)i * numSamples * 3;
 			for (uint32_t k = 0; k < numSamples; k++) acc = acc + v3(s[k * 3], s[k * 3 + 1], s[k * 3 + 2]);
+			if (running) { running[(size_t)i * 3] = acc.x; running[(size_t)i * 3 + 1] = acc.y; running[(size_t)i * 3 + 2] = acc.z; }
 			const V3 res = acc / (float)msaa;
 			const size_t o = ((size_t)(height - y - 1) * width + x) * 3;
 			image[o] = res.x; image[o + 1] = res.y; image[o + 2] = res.z;

@@ -156,7 +156,12 @@ namespace spt
 	inline uint64_t BatchBudget(uint64_t held)
 	{
 		uint64_t budget = 40960ull << 20;
-		const uint64_t avail = ((uint64_t)DevMemAvailable() + held) / 3u;
+		// cudaMemGetInfo goes through the driver's resource-manager lock and was seen to block for tens of milliseconds on a busy
+		// box (profiles/r01e_SUMMARY.md): ask at most once every few seconds
+		static uint64_t cachedFree = 0; static double cachedAt = -1e30;
+		const double now = HostNow();
+		if (now - cachedAt > 5.0) { cachedFree = (uint64_t)DevMemAvailable() + held; cachedAt = now; }
+		const uint64_t avail = cachedFree / 3u;
 		if (avail && budget > avail) budget = avail;
 		if (budget < (256ull << 20)) budget = 256ull << 20;
 		if (const char* e = getenv("SAILOR_PT_BATCH_MB")) { const long v = atol(e); if (v > 0) budget = (uint64_t)v << 20; }
@@ -193,7 +198,11 @@ namespace spt
 		return false;
 	}
 
-	inline int RenderFrame(SceneDevice& D, const CameraGpu& cam, const SailorPtParams& p, float* dImage, RenderStats& rs)
+	// Progressive pass (optional): `running` carries the un-normalised sum of the primary samples rendered so far, `runningValid`
+	// says whether to continue from it, and the image is normalised by `norm` (samples accumulated so far) instead of p.msaa.
+	struct ProgressiveArgs { float* running = nullptr; bool runningValid = false; uint32_t norm = 0; };
+
+	inline int RenderFrame(SceneDevice& D, const CameraGpu& cam, const SailorPtParams& p, float* dImage, RenderStats& rs, const ProgressiveArgs& prog = ProgressiveArgs())
 	{
 		Ctx& ctx = D.ctx;
 		const uint32_t rowBegin = p.rowEnd ? p.rowBegin : 0u, rowEnd = p.rowEnd ? (p.rowEnd < cam.height ? p.rowEnd : cam.height) : cam.height;
@@ -220,6 +229,8 @@ namespace spt
 		SpanTimer& tt = D.traceTimer;
 		SpanTimer* st = D.stageTimer;
 
+		const bool hostTrace = getenv("SAILOR_PT_TRACE_HOST") != nullptr;
+		const double tFrame0 = HostNow();
 		ctx.Mark(0);
 		// ---- primary pass ----
 		PrimaryArgs pa;
@@ -244,8 +255,7 @@ namespace spt
 			uint64_t held = 0;
 			for (const int k : { 0, 1, 2, 3, 8, 9, 10, 11, 12, 13, 14 }) held += D.renderMem[k].n;
 			const uint64_t budget = BatchBudget(held);
-			const bool hostTrace = getenv("SAILOR_PT_TRACE_HOST") != nullptr;
-			const double tFrame0 = HostNow();
+			if (hostTrace) fprintf(stderr, "[sailor_pt] t=%.3f ms primary pass done: %u first hits\n", (HostNow() - tFrame0) * 1e3, hitCount);
 			while (done < hitCount && ctx.ok)
 			{
 				const BatchPlan plan = PlanBatch(budget, hitCount - done, numLights, p.numAmbientSamples, p.numSamples, p.maxBounces, ambientOn, shrink);
@@ -273,6 +283,9 @@ namespace spt
 				launch_for(ctx, 1, BeginBatchKernel{ counters, plan.firstHits });
 				launch_for(ctx, plan.firstHits, SeedKernel{ a });
 				uint32_t usedLevels = levels;
+				uint32_t* pin = ctx.Pinned();
+				constexpr int kMarkLevel = 10;                                  // markers 10 / 11: level read-backs (alternating)
+				if (!ctx.ok || !pin) return SAILOR_PT_ERR_CUDA;
 				for (uint32_t level = 0; level < levels; level++)
 				{
 					const LevelInfo* L = &counters->level[level];
@@ -306,15 +319,22 @@ namespace spt
 						}
 					}
 					launch_for(ctx, 1, NextLevelKernel{ counters, level, plan.recCap });
-					// A level without activations ends the batch (paths that left the scene, the 0.01 throughput cut): one 8-byte read
-					// per level instead of six launches for every remaining level (a convex object's batch stops after level 1).
+					// A level without activations ends the batch (paths that left the scene, the 0.01 throughput cut).  Its record range is
+					// read back WITHOUT draining the queue: the copy for level L+1 is queued behind level L, and the host looks at it only
+					// after it has queued level L+1 as well, so the GPU works on the next level while the host round trip happens.  The price
+					// is one level of empty launches at the end of a batch (a few microseconds) instead of an idle GPU at every level.
 					if (level + 1u < levels)
 					{
-						uint32_t nextRange[2] = { 0u, 0u };
-						DevDownload(ctx, nextRange, &counters->level[level + 1u].recBegin, sizeof(nextRange));      // synchronises
+						ctx.ReadAsync(pin + 2u * (level + 1u), &counters->level[level + 1u].recBegin, 2u * sizeof(uint32_t));
+						ctx.Mark(kMarkLevel + (int)((level + 1u) & 1u));
+					}
+					if (level >= 1u)
+					{
+						ctx.WaitMark(kMarkLevel + (int)(level & 1u));
 						if (!ctx.ok) break;
-						if (hostTrace) fprintf(stderr, "[sailor_pt] t=%.3f ms   level %u done, next level has %u activations\n", (HostNow() - tFrame0) * 1e3, level, nextRange[1] - nextRange[0]);
-						if (nextRange[1] <= nextRange[0]) { usedLevels = level + 1u; break; }
+						const uint32_t nAct = pin[2u * level + 1u] > pin[2u * level] ? pin[2u * level + 1u] - pin[2u * level] : 0u;
+						if (hostTrace) fprintf(stderr, "[sailor_pt] t=%.3f ms   level %u was queued with %u activations\n", (HostNow() - tFrame0) * 1e3, level, nAct);
+						if (!nAct) { usedLevels = level; break; }              // this level's launches found nothing to do
 					}
 				}
 				st[3].Begin(ctx);
@@ -326,11 +346,12 @@ namespace spt
 				st[3].End(ctx);
 				// The batch's counters (overflow flag, ray count) are read back with a host round trip.  For the LAST batch of the frame
 				// the resolve kernel is queued first, so the GPU never idles on that read.
-				const bool lastBatch = (uint64_t)done + plan.firstHits >= hitCount;
-				if (lastBatch) launch_for(ctx, rows * cam.width, ResolveKernel{ sampleBuf, dImage, cam.width, cam.height, rowBegin, rowEnd, ns, p.msaa });
+				const bool lastBatch = (uint64_t)done + plan.firstHits >= hitCount && !prog.running;   // a running sum must be updated exactly once: only after the batch is known to be valid
+				if (lastBatch) launch_for(ctx, rows * cam.width, ResolveKernel{ sampleBuf, dImage, cam.width, cam.height, rowBegin, rowEnd, ns, prog.norm ? prog.norm : p.msaa, prog.running, prog.runningValid ? 1u : 0u });
 				struct { uint32_t recAlloc, auxAlloc, overflow, sky0, sky1, zero, fanEntries, slowCount, fan0, fan1; unsigned long long rays, fanSamples; } head;
 				DevDownload(ctx, &head, counters, sizeof(head));          // synchronises
 				if (!ctx.ok) break;
+				if (hostTrace) fprintf(stderr, "[sailor_pt] t=%.3f ms   batch done (%u levels)\n", (HostNow() - tFrame0) * 1e3, usedLevels);
 				if (head.overflow)
 				{
 					if (plan.firstHits <= 1024u || shrink > 16u) { ctx.error = "wavefront arenas overflow even for the smallest batch"; return SAILOR_PT_ERR_LIMIT; }
@@ -342,7 +363,7 @@ namespace spt
 				resolved = lastBatch;
 			}
 		}
-		if (!resolved) launch_for(ctx, rows * cam.width, ResolveKernel{ sampleBuf, dImage, cam.width, cam.height, rowBegin, rowEnd, ns, p.msaa });
+		if (!resolved) launch_for(ctx, rows * cam.width, ResolveKernel{ sampleBuf, dImage, cam.width, cam.height, rowBegin, rowEnd, ns, prog.norm ? prog.norm : p.msaa, prog.running, prog.runningValid ? 1u : 0u });
 		ctx.Mark(1);
 		ctx.Sync();
 		rs.traverseLaunches = tt.Spans();

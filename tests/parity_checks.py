@@ -119,3 +119,79 @@ def render_mean(lib, path, params, seeds):
             lin, _ = s.render(params, want_srgb=False)
             acc = lin.astype(np.float64) if acc is None else acc + lin
     return acc / len(seeds)
+
+
+def read_pfm(path):
+    with open(path, "rb") as f:
+        assert f.readline().strip() == b"PF"
+        w, h = (int(v) for v in f.readline().split())
+        assert float(f.readline()) < 0              # little endian
+        data = np.frombuffer(f.read(), dtype="<f4").reshape(h, w, 3)
+    return data[::-1]                               # PFM stores the bottom row first
+
+
+def read_hdr(path):
+    with open(path, "rb") as f:
+        assert f.readline().startswith(b"#?RADIANCE")
+        while f.readline().strip():
+            pass
+        dims = f.readline().split()
+        h, w = int(dims[1]), int(dims[3])
+        rgbe = np.frombuffer(f.read(), np.uint8).reshape(h, w, 4).astype(np.float32)
+    scale = np.where(rgbe[..., 3:] > 0, np.exp2(rgbe[..., 3:] - 136.0), 0.0)
+    return rgbe[..., :3] * scale
+
+
+def check_progressive_and_image_io(lib, path, tmpdir):
+    """a progressive render (in passes, interrupted, resumed from its checkpoint in a NEW scene object)
+    has the same bits as the one-shot render; .pfm keeps the exact bits, .hdr is within RGBE precision; the comparison report
+    equals numpy's."""
+    import os
+    from sailor_b200.capi import Params, SailorPtError
+    base = dict(height=40, num_samples=2, num_ambient_samples=2, max_bounces=2, msaa=5, ambient=(0.9, 0.8, 0.7), seed=11)
+    ck = os.path.join(str(tmpdir), "frame.ckpt")
+    with lib.load_scene(path) as s:
+        full, srgb_full = s.render(Params(**base))
+        # 1. all passes in one call
+        lin, srgb, done = s.render_progressive(Params(**base), 2)
+        assert done == 5 and np.array_equal(bits(lin), bits(full)) and np.array_equal(srgb, srgb_full)
+        # 2. interrupted after one pass of 2 samples: the partial estimate is normalised by the samples done
+        part, _, done = s.render_progressive(Params(**base), 2, max_passes=1, checkpoint=ck)
+        assert done == 2 and os.path.exists(ck)
+        two = s.render(Params(msaa_range=(0, 2), **base))[0].astype(np.float64) * 5 / 2
+        assert np.allclose(part, two, rtol=1e-5, atol=1e-6)
+    with lib.load_scene(path) as s2:                # a new process would start here
+        # 3. resume: 2 + 2 + 1 samples, checkpoint after every pass
+        lin2, srgb2, done = s2.render_progressive(Params(**base), 2, checkpoint=ck, resume=True, checkpoint_every_pass=True)
+        assert done == 5 and np.array_equal(bits(lin2), bits(full)) and np.array_equal(srgb2, srgb_full)
+        # 4. resuming a finished checkpoint renders nothing and returns the same frame
+        lin3, _, done = s2.render_progressive(Params(**base), 2, checkpoint=ck, resume=True)
+        assert done == 5 and np.array_equal(bits(lin3), bits(full))
+        # 5. a checkpoint of another parameter set is refused
+        other = dict(base); other["max_bounces"] = 3
+        with pytest_raises(SailorPtError):
+            s2.render_progressive(Params(**other), 2, checkpoint=ck, resume=True)
+        # 6. a damaged checkpoint is an error, not a silent restart
+        blob = bytearray(open(ck, "rb").read()); blob[200] ^= 0x40
+        bad = os.path.join(str(tmpdir), "bad.ckpt"); open(bad, "wb").write(bytes(blob))
+        with pytest_raises(SailorPtError):
+            s2.render_progressive(Params(**base), 2, checkpoint=bad, resume=True)
+    # image files
+    pfm, hdr, png = (os.path.join(str(tmpdir), "f." + e) for e in ("pfm", "hdr", "png"))
+    lib.write_image(pfm, full); lib.write_image(hdr, full); lib.write_image(png, full)
+    assert np.array_equal(bits(read_pfm(pfm)), bits(full))
+    back = read_hdr(hdr)
+    assert np.all(np.abs(back - full) <= full.max(axis=2, keepdims=True) / 128.0 + 1e-6)
+    assert open(png, "rb").read(8) == b"\x89PNG\r\n\x1a\n"
+    # comparison report
+    noisy = (full * 1.01 + 0.001).astype(np.float32)
+    m = lib.compare_images(noisy, full)
+    d = np.abs(noisy.astype(np.float64) - full.astype(np.float64))
+    assert np.isclose(m["mean_rel_error"], d.sum() / np.abs(full.astype(np.float64)).sum(), rtol=1e-9)
+    assert np.isclose(m["rmse"], np.sqrt((d * d).mean()), rtol=1e-9) and np.isclose(m["max_abs"], d.max(), rtol=1e-9)
+    assert lib.compare_images(full, full)["psnr_db"] == 1e30
+
+
+def pytest_raises(exc):
+    import pytest
+    return pytest.raises(exc)

@@ -161,3 +161,19 @@ def test_run_writes_a_png(gpu, scene_dir, tmp_path):
     assert sailor_b200.PathTracer().Run(p) == 0
     data = open(out, "rb").read()
     assert data[:8] == b"\x89PNG\r\n\x1a\n" and len(data) > 100
+
+
+def test_progressive_render_checkpoint_resume_and_linear_image_files(gpu, scene_dir, tmp_path):
+    pc.check_progressive_and_image_io(gpu, _scene(scene_dir, "pbr", {}), tmp_path)
+
+
+def test_run_writes_linear_dumps_by_extension(gpu, scene_dir, tmp_path):
+    import sailor_b200
+    out = str(tmp_path / "cube.pfm")
+    p = Params()
+    sailor_b200.PathTracer.ParseCommandLineArgs(p, ["exe", "--in", _scene(scene_dir, "cube", {}), "--out", out, "--height", "48",
+                                                    "--samples", "4", "--bounces", "2", "--ambient", "ffffff"])
+    p.m_numAmbientSamples = p.m_numSamples
+    assert sailor_b200.PathTracer().Run(p) == 0
+    img = pc.read_pfm(out)
+    assert img.shape[0] == 48 and np.isfinite(img).all() and img.max() > 0

@@ -141,3 +141,7 @@ def test_converged_image_tolerance_cpu(emu, G, scene_dir):
     p = Params(height=24, camera="main_cam", num_samples=64, num_ambient_samples=64, max_bounces=4, msaa=8, ambient=(1.0, 1.0, 1.0))
     img = pc.render_mean(emu, _scene(scene_dir, "pbr", {}), p, seeds=range(300, 308))
     assert pc.mean_rel_error(img, G["pbr_converged"]) < 0.035
+
+
+def test_progressive_render_checkpoint_resume_and_linear_image_files(emu, scene_dir, tmp_path):
+    pc.check_progressive_and_image_io(emu, _scene(scene_dir, "pbr", {}), tmp_path)

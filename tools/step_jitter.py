@@ -14,7 +14,7 @@ p = bench.make_params(w, seed=1)
 with gpu.load_scene(path) as s:
     rows = []
     for i in range(n):
-        if i == n - 2: os.environ["SAILOR_PT_TRACE_HOST"] = "1"
+        if i == 2: os.environ["SAILOR_PT_TRACE_HOST"] = "1"
         t0 = time.perf_counter()
         s.render_resident(p, rebuild_bvh=True, output_stage=True)
         t1 = time.perf_counter()
