@@ -114,7 +114,7 @@ namespace spt
 	{
 		__shared__ uint32_t stackMem[kSmemStack * kTraceBlock];
 		PrimaryPassSource src{ a }; PrimaryPassSink sink{ a };
-		TraceWarpLoop<false>(a.bvh, a.total, counter, stackMem, src, sink);
+		TraceWarpLoop(a.bvh, a.total, counter, stackMem, src, sink);
 	}
 
 	inline void LaunchPrimaryPass(Ctx& ctx, const PrimaryArgs& a, uint32_t* counter)

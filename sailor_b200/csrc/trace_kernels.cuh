@@ -89,21 +89,7 @@ namespace spt
 #define SPT_STAT(i, v) do { } while (0)
 #endif
 
-	// node / triangle record loads: LDG.128 through the read-only path, or LDS.128 when the whole traversal layout was
-	// staged in shared memory (small scenes, kShared)
-	template<bool kShared>
-	__device__ __forceinline__ V4 LoadRec(const V4* p)
-	{
-		if (kShared)
-		{
-			V4 r;
-			asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
-			return r;
-		}
-		return ld4(p);
-	}
-
-	template<bool kShared, class Source, class Sink>
+	template<class Source, class Sink>
 	__device__ __forceinline__ void TraceWarpLoop(const BvhView& bvh, uint32_t n, uint32_t* __restrict__ counter, uint32_t* stackMem, Source& src, Sink& sink)
 	{
 		// 32-bit shared-window address of this lane's stack column: [entry][thread], 4-byte entries
@@ -177,8 +163,8 @@ namespace spt
 					if (!(cur & kLeafBit))
 					{
 						const TNode* nd = bvh.nodes + cur;
-						const V4 q0 = LoadRec<kShared>(&nd->q0), q1 = LoadRec<kShared>(&nd->q1), q2 = LoadRec<kShared>(&nd->q2);
-						const V4 q3 = LoadRec<kShared>(reinterpret_cast<const V4*>(&nd->left));
+						const V4 q0 = ld4(&nd->q0), q1 = ld4(&nd->q1), q2 = ld4(&nd->q2);
+						const V4 q3 = ld4(reinterpret_cast<const V4*>(&nd->left));
 						uint32_t c1 = f2u(q3.x), c2 = f2u(q3.y);
 						float d1, d2;
 						if (safe)
@@ -229,7 +215,7 @@ namespace spt
 					if ((cur & kLeafBit) && cur != kLaneIdle)
 					{
 						const TTri* T = bvh.tris + (cur & ~kLeafBit);
-						const V4 a = LoadRec<kShared>(&T->a), b = LoadRec<kShared>(&T->b), c = LoadRec<kShared>(&T->c);
+						const V4 a = ld4(&T->a), b = ld4(&T->b), c = ld4(&T->c);
 						const uint32_t triId = f2u(c.y);
 						bool pop = f2u(c.w) != 0u;                                  // last triangle of its leaf
 						if (ignore != triId)                                       // BVH.cpp:136-139
@@ -317,7 +303,7 @@ namespace spt
 		__shared__ uint32_t stackMem[kSmemStack * kTraceBlock];
 		if (nPtr) { const uint32_t m = *nPtr; if (m < n) n = m; }
 		QueueSource src{ rays }; QueueSink sink{ hits };
-		TraceWarpLoop<false>(bvh, n, counter, stackMem, src, sink);
+		TraceWarpLoop(bvh, n, counter, stackMem, src, sink);
 	}
 
 	__global__ void __launch_bounds__(kTraceBlock) k_trace_level(BvhView bvh, const RayRec* __restrict__ rays, Hit* __restrict__ hits,
@@ -326,7 +312,7 @@ namespace spt
 		__shared__ uint32_t stackMem[kSmemStack * kTraceBlock];
 		{ const uint32_t m = *nPtr; if (m < n) n = m; }
 		QueueSource src{ rays }; WavefrontSink sink{ hits, out.status + *out.auxBase, out.slowList, out.slowCount };
-		TraceWarpLoop<false>(bvh, n, counter, stackMem, src, sink);
+		TraceWarpLoop(bvh, n, counter, stackMem, src, sink);
 	}
 
 	// ---- small scenes: the whole traversal layout lives in shared memory --------------------------------------------
@@ -432,33 +418,10 @@ namespace spt
 		}
 	}
 
-	// Small scene, warp-loop form (tuning variant, OFF): the persistent vote / refill loop of the big kernels reading nodes and
-	// triangles from shared memory.  Measured on C2 (tools/trace_variants.py, profiles/r01e_SUMMARY.md): 3.54 ms against 2.52 ms
-	// for the thread-per-ray form above — with traversals of one to five steps the vote + refill bookkeeping costs more than the
-	// idle lanes it removes (17 of 32 lanes active in the thread-per-ray form).
-#ifndef SPT_SMALL_WARP
-#define SPT_SMALL_WARP 0
-#endif
-	template<bool kWavefront>
-	__global__ void __launch_bounds__(kTraceBlock) k_trace_small_warp(const TNode* __restrict__ gNodes, uint32_t numNodes, const TTri* __restrict__ gTris, uint32_t numTris,
-		uint32_t rootRef, const RayRec* __restrict__ rays, Hit* __restrict__ hits, uint32_t n, const uint32_t* __restrict__ nPtr, uint32_t* __restrict__ counter, WavefrontOut out)
-	{
-		extern __shared__ __align__(16) unsigned char smallMem[];
-		uint32_t* stackMem = reinterpret_cast<uint32_t*>(smallMem);
-		V4* sNodes = reinterpret_cast<V4*>(smallMem + (size_t)kSmemStack * kTraceBlock * 4u);
-		V4* sTris = sNodes + (size_t)numNodes * 4;
-		{
-			const V4* gn = reinterpret_cast<const V4*>(gNodes); const V4* gt = reinterpret_cast<const V4*>(gTris);
-			for (uint32_t i = threadIdx.x; i < numNodes * 4u; i += kTraceBlock) sNodes[i] = ld4(gn + i);
-			for (uint32_t i = threadIdx.x; i < numTris * 3u; i += kTraceBlock) sTris[i] = ld4(gt + i);
-		}
-		__syncthreads();
-		if (nPtr) { const uint32_t m = *nPtr; if (m < n) n = m; }
-		BvhView bvh; bvh.nodes = reinterpret_cast<const TNode*>(sNodes); bvh.tris = reinterpret_cast<const TTri*>(sTris); bvh.rootRef = rootRef; bvh.numNodes = numNodes; bvh.numTris = numTris;
-		QueueSource src{ rays };
-		if (kWavefront) { WavefrontSink sink{ hits, out.status + *out.auxBase, out.slowList, out.slowCount }; TraceWarpLoop<true>(bvh, n, counter, stackMem, src, sink); }
-		else { QueueSink sink{ hits }; TraceWarpLoop<true>(bvh, n, counter, stackMem, src, sink); }
-	}
+	// Two other forms of the small-scene kernel were measured on C2 and rejected (profiles/r01f_SUMMARY.md): the persistent
+	// vote / refill warp loop reading shared memory (3.54 ms against 2.52 ms: with walks of a few steps the bookkeeping costs
+	// more than the idle lanes it removes) and a two-phase form that retires root-miss rays first and compacts the survivors
+	// (2.67 ms: 70 % of a first-hit level's rays point INTO a convex object and cross it, so there is little to compact).
 
 	// primary rays of sample 0 generated in-kernel (no ray queue traffic): work index -> 8x4 pixel tile + lane
 	struct PrimarySource
@@ -494,7 +457,7 @@ namespace spt
 		// 8x4 pixel tiles per warp keep the 32 rays of a fetch spatially coherent
 		const uint32_t tilesX = (cam.width + 7) / 8, tilesY = (cam.height + 3) / 4;
 		PrimarySource src{ cam, tilesX }; PrimarySink sink{ hits, src };
-		TraceWarpLoop<false>(bvh, tilesX * tilesY * 32u, counter, stackMem, src, sink);
+		TraceWarpLoop(bvh, tilesX * tilesY * 32u, counter, stackMem, src, sink);
 	}
 
 	inline int TraceGridSize()
@@ -524,24 +487,6 @@ namespace spt
 		}
 		return true;
 	}
-	template<bool kWavefront>
-	inline int SmallWarpGrid(size_t sceneBytes, size_t& smem)
-	{
-		smem = (size_t)kSmemStack * kTraceBlock * 4u + sceneBytes;
-		static int perSm[2] = { 0, 0 }; static size_t forBytes[2] = { 0, 0 };
-		int& v = perSm[kWavefront ? 1 : 0];
-		if (!v || forBytes[kWavefront ? 1 : 0] != smem)
-		{
-			cudaFuncSetAttribute(k_trace_small_warp<kWavefront>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmallSceneBytes + (size_t)kSmemStack * kTraceBlock * 4u));
-			int n = 1;
-			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_small_warp<kWavefront>, kTraceBlock, smem);
-			v = n > 0 ? n : 1; forBytes[kWavefront ? 1 : 0] = smem;
-		}
-		int dev = 0, sms = 148;
-		cudaGetDevice(&dev);
-		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-		return sms * v;
-	}
 	inline uint32_t SmallGrid(uint32_t n)
 	{
 		uint32_t blocks = (n + kSmallBlock - 1) / kSmallBlock;
@@ -555,13 +500,7 @@ namespace spt
 		size_t smallBytes;
 		if (SmallScene(bvh, smallBytes))
 		{
-#if SPT_SMALL_WARP
-			size_t smem; const int grid = SmallWarpGrid<false>(smallBytes, smem);
-			DevMemset(ctx, counter, 0, sizeof(uint32_t));
-			k_trace_small_warp<false><<<grid, kTraceBlock, smem, ctx.stream>>>(bvh.nodes, bvh.numNodes, bvh.tris, bvh.numTris, bvh.rootRef, rays, hits, n, nPtr, counter, WavefrontOut{});
-#else
 			k_trace_rays_small<false><<<SmallGrid(n), kSmallBlock, smallBytes, ctx.stream>>>(bvh.nodes, bvh.numNodes, bvh.tris, bvh.numTris, bvh.rootRef, rays, hits, n, nPtr, WavefrontOut{});
-#endif
 			ctx.kernelLaunches++;
 			SPT_CUDA_CHECK(ctx, cudaGetLastError());
 			return;
@@ -579,13 +518,7 @@ namespace spt
 		size_t smallBytes;
 		if (SmallScene(bvh, smallBytes))
 		{
-#if SPT_SMALL_WARP
-			size_t smem; const int grid = SmallWarpGrid<true>(smallBytes, smem);
-			DevMemset(ctx, counter, 0, sizeof(uint32_t));
-			k_trace_small_warp<true><<<grid, kTraceBlock, smem, ctx.stream>>>(bvh.nodes, bvh.numNodes, bvh.tris, bvh.numTris, bvh.rootRef, rays, hits, cap, nPtr, counter, out);
-#else
 			k_trace_rays_small<true><<<SmallGrid(cap), kSmallBlock, smallBytes, ctx.stream>>>(bvh.nodes, bvh.numNodes, bvh.tris, bvh.numTris, bvh.rootRef, rays, hits, cap, nPtr, out);
-#endif
 		}
 		else
 		{

@@ -26,7 +26,6 @@ VARIANTS = {
     "block256": ["SPT_TRACE_BLOCK=256"],
     "fan4": ["SPT_FAN_MIN_BLOCKS=4"],
     "fan2": ["SPT_FAN_MIN_BLOCKS=2"],
-    "smallthread": ["SPT_SMALL_WARP=0"],
 }
 
 if sys.argv[1] == "build":
