@@ -712,6 +712,11 @@ namespace spt
 		}
 	};
 
+#ifndef SPT_GATHER_BLOCK
+#define SPT_GATHER_BLOCK 4
+#endif
+	constexpr uint32_t kGatherBlock = SPT_GATHER_BLOCK;      // RayAux entries fetched per round of GatherKernel's loops
+
 	// ---- gather: replay :690-871 over one activation's rays, bottom-up ----------------------------------------------
 	struct GatherKernel
 	{
@@ -740,36 +745,55 @@ namespace spt
 					V3 amb1 = v3(0.0f);
 					if (!(flags & kNfThick))
 					{
-#pragma unroll 8
-						for (uint32_t k = 0; k < nA; k++, g++)
+						// entries are fetched kGatherBlock at a time (records AND status bytes, unconditionally) before any of them is looked at:
+						// the loop is bound by memory latency, and a status load that waits for its record's tag doubles the chain
+						for (uint32_t k0 = 0; k0 < nA; k0 += kGatherBlock)
 						{
-							const RayAux x = a.aux[g];
-							if ((x.tag & kRkMask) != kRkHemi) continue;                                                       // dead ray (maxBounces == 0)
-							if (x.tag & kRsSky2) amb1 = amb1 + v3(x.a0, x.a1, x.a2);                                          // a sky walk ended (:730-735)
-							else if (!a.status[g]) amb1 = amb1 + glm_clamp((v3(x.a0, x.a1, x.a2) * a.ambient * x.a3) / pdfHemisphere, 0.0f, 10.0f);   // miss: att = 1 (:587-590)
+							RayAux xs[kGatherBlock]; uint8_t hitSomething[kGatherBlock];
+#pragma unroll
+							for (uint32_t j = 0; j < kGatherBlock; j++) if (k0 + j < nA) { xs[j] = a.aux[g + j]; hitSomething[j] = a.status[g + j]; }
+#pragma unroll
+							for (uint32_t j = 0; j < kGatherBlock; j++)
+							{
+								if (k0 + j >= nA) break;
+								const RayAux& x = xs[j];
+								if ((x.tag & kRkMask) != kRkHemi) continue;                                                   // dead ray (maxBounces == 0)
+								if (x.tag & kRsSky2) amb1 = amb1 + v3(x.a0, x.a1, x.a2);                                      // a sky walk ended (:730-735)
+								else if (!hitSomething[j]) amb1 = amb1 + glm_clamp((v3(x.a0, x.a1, x.a2) * a.ambient * x.a3) / pdfHemisphere, 0.0f, 10.0f);   // miss: att = 1 (:587-590)
+							}
+							g += (nA - k0 < kGatherBlock) ? nA - k0 : kGatherBlock;
 						}
 					}
 					amb1 = amb1 / (float)nA;                                              // :739
 					V3 amb2 = v3(0.0f), indirect = v3(0.0f); float avgPdf = 0.0f, cnt = 0.0f;
-#pragma unroll 8
-					for (uint32_t i = 0; i < nS; i++, g++)
+					const bool bouncesLeft = (rec->bounces & 0xFFFFu) > 0;
+					for (uint32_t i0 = 0; i0 < nS; i0 += kGatherBlock)
 					{
-						const RayAux x = a.aux[g];
-						if (x.tag & kRsSkipped) continue;
-						V3 value = v3(x.a0, x.a1, x.a2);
-						if (!a.status[g])                                                                                 // miss (:786-796)
+						RayAux xs[kGatherBlock]; uint8_t hitSomething[kGatherBlock];
+#pragma unroll
+						for (uint32_t j = 0; j < kGatherBlock; j++) if (i0 + j < nS) { xs[j] = a.aux[g + j]; hitSomething[j] = a.status[g + j]; }
+#pragma unroll
+						for (uint32_t j = 0; j < kGatherBlock; j++)
 						{
-							value = glm_clamp(value * a.ambient, 0.0f, 10.0f);
-							amb2 = amb2 + value; avgPdf += x.a3; indirect = indirect + value;
+							if (i0 + j >= nS) break;
+							const RayAux& x = xs[j];
+							if (x.tag & kRsSkipped) continue;
+							V3 value = v3(x.a0, x.a1, x.a2);
+							if (!hitSomething[j])                                                                         // miss (:786-796)
+							{
+								value = glm_clamp(value * a.ambient, 0.0f, 10.0f);
+								amb2 = amb2 + value; avgPdf += x.a3; indirect = indirect + value;
+							}
+							else if (x.tag & kRsHit)                                                                      // :816-832, value = clamp(term*att*L)
+							{
+								indirect = indirect + value;
+								if (x.tag & kRsSky2) { amb2 = amb2 + value * v3(x.b0, x.b1, x.b2); avgPdf += x.a3; }
+							}
+							else if (bouncesLeft)                                                                         // boolean ray below the 0.01 cut: raytraced = 0 (:809,:816)
+								indirect = indirect + glm_clamp(value * v3(0.0f), 0.0f, 10.0f);
+							cnt += 1.0f;                                                                                  // :835
 						}
-						else if (x.tag & kRsHit)                                                                          // :816-832, value = clamp(term*att*L)
-						{
-							indirect = indirect + value;
-							if (x.tag & kRsSky2) { amb2 = amb2 + value * v3(x.b0, x.b1, x.b2); avgPdf += x.a3; }
-						}
-						else if ((rec->bounces & 0xFFFFu) > 0)                                                            // boolean ray below the 0.01 cut: raytraced = 0 (:809,:816)
-							indirect = indirect + glm_clamp(value * v3(0.0f), 0.0f, 10.0f);
-						cnt += 1.0f;                                                                                      // :835
+						g += (nS - i0 < kGatherBlock) ? nS - i0 : kGatherBlock;
 					}
 					amb2 = amb2 / cnt; avgPdf = avgPdf / cnt;                             // :838-839
 					const V3 ambient = amb1 + amb2;
