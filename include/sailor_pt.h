@@ -97,7 +97,7 @@ typedef struct SailorPtStats {
 	uint32_t traverseLaunches;
 	uint32_t kernelLaunches;  /* product: all kernel launches of the last call */
 	uint32_t threads;         /* oracle: worker threads used */
-	uint32_t reserved;
+	uint32_t batches;         /* product, render calls: batches of first hits the wavefront processed (one non-empty fan-out pass pair each) */
 	uint64_t h2dBytes;        /* product: bytes copied host->device by the last call */
 	uint64_t d2hBytes;        /* product: bytes copied device->host by the last call */
 	/* product, render calls: device time per wavefront stage (CUDA events on the launch stream); secondsShade is their sum + the rest */

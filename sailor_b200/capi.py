@@ -37,7 +37,7 @@ class SailorPtStats(C.Structure):
         ("secondsTotal", C.c_double), ("secondsFlatten", C.c_double), ("secondsBvhBuild", C.c_double),
         ("secondsTraverse", C.c_double), ("secondsShade", C.c_double), ("secondsOutput", C.c_double),
         ("traverseLaunches", C.c_uint32), ("kernelLaunches", C.c_uint32), ("threads", C.c_uint32),
-        ("reserved", C.c_uint32), ("h2dBytes", C.c_uint64), ("d2hBytes", C.c_uint64),
+        ("batches", C.c_uint32), ("h2dBytes", C.c_uint64), ("d2hBytes", C.c_uint64),
         ("secondsExpand", C.c_double), ("secondsFanOut", C.c_double), ("secondsClassify", C.c_double), ("secondsGather", C.c_double),
         ("fanOutSamples", C.c_uint64),
     ]

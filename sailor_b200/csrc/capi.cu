@@ -367,7 +367,7 @@ int32_t SailorPt_RenderResident(SailorPtScene* s, const SailorPtParams* p, uint3
 	g_stats.secondsFlatten = D.ctx.Between(Ctx::kMarkCall0, Ctx::kMarkCall1);         // whole call on the launch stream (CUDA events); field reused: no flatten here
 	g_stats.rays = rs.rays; g_stats.primarySamples = rs.primarySamples; g_stats.secondsTraverse = rs.secondsTraverse;
 	g_stats.secondsShade = rs.secondsShade; g_stats.secondsExpand = rs.secondsStage[0]; g_stats.secondsFanOut = rs.secondsStage[1]; g_stats.secondsClassify = rs.secondsStage[2];
-	g_stats.secondsGather = rs.secondsStage[3]; g_stats.fanOutSamples = rs.fanOutSamples; g_stats.secondsOutput = tOut; g_stats.secondsBvhBuild = tBuild; g_stats.traverseLaunches = rs.traverseLaunches;
+	g_stats.secondsGather = rs.secondsStage[3]; g_stats.fanOutSamples = rs.fanOutSamples; g_stats.secondsOutput = tOut; g_stats.secondsBvhBuild = tBuild; g_stats.traverseLaunches = rs.traverseLaunches; g_stats.batches = rs.batches;
 	g_stats.kernelLaunches = D.ctx.kernelLaunches; g_stats.h2dBytes = D.ctx.h2dBytes; g_stats.d2hBytes = D.ctx.d2hBytes;
 	g_stats.secondsTotal = HostNow() - t0;
 	return FromCtx(D, SAILOR_PT_OK);

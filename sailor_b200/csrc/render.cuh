@@ -358,7 +358,7 @@ namespace spt
 					shrink++;
 					continue;                                                // redo this batch smaller (results are keyed per activation, not per batch); the resolve is redone too
 				}
-				rs.rays += head.rays; rs.fanOutSamples += head.fanSamples;
+				rs.rays += head.rays; rs.fanOutSamples += head.fanSamples; rs.batches++;
 				done += plan.firstHits;
 				resolved = lastBatch;
 			}
