@@ -63,7 +63,23 @@ def build(force=False, verbose=False, defines=(), out=None):
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("link failed")
+    if out is None:
+        build_cli()
     return out or LIB
+
+
+CLI = os.path.join(HERE, "sailor_pt")
+
+
+def build_cli():
+    """sailor_b200/sailor_pt: the C++ host of csrc/cli_main.cpp, linked against the C-ABI library only (rpath $ORIGIN)."""
+    cmd = ["g++", "-std=c++17", "-O2", "-o", CLI, os.path.join(SRC, "cli_main.cpp"), "-I", os.path.join(HERE, "..", "include"),
+           "-L", HERE, "-lsailor_pt_cuda", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("building the sailor_pt host failed")
+    return CLI
 
 
 if __name__ == "__main__":

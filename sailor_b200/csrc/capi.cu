@@ -542,7 +542,12 @@ int32_t SailorPt_RenderProgressive(SailorPtScene* s, const SailorPtParams* p, ui
 	if (msaaDoneOut) *msaaDoneOut = done;
 	g_stats = SailorPtStats{};
 	g_stats.rays = rays; g_stats.primarySamples = samples; g_stats.kernelLaunches = launches; g_stats.secondsTraverse = tTrav; g_stats.secondsTotal = HostNow() - t0;
-	if (rc == SAILOR_PT_OK && done >= p->msaa && p->output && p->output[0] && linearRGB) rc = SailorPt_WriteImage(p->output, c.width, c.height, linearRGB);
+	if (rc == SAILOR_PT_OK && done >= p->msaa && p->output && p->output[0])
+	{
+		std::vector<float> own;
+		if (!linearRGB) { own.resize(n * 3); D.residentLin.Download(D.ctx, own.data(), n * 3); if (!D.ctx.ok) return FromCtx(D, SAILOR_PT_ERR_CUDA); }
+		rc = SailorPt_WriteImage(p->output, c.width, c.height, linearRGB ? linearRGB : own.data());
+	}
 	return FromCtx(D, rc);
 }
 

@@ -82,3 +82,17 @@ def test_parse_command_line_args_matches_the_reference(which, request):
         assert (q.m_msaa, q.m_numSamples) == (msaa, s)
     p = lib.parse_command_line_args(Params(), ["exe", "--in", '"my', 'scene.glb"'])
     assert p.m_pathToModel == "my scene.glb"
+
+
+def test_cpp_host_builds_and_fails_loudly_without_a_cuda_device(scene_dir):
+    """sailor_b200/sailor_pt (csrc/cli_main.cpp): the C++ caller the reference lacks, linked against the C-ABI only."""
+    import subprocess
+    import torch
+    from sailor_b200 import build as product_build
+    product_build.build()
+    exe = product_build.build_cli()
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 1 and "usage:" in r.stderr and "cuda sm_100a" in r.stderr
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe, "--in", scenes.ensure(scene_dir, "cube"), "--out", os.path.join(scene_dir, "cli.png")], capture_output=True, text=True)
+        assert r.returncode == -ERR_NO_DEVICE and "no CPU path" in r.stderr

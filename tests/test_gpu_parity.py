@@ -177,3 +177,25 @@ def test_run_writes_linear_dumps_by_extension(gpu, scene_dir, tmp_path):
     assert sailor_b200.PathTracer().Run(p) == 0
     img = pc.read_pfm(out)
     assert img.shape[0] == 48 and np.isfinite(img).all() and img.max() > 0
+
+
+def test_cpp_host_renders_like_the_library(gpu, scene_dir, tmp_path):
+    """The C++ host (csrc/cli_main.cpp) over the C-ABI: one-shot PNG, and a progressive render whose .pfm has the bits of SailorPt_Render."""
+    import subprocess
+    from sailor_b200 import build as product_build
+    exe = product_build.build_cli()
+    scene = _scene(scene_dir, "cube", {})
+    png, pfm, ck = str(tmp_path / "a.png"), str(tmp_path / "a.pfm"), str(tmp_path / "a.ckpt")
+    common = ["--in", scene, "--height", "64", "--samples", "16", "--bounces", "2", "--ambient", "ffffff", "--seed", "5"]
+    r = subprocess.run([exe] + common + ["--out", png], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(png, "rb").read(8) == b"\x89PNG\r\n\x1a\n"
+    r = subprocess.run([exe] + common + ["--out", pfm, "--passes", "1", "--checkpoint", ck], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    p = Params()
+    gpu.parse_command_line_args(p, ["exe"] + common)
+    p.m_numAmbientSamples = p.m_numSamples
+    p.seed = 5
+    with gpu.load_scene(scene) as s:
+        lin, _ = s.render(p)
+    assert np.array_equal(pc.bits(pc.read_pfm(pfm)), pc.bits(lin))
