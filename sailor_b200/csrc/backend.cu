@@ -46,10 +46,8 @@ namespace spt
 			Fail("cudaStreamCreate/cudaEventCreate", (int)cudaGetLastError());
 			return SAILOR_PT_ERR_CUDA;
 		}
-		for (int i = 0; i < kMarkers; i++)
-		{
-			if (cudaEventCreate(&ev[i]) != cudaSuccess) { Fail("cudaEventCreate", (int)cudaGetLastError()); return SAILOR_PT_ERR_CUDA; }
-		}
+		// marker events are created on first use (Mark): a scene object per frame, like the reference's PathTracer object per Run,
+		// should not pay for 64 events it never records
 		ok = true;
 		return SAILOR_PT_OK;
 	}
@@ -74,7 +72,12 @@ namespace spt
 		return (double)ms * 1e-3;
 	}
 
-	void Ctx::Mark(int i) { if (ok) SPT_CUDA_CHECK(*this, cudaEventRecord(ev[i], stream)); }
+	void Ctx::Mark(int i)
+	{
+		if (!ok) return;
+		if (!ev[i]) SPT_CUDA_CHECK(*this, cudaEventCreate(&ev[i]));
+		if (ok) SPT_CUDA_CHECK(*this, cudaEventRecord(ev[i], stream));
+	}
 	void Ctx::WaitMark(int i) { if (ok) SPT_CUDA_CHECK(*this, cudaEventSynchronize(ev[i])); }
 	uint32_t* Ctx::Pinned()
 	{
@@ -310,10 +313,29 @@ namespace spt
 		return blocks;
 	}
 
+	// Timing events are recycled through a process-wide free list: a host that creates one scene object per frame (the reference's
+	// PathTracer object per Run) would otherwise create and destroy ~40 events per frame.
+	namespace
+	{
+		std::mutex g_eventPoolMutex;
+		std::unordered_map<int, std::vector<cudaEvent_t>> g_eventPool;     // per device: an event belongs to the device it was created on
+		int CurrentDevice() { int d = 0; if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); d = 0; } return d; }
+	}
 	void SpanTimer::Begin(Ctx& ctx)
 	{
 		if (!ctx.ok) return;
-		while (ev.size() < used + 2) { cudaEvent_t e = nullptr; if (cudaEventCreate(&e) != cudaSuccess) { ctx.Fail("cudaEventCreate", (int)cudaGetLastError()); return; } ev.push_back(e); }
+		while (ev.size() < used + 2)
+		{
+			cudaEvent_t e = nullptr;
+			{
+				std::lock_guard<std::mutex> lock(g_eventPoolMutex);
+				if (device < 0) device = CurrentDevice();
+				std::vector<cudaEvent_t>& pool = g_eventPool[device];
+				if (!pool.empty()) { e = pool.back(); pool.pop_back(); }
+			}
+			if (!e && cudaEventCreate(&e) != cudaSuccess) { ctx.Fail("cudaEventCreate", (int)cudaGetLastError()); return; }
+			ev.push_back(e);
+		}
 		SPT_CUDA_CHECK(ctx, cudaEventRecord(ev[used], ctx.stream));
 	}
 	void SpanTimer::End(Ctx& ctx)
@@ -329,7 +351,13 @@ namespace spt
 		used = 0;
 		return s;
 	}
-	void SpanTimer::Destroy() { for (cudaEvent_t e : ev) cudaEventDestroy(e); ev.clear(); used = 0; }
+	void SpanTimer::Destroy()
+	{
+		std::lock_guard<std::mutex> lock(g_eventPoolMutex);
+		std::vector<cudaEvent_t>& pool = g_eventPool[device < 0 ? CurrentDevice() : device];
+		for (cudaEvent_t e : ev) { if (pool.size() < 4096) pool.push_back(e); else cudaEventDestroy(e); }
+		ev.clear(); used = 0;
+	}
 
 	// ---- exclusive scan: reduce-then-scan, 2048 items per CTA, coalesced, warp shuffles -----------------
 	namespace

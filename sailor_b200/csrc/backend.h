@@ -213,6 +213,7 @@ namespace spt
 		std::vector<cudaEvent_t> ev;
 #endif
 		size_t used = 0; double acc = 0.0; double t0 = 0.0;
+		int device = -1;            // device the events were created on (they go back to that device's free list)
 		void Begin(Ctx& ctx);
 		void End(Ctx& ctx);
 		double Collect(Ctx& ctx);     // after ctx.Sync(): seconds of all spans since the last Collect
