@@ -131,6 +131,14 @@ namespace spt
 		g_allocStream[p] = ctx.stream;
 		return p;
 	}
+	int DevCurrent() { int d = 0; if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); d = 0; } return d; }
+	void* DevAllocPlain(Ctx& ctx, size_t bytes)
+	{
+		void* p = nullptr;
+		if (ctx.ok) SPT_CUDA_CHECK(ctx, cudaMalloc(&p, bytes));
+		return ctx.ok ? p : nullptr;
+	}
+	void DevFreePlain(void* p) { if (p && cudaFree(p) != cudaSuccess) cudaGetLastError(); }
 	size_t DevMemAvailable()
 	{
 		size_t freeB = 0, totalB = 0;
@@ -464,6 +472,9 @@ namespace spt
 	void* DevAllocBytes(Ctx&, size_t bytes) { return malloc(bytes ? bytes : 1); }
 	void DevFreeBytes(void* p) { free(p); }
 	size_t DevMemAvailable() { return (size_t)4 << 30; }
+	int DevCurrent() { return 0; }
+	void* DevAllocPlain(Ctx&, size_t bytes) { return malloc(bytes ? bytes : 1); }
+	void DevFreePlain(void* p) { free(p); }
 	void DevUpload(Ctx& ctx, void* dst, const void* src, size_t bytes) { ctx.h2dBytes += bytes; memcpy(dst, src, bytes); }
 	void DevDownload(Ctx& ctx, void* dst, const void* src, size_t bytes) { ctx.d2hBytes += bytes; memcpy(dst, src, bytes); }
 	int HostPin(void* p, size_t bytes) { return (p && bytes) ? 0 : -1; }

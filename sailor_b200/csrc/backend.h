@@ -62,6 +62,10 @@ namespace spt
 #endif
 
 	void* DevAllocBytes(Ctx& ctx, size_t bytes);
+	int DevCurrent();                  // index of the current CUDA device (emu: 0)
+	// allocations that outlive the context (stream) they were made from: plain cudaMalloc / cudaFree, not stream-ordered
+	void* DevAllocPlain(Ctx& ctx, size_t bytes);
+	void DevFreePlain(void* p);
 	size_t DevMemAvailable();          // bytes a new allocation can still get (free device memory + what the pool holds back); emu: 4 GiB
 	void DevFreeBytes(void* p);
 	void DevUpload(Ctx& ctx, void* dst, const void* src, size_t bytes);
@@ -89,6 +93,18 @@ namespace spt
 		void Download(Ctx& ctx, T* dst, size_t count) const { if (count) DevDownload(ctx, dst, p, count * sizeof(T)); }
 		void Zero(Ctx& ctx) { if (n) DevMemset(ctx, p, 0, n * sizeof(T)); }
 		void Zero(Ctx& ctx, size_t count) { if (count) DevMemset(ctx, p, 0, count * sizeof(T)); }
+	};
+
+	// Buffer shared by every context of the process on one device (the wavefront arenas): not tied to any stream.
+	struct PlainBuf
+	{
+		unsigned char* p = nullptr; size_t n = 0;
+		void Ensure(Ctx& ctx, size_t bytes)
+		{
+			if (bytes <= n) return;
+			if (p) { ctx.Sync(); DevFreePlain(p); p = nullptr; n = 0; }
+			p = (unsigned char*)DevAllocPlain(ctx, bytes); n = p ? bytes : 0;
+		}
 	};
 
 	// ---- atomics usable from kernel bodies -------------------------------------------------------------

@@ -47,10 +47,6 @@ namespace spt
 		// results of the last RenderResident (stay on the device until read back or handed to NCCL)
 		DevBuf<float> residentLin; DevBuf<uint8_t> residentSrgb; uint32_t residentW = 0, residentH = 0;
 
-		// wavefront working set, kept across renders (only ever grows): 0 activation records, 1 RayAux arena, 2 rays,
-		// 3 hits, 4 per-sample results, 5 primary-hit queue, 6 batch counters, 7 blue-noise table, 8 fan-out contexts,
-		// 9 sky states, 10 sky rays, 11 sky hits, 12 ray status bytes, 13 slow list, 14 fan-out slot tables
-		DevBuf<unsigned char> renderMem[15];
 		SpanTimer traceTimer, stageTimer[4];      // stageTimer: expand, fan-out, classify (+sky), gather
 		// BVH build scratch, kept across builds
 		DevBuf<uint32_t> buildU32[24];

@@ -12,6 +12,8 @@
 // All working buffers live with the scene and are reused across frames (no allocation in the steady state).
 #pragma once
 #include "integrator.cuh"
+#include <mutex>
+#include <unordered_map>
 
 #ifndef SPT_EXPAND_MIN_BLOCKS
 #define SPT_EXPAND_MIN_BLOCKS 2
@@ -138,7 +140,7 @@ namespace spt
 	}
 #endif
 
-	template<class T> inline T* EnsureBytes(Ctx& ctx, DevBuf<unsigned char>& b, size_t count)
+	template<class T> inline T* EnsureBytes(Ctx& ctx, PlainBuf& b, size_t count)
 	{
 		b.Ensure(ctx, count * sizeof(T) + 16);
 		return reinterpret_cast<T*>(b.p);
@@ -192,6 +194,24 @@ namespace spt
 		return p;
 	}
 
+	// Wavefront working set, shared by every scene object of the process on one device and kept for the life of the process (it
+	// only ever grows): 0 activation records, 1 RayAux arena, 2 rays, 3 hits, 4 per-sample results, 5 primary-hit queue, 6 batch
+	// counters, 7 blue-noise table, 8 fan-out contexts, 9 sky states, 10 sky rays, 11 sky hits, 12 ray status bytes, 13 slow list,
+	// 14 fan-out slot tables.  A host that creates one scene object per frame (the reference's PathTracer object per Run) would
+	// otherwise allocate and free tens of GiB of arenas every frame (~1.5 ms per C2 frame even from the stream-ordered pool); plain
+	// cudaMalloc memory, because a stream-ordered allocation must be freed on a stream that may no longer exist.  One
+	// frame renders at a time per device (`frame` mutex); a frame saturates the GPU anyway.
+	struct SharedArenas { PlainBuf mem[15]; std::mutex frame; };
+	inline SharedArenas& ArenasOfCurrentDevice()
+	{
+		static std::mutex m;
+		static std::unordered_map<int, SharedArenas*>* all = new std::unordered_map<int, SharedArenas*>();   // leaked on purpose: never freed after CUDA teardown
+		std::lock_guard<std::mutex> lock(m);
+		SharedArenas*& p = (*all)[DevCurrent()];
+		if (!p) p = new SharedArenas();
+		return *p;
+	}
+
 	inline bool SceneHasThickTransmission(const HostScene& h)
 	{
 		for (const auto& m : h.materials) if (m.transmission > 0.0f && m.thickness > 0.0f) return true;
@@ -215,11 +235,14 @@ namespace spt
 		const uint64_t realSamples = (uint64_t)rows * cam.width * ns;
 		if (total >= 0xFFFFFF00ull) { ctx.error = "shard too large for one launch: split rows or samples"; return SAILOR_PT_ERR_LIMIT; }
 
-		float* sampleBuf = EnsureBytes<float>(ctx, D.renderMem[4], (size_t)realSamples * 3);
-		PrimaryHitRec* queue = EnsureBytes<PrimaryHitRec>(ctx, D.renderMem[5], (size_t)realSamples);
-		BatchCounters* counters = EnsureBytes<BatchCounters>(ctx, D.renderMem[6], 1);
-		if (D.renderMem[7].n == 0) { uint16_t* b = EnsureBytes<uint16_t>(ctx, D.renderMem[7], kBlueNoiseCount); DevUpload(ctx, b, kBlueNoiseK, sizeof(kBlueNoiseK)); }
-		const uint16_t* blue = reinterpret_cast<const uint16_t*>(D.renderMem[7].p);
+		SharedArenas& arenas = ArenasOfCurrentDevice();
+		std::lock_guard<std::mutex> frameLock(arenas.frame);
+		PlainBuf* renderMem = arenas.mem;
+		float* sampleBuf = EnsureBytes<float>(ctx, renderMem[4], (size_t)realSamples * 3);
+		PrimaryHitRec* queue = EnsureBytes<PrimaryHitRec>(ctx, renderMem[5], (size_t)realSamples);
+		BatchCounters* counters = EnsureBytes<BatchCounters>(ctx, renderMem[6], 1);
+		if (renderMem[7].n == 0) { uint16_t* b = EnsureBytes<uint16_t>(ctx, renderMem[7], kBlueNoiseCount); DevUpload(ctx, b, kBlueNoiseK, sizeof(kBlueNoiseK)); }
+		const uint16_t* blue = reinterpret_cast<const uint16_t*>(renderMem[7].p);
 		uint32_t* hitCounter = D.counter.p + 2;
 		if (!ctx.ok) return SAILOR_PT_ERR_CUDA;
 		DevMemset(ctx, hitCounter, 0, sizeof(uint32_t));
@@ -253,7 +276,7 @@ namespace spt
 			uint32_t shrink = 0;
 			uint32_t done = 0;
 			uint64_t held = 0;
-			for (const int k : { 0, 1, 2, 3, 8, 9, 10, 11, 12, 13, 14 }) held += D.renderMem[k].n;
+			for (const int k : { 0, 1, 2, 3, 8, 9, 10, 11, 12, 13, 14 }) held += renderMem[k].n;
 			const uint64_t budget = BatchBudget(held);
 			if (hostTrace) fprintf(stderr, "[sailor_pt] t=%.3f ms primary pass done: %u first hits\n", (HostNow() - tFrame0) * 1e3, hitCount);
 			while (done < hitCount && ctx.ok)
@@ -266,15 +289,15 @@ namespace spt
 				a.maxBounces = p.maxBounces; a.numSamples = p.numSamples; a.numAmbientSamples = p.numAmbientSamples;
 				a.ambient = pa.ambient; a.seed = p.seed;
 				a.hitQueue = queue; a.queueBegin = done; a.queueCount = plan.firstHits;
-				a.recs = EnsureBytes<NodeRec>(ctx, D.renderMem[0], plan.recCap); a.recCap = plan.recCap;
-				a.aux = EnsureBytes<RayAux>(ctx, D.renderMem[1], plan.auxCap); a.auxCap = plan.auxCap; a.hasSky = hasSky ? 1u : 0u;
-				a.rays = EnsureBytes<RayRec>(ctx, D.renderMem[2], plan.rayCap); a.hits = EnsureBytes<Hit>(ctx, D.renderMem[3], plan.rayCap); a.rayCap = plan.rayCap;
+				a.recs = EnsureBytes<NodeRec>(ctx, renderMem[0], plan.recCap); a.recCap = plan.recCap;
+				a.aux = EnsureBytes<RayAux>(ctx, renderMem[1], plan.auxCap); a.auxCap = plan.auxCap; a.hasSky = hasSky ? 1u : 0u;
+				a.rays = EnsureBytes<RayRec>(ctx, renderMem[2], plan.rayCap); a.hits = EnsureBytes<Hit>(ctx, renderMem[3], plan.rayCap); a.rayCap = plan.rayCap;
 				a.skyCap = hasSky ? plan.skyCap : 16u;
-				a.sky[0] = EnsureBytes<SkyState>(ctx, D.renderMem[9], (size_t)a.skyCap * 2); a.sky[1] = a.sky[0] + a.skyCap;
-				a.skyRays = EnsureBytes<RayRec>(ctx, D.renderMem[10], (size_t)a.skyCap * 2); a.skyHits = EnsureBytes<Hit>(ctx, D.renderMem[11], a.skyCap);
-				a.status = EnsureBytes<uint8_t>(ctx, D.renderMem[12], plan.auxCap); a.slowList = EnsureBytes<uint32_t>(ctx, D.renderMem[13], plan.rayCap);
-				a.fanCap = plan.firstHits + 1024u; a.fan = EnsureBytes<ShadeCtx>(ctx, D.renderMem[8], a.fanCap);
-				a.fanSlots[0] = EnsureBytes<uint32_t>(ctx, D.renderMem[14], (size_t)a.fanCap * 8u); a.fanSlots[1] = a.fanSlots[0] + (size_t)a.fanCap * 4u;
+				a.sky[0] = EnsureBytes<SkyState>(ctx, renderMem[9], (size_t)a.skyCap * 2); a.sky[1] = a.sky[0] + a.skyCap;
+				a.skyRays = EnsureBytes<RayRec>(ctx, renderMem[10], (size_t)a.skyCap * 2); a.skyHits = EnsureBytes<Hit>(ctx, renderMem[11], a.skyCap);
+				a.status = EnsureBytes<uint8_t>(ctx, renderMem[12], plan.auxCap); a.slowList = EnsureBytes<uint32_t>(ctx, renderMem[13], plan.rayCap);
+				a.fanCap = plan.firstHits + 1024u; a.fan = EnsureBytes<ShadeCtx>(ctx, renderMem[8], a.fanCap);
+				a.fanSlots[0] = EnsureBytes<uint32_t>(ctx, renderMem[14], (size_t)a.fanCap * 8u); a.fanSlots[1] = a.fanSlots[0] + (size_t)a.fanCap * 4u;
 				a.c = counters; a.sampleBuf = sampleBuf;
 				if (!ctx.ok) return SAILOR_PT_ERR_CUDA;
 				if (hostTrace) fprintf(stderr, "[sailor_pt] t=%.3f ms batch: first hits %u of %u (done %u), budget %.1f GiB, rayCap %u auxCap %u recCap %u shrink %u\n",
