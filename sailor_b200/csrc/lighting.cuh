@@ -180,9 +180,26 @@ namespace spt
 		outTransmissionRay = bHasTransmission && (randTransmission > 0.5f);
 		const float importanceRoughness = bSpecular ? s.orm.y : 1.0f;
 		const bool bBeckmann = importanceRoughness < 0.2f;
-		V3 H;
-		if (bBeckmann) H = bSpecular ? ImportanceSampleBeckmann(Xi, s.orm.y, N) : ImportanceSampleLambert(Xi, N);
-		else H = bSpecular ? ImportanceSampleGGX(Xi, s.orm.y, N) : ImportanceSampleLambert(Xi, N);
+		// The three lobes (ImportanceSampleBeckmann / GGX / Lambert, :162-230) differ only in cos(theta); phi, sin(theta) and the change
+		// of basis are the same expressions.  The 50/50 lobe pick splits a warp in two, so only cos(theta) is computed inside the
+		// branch and the expensive common tail (sincos, two normalisations) runs once with all lanes: same values, half the issue slots.
+		float cosTheta;
+		if (bSpecular)
+		{
+			if (bBeckmann)
+			{
+				const float alpha = std_max(s.orm.y * s.orm.y, 0.001f);
+				const float tanTheta2 = -alpha * alpha * logf(1.0f - Xi.y);
+				cosTheta = 1.0f / sqrtf(1.0f + tanTheta2);
+			}
+			else
+			{
+				const float a = std_max(s.orm.y * s.orm.y, 0.001f);
+				cosTheta = sqrtf((1.0f - Xi.y) / (1.0f + (a * a - 1.0f) * Xi.y));
+			}
+		}
+		else cosTheta = sqrtf(1.0f - Xi.y);
+		const V3 H = ToWorld(sqrtf(1.0f - cosTheta * cosTheta), cosTheta, 2.0f * kPiGlm * Xi.x, N);
 
 		if (eq0(inOutDirection))
 		{
