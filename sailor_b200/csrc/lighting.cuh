@@ -4,7 +4,8 @@
 // reference's own constants (two different pi values are in play: glm::pi<float>() and Math::Pi = 3.1415926f),
 // clamps (max(r*r,1e-3), max(NdotH,1e-4) ...) and early-outs.  The integer powers the reference writes as pow(x, 5.0f),
 // pow(x, 2.0f), pow(x, 4.0f) are evaluated by multiplication (within 2 ulp of glibc's correctly rounded pow, closer to
-// it than CUDA's powf and an order of magnitude cheaper); expf/logf/sinf/cosf are the CUDA libm ones, which differ from
+// it than CUDA's powf and an order of magnitude cheaper); the vec3 / float that ends CalculateBRDF / CalculateBTDF multiplies by
+// one reciprocal (<= 1.5 ulp, see ScaleByReciprocal); expf/logf/sinf/cosf are the CUDA libm ones, which differ from
 // glibc in the last ulp or two.  All of that is inside the converged-image tolerance and is checked per function against
 // the reference's own LightingModel by SailorPt_EvalLighting (tests: check_lighting, rtol 2e-4).
 #pragma once
@@ -18,6 +19,19 @@ namespace spt
 		V4 baseColor; V3 orm; V3 emissive; V3 normal;
 		float ior, thickness, transmission; bool opaque;
 	};
+
+	// vec3 / float at the end of CalculateBRDF / CalculateBTDF (:119,:157-158): the reference divides each component; here the
+	// reciprocal is taken once (one IEEE division) and multiplied in, <= 1.5 ulp from the component-wise quotients.  Three IEEE
+	// divisions per vector were 22 % of the hemisphere pass of FanOutKernel, a third of it in the divider's slow path, which a ZERO
+	// numerator (a base colour with zero channels) always takes; a multiplication has no slow path (profiles/r01g_SUMMARY.md).
+	SPT_HD V3 ScaleByReciprocal(V3 a, float s)
+	{
+#if defined(SPT_BSDF_EXACT_DIV)
+		return a / s;
+#else
+		return a * (1.0f / s);
+#endif
+	}
 
 	SPT_HD float DistributionGGX(V3 N, V3 H, float roughness)                 // LightingModel.cpp:28-40
 	{
@@ -58,7 +72,7 @@ namespace spt
 		const V3 kT = (1.0f - F) * transmission * (1.0f - metallic) * base;
 		if (nDotL < 0.0f || nDotV < 0.0f) return v3(0.0f);
 		const float denominator = (4.0f * std_max(nDotV, 0.0f) * std_max(nDotL, 0.0f)) + 0.001f;
-		return (kT * NDF * G) / denominator;
+		return ScaleByReciprocal(kT * NDF * G, denominator);
 	}
 
 	SPT_HD V3 CalculateBRDF(V3 V, V3 N, V3 L, const SampledData& s)           // :123-160
@@ -76,8 +90,8 @@ namespace spt
 		kD = kD * (1.0f - s.transmission);
 		if (nDotL < 0.0f || nDotV < 0.0f) return v3(0.0f);
 		const float denominator = (4.0f * std_max(nDotV, 0.0f) * std_max(nDotL, 0.0f)) + 0.001f;
-		const V3 specular = (F * NDF * G) / denominator;
-		const V3 diffuse = (kD * base) / kPiGlm;
+		const V3 specular = ScaleByReciprocal(F * NDF * G, denominator);
+		const V3 diffuse = ScaleByReciprocal(kD * base, kPiGlm);
 		return diffuse + specular;
 	}
 
