@@ -118,7 +118,7 @@ namespace spt
 	// Warp-aggregated forms: the lanes that are active at the call each reserve v (or 1) consecutive units of *p, which must
 	// be the SAME address in every lane; one atomic per warp instead of one per lane, ranges handed out in lane order.
 	// The wavefront counters (ray queue length, record arena, fan-out tables) are bumped once per activation: per-lane
-	// atomics on four addresses were what bounded ExpandKernel (profiles/r01d_SUMMARY.md).
+	// atomics on four addresses were what bounded ExpandKernel (profiles/r01g_SUMMARY.md).
 	__device__ __forceinline__ uint32_t atomic_inc_u32_agg(uint32_t* p)
 	{
 		const uint32_t mask = __activemask(), lane = threadIdx.x & 31u;

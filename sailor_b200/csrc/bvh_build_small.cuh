@@ -2,7 +2,7 @@
 //
 // A scene of a few thousand triangles (BASELINE configs C1/C2 are a 12-triangle cube) gives the multi-launch build nothing
 // to parallelise: it spends its time in ~20 launches and one host read-back per tree level (99 launches + 6 syncs, 0.5 ms,
-// for the cube — 6 % of a whole C2 frame, profiles/r01e_SUMMARY.md).  Here the same per-level functors (same code, hence
+// for the cube — 6 % of a whole C2 frame, profiles/r01g_SUMMARY.md).  Here the same per-level functors (same code, hence
 // the same bits: BoundsKernel, PrepareKernel, BinKernel, SplitKernel, FlagKernel, CountKernel, AllocKernel, HoleKernel,
 // ScatterKernel, then Subtree / Renumber / LeafCount / Emit and the traversal-layout pack) are called from a single CTA
 // with __syncthreads() between the phases; the level loop, the two prefix sums per level and the final renumbering run

@@ -159,7 +159,7 @@ namespace spt
 	{
 		uint64_t budget = 40960ull << 20;
 		// cudaMemGetInfo goes through the driver's resource-manager lock and was seen to block for tens of milliseconds on a busy
-		// box (profiles/r01e_SUMMARY.md): ask at most once every few seconds
+		// box (profiles/r01g_SUMMARY.md): ask at most once every few seconds
 		static uint64_t cachedFree = 0; static double cachedAt = -1e30;
 		const double now = HostNow();
 		if (now - cachedAt > 5.0) { cachedFree = (uint64_t)DevMemAvailable() + held; cachedAt = now; }

@@ -418,7 +418,7 @@ namespace spt
 		}
 	}
 
-	// Two other forms of the small-scene kernel were measured on C2 and rejected (profiles/r01f_SUMMARY.md): the persistent
+	// Two other forms of the small-scene kernel were measured on C2 and rejected (profiles/r01g_SUMMARY.md): the persistent
 	// vote / refill warp loop reading shared memory (3.54 ms against 2.52 ms: with walks of a few steps the bookkeeping costs
 	// more than the idle lanes it removes) and a two-phase form that retires root-miss rays first and compacts the survivors
 	// (2.67 ms: 70 % of a first-hit level's rays point INTO a convex object and cross it, so there is little to compact).
