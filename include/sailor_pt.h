@@ -206,6 +206,11 @@ SAILOR_PT_API int32_t SailorPt_RenderProgressive(SailorPtScene* scene, const Sai
 SAILOR_PT_API int32_t SailorPt_PinHostBuffer(void* hostBuffer, uint64_t bytes);
 SAILOR_PT_API int32_t SailorPt_UnpinHostBuffer(void* hostBuffer);
 
+/* Product: release the working memory the library keeps between frames (the wavefront arenas shared by every scene of the
+ * process on the current device, up to 40 GiB, and the cached blocks of the stream-ordered pool).  Scenes stay valid; the next
+ * frame allocates its working set again.  The oracle has nothing to release and returns SAILOR_PT_OK. */
+SAILOR_PT_API int32_t SailorPt_TrimMemory(void);
+
 /* Output stage alone (PathTracer.cpp:535-565 + Core/Utils.cpp:48-57). */
 SAILOR_PT_API int32_t SailorPt_OutputStage(uint32_t width, uint32_t height, const float* linearRGB, uint8_t* srgb8);
 

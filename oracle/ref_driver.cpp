@@ -629,6 +629,7 @@ int32_t SailorPt_SetDevice(int32_t device) { return device == 0 ? SAILOR_PT_OK :
 int32_t SailorPt_WriteImage(const char*, uint32_t, uint32_t, const float*) { return SAILOR_PT_ERR_UNSUPPORTED; }
 int32_t SailorPt_CompareImages(uint32_t, uint32_t, const float*, const float*, double*) { return SAILOR_PT_ERR_UNSUPPORTED; }
 int32_t SailorPt_RenderProgressive(SailorPtScene*, const SailorPtParams*, uint32_t, uint32_t, const char*, uint32_t, float*, uint8_t*, uint32_t*) { return SAILOR_PT_ERR_UNSUPPORTED; }
+int32_t SailorPt_TrimMemory(void) { return SAILOR_PT_OK; }
 int32_t SailorPt_PinHostBuffer(void* hostBuffer, uint64_t bytes) { return (hostBuffer && bytes) ? SAILOR_PT_OK : SAILOR_PT_ERR_ARG; }   // host memory is the oracle's own memory
 int32_t SailorPt_UnpinHostBuffer(void* hostBuffer) { return hostBuffer ? SAILOR_PT_OK : SAILOR_PT_ERR_ARG; }
 const char* SailorPt_LastError(void) { return t_lastError.c_str(); }

@@ -57,6 +57,7 @@ SYMBOLS = [
     "SailorPt_OutputStage", "SailorPt_SampleTexture", "SailorPt_EvalLighting", "SailorPt_GetStats",
     "SailorPt_LastError", "SailorPt_Backend", "SailorPt_RenderResident", "SailorPt_ReadResident", "SailorPt_CopyResidentToDevice", "SailorPt_SetDevice", "SailorPt_OutputStageResident",
     "SailorPt_PinHostBuffer", "SailorPt_UnpinHostBuffer", "SailorPt_WriteImage", "SailorPt_CompareImages", "SailorPt_RenderProgressive",
+    "SailorPt_TrimMemory",
 ]
 
 
@@ -177,6 +178,10 @@ class Library:
         m = (C.c_double * 4)()
         self.check(self.lib.SailorPt_CompareImages(a.shape[1], a.shape[0], _ptr(a, C.c_float), _ptr(b, C.c_float), m), "SailorPt_CompareImages")
         return dict(mean_rel_error=m[0], rmse=m[1], max_abs=m[2], psnr_db=m[3])
+
+    def trim_memory(self):
+        """SailorPt_TrimMemory: hand the working memory kept between frames back to the device."""
+        self.check(self.lib.SailorPt_TrimMemory(), "SailorPt_TrimMemory")
 
     def pin_host_buffer(self, array):
         """Page-lock a numpy array the caller reuses for results (SailorPt_PinHostBuffer); unpin before dropping it."""

@@ -132,6 +132,12 @@ namespace spt
 		return p;
 	}
 	int DevCurrent() { int d = 0; if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); d = 0; } return d; }
+	void TrimDevicePool()
+	{
+		int dev = 0; cudaMemPool_t pool = nullptr;
+		if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) { cudaDeviceSynchronize(); cudaMemPoolTrimTo(pool, 0); }
+		cudaGetLastError();
+	}
 	void* DevAllocPlain(Ctx& ctx, size_t bytes)
 	{
 		void* p = nullptr;
@@ -473,6 +479,7 @@ namespace spt
 	void DevFreeBytes(void* p) { free(p); }
 	size_t DevMemAvailable() { return (size_t)4 << 30; }
 	int DevCurrent() { return 0; }
+	void TrimDevicePool() {}
 	void* DevAllocPlain(Ctx&, size_t bytes) { return malloc(bytes ? bytes : 1); }
 	void DevFreePlain(void* p) { free(p); }
 	void DevUpload(Ctx& ctx, void* dst, const void* src, size_t bytes) { ctx.h2dBytes += bytes; memcpy(dst, src, bytes); }

@@ -63,6 +63,7 @@ namespace spt
 
 	void* DevAllocBytes(Ctx& ctx, size_t bytes);
 	int DevCurrent();                  // index of the current CUDA device (emu: 0)
+	void TrimDevicePool();             // hand the stream-ordered pool's cached memory back to the driver (emu: no-op)
 	// allocations that outlive the context (stream) they were made from: plain cudaMalloc / cudaFree, not stream-ordered
 	void* DevAllocPlain(Ctx& ctx, size_t bytes);
 	void DevFreePlain(void* p);

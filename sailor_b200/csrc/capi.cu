@@ -77,6 +77,14 @@ int32_t SailorPt_SetDevice(int32_t device)
 	return SAILOR_PT_OK;
 #endif
 }
+int32_t SailorPt_TrimMemory(void)
+{
+	ScopedCtx sc;
+	if (sc.rc != SAILOR_PT_OK) return SetError(sc.rc, sc.ctx.error);
+	ReleaseSharedArenas(sc.ctx);
+	TrimDevicePool();
+	return sc.ctx.ok ? SAILOR_PT_OK : SetError(SAILOR_PT_ERR_CUDA, sc.ctx.error);
+}
 int32_t SailorPt_PinHostBuffer(void* hostBuffer, uint64_t bytes)
 {
 	if (!hostBuffer || !bytes) return SetError(SAILOR_PT_ERR_ARG, "null buffer");

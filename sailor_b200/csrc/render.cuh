@@ -212,6 +212,15 @@ namespace spt
 		return *p;
 	}
 
+	// Give the shared working set of the current device back (SailorPt_TrimMemory): the next frame allocates it again.
+	inline void ReleaseSharedArenas(Ctx& ctx)
+	{
+		SharedArenas& arenas = ArenasOfCurrentDevice();
+		std::lock_guard<std::mutex> frameLock(arenas.frame);
+		ctx.Sync();
+		for (PlainBuf& b : arenas.mem) { if (b.p) DevFreePlain(b.p); b.p = nullptr; b.n = 0; }
+	}
+
 	inline bool SceneHasThickTransmission(const HostScene& h)
 	{
 		for (const auto& m : h.materials) if (m.transmission > 0.0f && m.thickness > 0.0f) return true;

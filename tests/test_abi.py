@@ -84,6 +84,10 @@ def test_parse_command_line_args_matches_the_reference(which, request):
     assert p.m_pathToModel == "my scene.glb"
 
 
+def test_trim_memory_is_a_no_op_for_the_checkers(emu, oracle):
+    emu.trim_memory(); oracle.trim_memory()
+
+
 def test_cpp_host_builds_and_fails_loudly_without_a_cuda_device(scene_dir):
     """sailor_b200/sailor_pt (csrc/cli_main.cpp): the C++ caller the reference lacks, linked against the C-ABI only."""
     import subprocess

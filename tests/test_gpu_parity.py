@@ -199,3 +199,15 @@ def test_cpp_host_renders_like_the_library(gpu, scene_dir, tmp_path):
     with gpu.load_scene(scene) as s:
         lin, _ = s.render(p)
     assert np.array_equal(pc.bits(pc.read_pfm(pfm)), pc.bits(lin))
+
+
+def test_trim_memory_releases_the_working_set_and_rendering_goes_on(gpu, scene_dir):
+    import torch
+    p = Params(height=120, num_samples=4, num_ambient_samples=4, max_bounces=2, msaa=2, ambient=(1, 1, 1), seed=6)
+    with gpu.load_scene(_scene(scene_dir, "cube", {})) as s:
+        a, _ = s.render(p)
+        free_before = torch.cuda.mem_get_info()[0]
+        gpu.trim_memory()
+        assert torch.cuda.mem_get_info()[0] >= free_before
+        b, _ = s.render(p)                       # the scene is still valid; the arenas come back
+        assert np.array_equal(a, b)

@@ -13,6 +13,7 @@ p = bench.make_params(w, seed=1)
 sc = [L.load_scene(path) for L in libs]
 keys = ("secondsFlatten", "secondsTraverse", "secondsExpand", "secondsFanOut", "secondsClassify", "secondsGather")
 acc = [[] for _ in libs]
+# two copies of the library = two sets of shared arenas (40 GiB each on a 180 GB device: both get the full budget)
 for rep in range(3 + 12):
     for i, (L, s) in enumerate(zip(libs, sc)):
         s.render_resident(p, rebuild_bvh=True, output_stage=True)

@@ -24,6 +24,13 @@ VARIANTS = {
     "stack16": ["SPT_SMEM_STACK=16"],
     "block64": ["SPT_TRACE_BLOCK=64"],
     "block256": ["SPT_TRACE_BLOCK=256"],
+    "ib2": ["SPT_VOTE_INNER_BIAS=2"],
+    "lb2": ["SPT_VOTE_LEAF_BIAS=2"],
+    "reps41": ["SPT_INNER_REPS=4", "SPT_LEAF_REPS=1"],
+    "reps43": ["SPT_INNER_REPS=4", "SPT_LEAF_REPS=3"],
+    "reps32": ["SPT_INNER_REPS=3", "SPT_LEAF_REPS=2"],
+    "reps82": ["SPT_INNER_REPS=8", "SPT_LEAF_REPS=2"],
+    "idle24": ["SPT_FETCH_MIN_IDLE=24"],
     "fan4": ["SPT_FAN_MIN_BLOCKS=4"],
     "fan2": ["SPT_FAN_MIN_BLOCKS=2"],
 }
@@ -73,5 +80,6 @@ else:
             v = list(buf)
             row["stats"] = dict(votes=v[0], idle_per_vote=v[1] / v[0], leaf_per_vote=v[2] / v[0], inner_per_vote=v[3] / v[0], inner_reps=v[4], lanes_per_inner_rep=v[5] / max(v[4], 1),
                                 leaf_reps=v[6], lanes_per_leaf_rep=v[7] / max(v[6], 1), refills=v[8], lanes_per_refill=v[9] / max(v[8], 1))
+        L.trim_memory()          # every loaded copy of the library owns its own shared arenas: give them back before the next variant
         res[f] = row
         print(f, json.dumps(row), flush=True)
