@@ -30,6 +30,11 @@ namespace spt
 
 #if !defined(SPT_EMU)
 	// ------------------------------------------------------------------------------------------------ CUDA
+	namespace
+	{
+		std::mutex g_pinnedPoolMutex;
+		std::vector<uint32_t*> g_pinnedPool;
+	}
 	int Ctx::Init()
 	{
 		int count = 0;
@@ -53,7 +58,12 @@ namespace spt
 	}
 	void Ctx::Destroy()
 	{
-		if (pinned) { cudaFreeHost(pinned); pinned = nullptr; }
+		if (pinned)
+		{
+			std::lock_guard<std::mutex> lock(g_pinnedPoolMutex);
+			if (g_pinnedPool.size() < 64) g_pinnedPool.push_back(pinned); else cudaFreeHost(pinned);
+			pinned = nullptr;
+		}
 		if (evA) cudaEventDestroy(evA);
 		if (evB) cudaEventDestroy(evB);
 		for (int i = 0; i < kMarkers; i++) { if (ev[i]) cudaEventDestroy(ev[i]); ev[i] = nullptr; }
@@ -79,9 +89,18 @@ namespace spt
 		if (ok) SPT_CUDA_CHECK(*this, cudaEventRecord(ev[i], stream));
 	}
 	void Ctx::WaitMark(int i) { if (ok) SPT_CUDA_CHECK(*this, cudaEventSynchronize(ev[i])); }
+	// The pinned scratch block is recycled through a process-wide free list: cudaHostAlloc / cudaFreeHost cost about a millisecond
+	// each (page locking + an implicit device synchronisation), which a scene object per frame would pay every frame.
 	uint32_t* Ctx::Pinned()
 	{
-		if (!pinned && ok) { void* p = nullptr; SPT_CUDA_CHECK(*this, cudaHostAlloc(&p, 256 * sizeof(uint32_t), cudaHostAllocDefault)); pinned = (uint32_t*)p; }
+		if (!pinned && ok)
+		{
+			{
+				std::lock_guard<std::mutex> lock(g_pinnedPoolMutex);
+				if (!g_pinnedPool.empty()) { pinned = g_pinnedPool.back(); g_pinnedPool.pop_back(); }
+			}
+			if (!pinned) { void* p = nullptr; SPT_CUDA_CHECK(*this, cudaHostAlloc(&p, 256 * sizeof(uint32_t), cudaHostAllocPortable)); pinned = (uint32_t*)p; }
+		}
 		return pinned;
 	}
 	void Ctx::ReadAsync(uint32_t* pinnedDst, const void* src, size_t bytes)
