@@ -67,10 +67,12 @@ namespace spt
 			numTris = (uint32_t)host.numTriangles;
 			counter.Alloc(ctx, 16);
 			if (numTris == 0) return CudaStatus();
-			// concatenate the primitive streams
+			// The primitive streams go to the device piece by piece, straight from the importer's vectors (no host-side concatenation:
+			// at 10 M triangles that was hundreds of MB of extra copies).  A stream a primitive lacks is never read (FlattenKernel
+			// looks at PrimDesc::has*), so its part of the device buffer stays uninitialised.
 			std::vector<PrimDesc> descs(host.prims.size());
-			std::vector<float> pos, nrm, uv0, uv1, tan; std::vector<uint32_t> idx;
-			uint32_t triStart = 0, vtxOffset = 0;
+			uint32_t triStart = 0, vtxOffset = 0, idxOffset = 0;
+			bool anyNrm = false, anyUv0 = false, anyUv1 = false, anyTan = false;
 			for (size_t i = 0; i < host.prims.size(); i++)
 			{
 				const HostPrimitive& hp = host.prims[i];
@@ -79,23 +81,57 @@ namespace spt
 				memcpy(d.world, hp.world, sizeof(d.world));
 				const uint32_t nv = (uint32_t)(hp.pos.size() / 3);
 				d.triStart = triStart; d.triCount = (uint32_t)(hp.idx.size() / 3);
-				d.vtxOffset = vtxOffset; d.idxOffset = (uint32_t)idx.size();
+				d.vtxOffset = vtxOffset; d.idxOffset = idxOffset;
 				d.hasNrm = !hp.nrm.empty(); d.hasUv0 = !hp.uv0.empty(); d.hasUv1 = !hp.uv1.empty(); d.hasTan = !hp.tan.empty();
+				anyNrm |= d.hasNrm != 0; anyUv0 |= d.hasUv0 != 0; anyUv1 |= d.hasUv1 != 0; anyTan |= d.hasTan != 0;
 				d.material = hp.material;
-				pos.insert(pos.end(), hp.pos.begin(), hp.pos.end());
-				nrm.resize((size_t)(vtxOffset + nv) * 3, 0.0f); if (d.hasNrm) memcpy(nrm.data() + (size_t)vtxOffset * 3, hp.nrm.data(), hp.nrm.size() * 4);
-				uv0.resize((size_t)(vtxOffset + nv) * 2, 0.0f); if (d.hasUv0) memcpy(uv0.data() + (size_t)vtxOffset * 2, hp.uv0.data(), hp.uv0.size() * 4);
-				uv1.resize((size_t)(vtxOffset + nv) * 2, 0.0f); if (d.hasUv1) memcpy(uv1.data() + (size_t)vtxOffset * 2, hp.uv1.data(), hp.uv1.size() * 4);
-				tan.resize((size_t)(vtxOffset + nv) * 4, 0.0f); if (d.hasTan) memcpy(tan.data() + (size_t)vtxOffset * 4, hp.tan.data(), hp.tan.size() * 4);
-				idx.insert(idx.end(), hp.idx.begin(), hp.idx.end());
-				triStart += d.triCount; vtxOffset += nv;
+				triStart += d.triCount; vtxOffset += nv; idxOffset += (uint32_t)hp.idx.size();
 			}
 			// empty primitives would break the binary search in FlattenKernel: drop them
 			std::vector<PrimDesc> live;
 			for (const auto& d : descs) if (d.triCount) live.push_back(d);
 
 			DevBuf<PrimDesc> dPrims; DevBuf<float> dPos, dNrm, dUv0, dUv1, dTan; DevBuf<uint32_t> dIdx;
-			dPrims.Upload(ctx, live); dPos.Upload(ctx, pos); dNrm.Upload(ctx, nrm); dUv0.Upload(ctx, uv0); dUv1.Upload(ctx, uv1); dTan.Upload(ctx, tan); dIdx.Upload(ctx, idx);
+			dPrims.Upload(ctx, live);
+			dPos.Alloc(ctx, (size_t)vtxOffset * 3 + 1); dIdx.Alloc(ctx, (size_t)idxOffset + 1);
+			dNrm.Alloc(ctx, anyNrm ? (size_t)vtxOffset * 3 : 1); dUv0.Alloc(ctx, anyUv0 ? (size_t)vtxOffset * 2 : 1);
+			dUv1.Alloc(ctx, anyUv1 ? (size_t)vtxOffset * 2 : 1); dTan.Alloc(ctx, anyTan ? (size_t)vtxOffset * 4 : 1);
+			if (!ctx.ok) return CudaStatus();
+			if (host.prims.size() > 32)
+			{
+				// many small primitives: one copy per stream from a host-side concatenation beats thousands of tiny transfers
+				std::vector<float> pos((size_t)vtxOffset * 3), nrm(anyNrm ? (size_t)vtxOffset * 3 : 0), uv0(anyUv0 ? (size_t)vtxOffset * 2 : 0), uv1(anyUv1 ? (size_t)vtxOffset * 2 : 0), tan(anyTan ? (size_t)vtxOffset * 4 : 0);
+				std::vector<uint32_t> idx(idxOffset);
+				for (size_t i = 0; i < host.prims.size(); i++)
+				{
+					const HostPrimitive& hp = host.prims[i];
+					const PrimDesc& d = descs[i];
+					if (!hp.pos.empty()) memcpy(pos.data() + (size_t)d.vtxOffset * 3, hp.pos.data(), hp.pos.size() * sizeof(float));
+					if (!hp.idx.empty()) memcpy(idx.data() + d.idxOffset, hp.idx.data(), hp.idx.size() * sizeof(uint32_t));
+					if (d.hasNrm) memcpy(nrm.data() + (size_t)d.vtxOffset * 3, hp.nrm.data(), hp.nrm.size() * sizeof(float));
+					if (d.hasUv0) memcpy(uv0.data() + (size_t)d.vtxOffset * 2, hp.uv0.data(), hp.uv0.size() * sizeof(float));
+					if (d.hasUv1) memcpy(uv1.data() + (size_t)d.vtxOffset * 2, hp.uv1.data(), hp.uv1.size() * sizeof(float));
+					if (d.hasTan) memcpy(tan.data() + (size_t)d.vtxOffset * 4, hp.tan.data(), hp.tan.size() * sizeof(float));
+				}
+				if (!pos.empty()) DevUpload(ctx, dPos.p, pos.data(), pos.size() * sizeof(float));
+				if (!idx.empty()) DevUpload(ctx, dIdx.p, idx.data(), idx.size() * sizeof(uint32_t));
+				if (!nrm.empty()) DevUpload(ctx, dNrm.p, nrm.data(), nrm.size() * sizeof(float));
+				if (!uv0.empty()) DevUpload(ctx, dUv0.p, uv0.data(), uv0.size() * sizeof(float));
+				if (!uv1.empty()) DevUpload(ctx, dUv1.p, uv1.data(), uv1.size() * sizeof(float));
+				if (!tan.empty()) DevUpload(ctx, dTan.p, tan.data(), tan.size() * sizeof(float));
+				ctx.Sync();                                   // the staging vectors die at the end of this block
+			}
+			else for (size_t i = 0; i < host.prims.size(); i++)
+			{
+				const HostPrimitive& hp = host.prims[i];
+				const PrimDesc& d = descs[i];
+				if (!hp.pos.empty()) DevUpload(ctx, dPos.p + (size_t)d.vtxOffset * 3, hp.pos.data(), hp.pos.size() * sizeof(float));
+				if (!hp.idx.empty()) DevUpload(ctx, dIdx.p + d.idxOffset, hp.idx.data(), hp.idx.size() * sizeof(uint32_t));
+				if (d.hasNrm) DevUpload(ctx, dNrm.p + (size_t)d.vtxOffset * 3, hp.nrm.data(), hp.nrm.size() * sizeof(float));
+				if (d.hasUv0) DevUpload(ctx, dUv0.p + (size_t)d.vtxOffset * 2, hp.uv0.data(), hp.uv0.size() * sizeof(float));
+				if (d.hasUv1) DevUpload(ctx, dUv1.p + (size_t)d.vtxOffset * 2, hp.uv1.data(), hp.uv1.size() * sizeof(float));
+				if (d.hasTan) DevUpload(ctx, dTan.p + (size_t)d.vtxOffset * 4, hp.tan.data(), hp.tan.size() * sizeof(float));
+			}
 			vtx.Alloc(ctx, (size_t)numTris * 3); centroid.Alloc(ctx, numTris); shade.Alloc(ctx, (size_t)numTris * 9); uv2.Alloc(ctx, (size_t)numTris * 3);
 			if (!ctx.ok) return CudaStatus();
 
