@@ -684,8 +684,9 @@ namespace spt
 			if (!spawned) val = glm_clamp(T * v3(0.0f), 0.0f, 10.0f);
 			x.a0 = val.x; x.a1 = val.y; x.a2 = val.z; x.b0 = 0.0f; x.b1 = 0.0f; x.b2 = 0.0f; x.tag |= kRsHit;
 			a.aux[g] = x;
-			// :822-832 sky behind a thick transmissive surface, independent of the child
-			if (!(oflags & kNfThick))
+			// :822-832 sky behind a thick transmissive surface, independent of the child.  Without such a material in the scene (hasSky)
+			// the test cannot pass, and the two dependent scattered loads it needs (triangle -> material) are skipped.
+			if (a.hasSky && !(oflags & kNfThick))
 			{
 				const MaterialGpu& hm = a.materials[MaterialOfTri(a, h.tri)];
 				if (hm.transmission > 0.0f && hm.thickness > 0.0f && pMaxBounces > 0)
