@@ -100,3 +100,21 @@ def test_cpp_host_builds_and_fails_loudly_without_a_cuda_device(scene_dir):
     if not torch.cuda.is_available():
         r = subprocess.run([exe, "--in", scenes.ensure(scene_dir, "cube"), "--out", os.path.join(scene_dir, "cli.png")], capture_output=True, text=True)
         assert r.returncode == -ERR_NO_DEVICE and "no CPU path" in r.stderr
+
+
+def test_header_is_plain_c_and_a_c_program_links_against_the_library(tmp_path):
+    """The boundary is a C ABI: include/sailor_pt.h compiles as C99, and a C program (no C++ runtime of its own) links and calls it."""
+    from sailor_b200 import build as product_build
+    lib = product_build.build()
+    src = tmp_path / "host.c"
+    src.write_text('#include "sailor_pt.h"\n#include <stdio.h>\n#include <string.h>\n'
+                   'int main(void) { SailorPtParams p; memset(&p, 0, sizeof p); const char* a[] = {"exe", "--samples", "64", "--bounces", "3"};\n'
+                   '  if (SailorPt_ParseCommandLineArgs(&p, a, 5) != SAILOR_PT_OK) return 2;\n'
+                   '  printf("%s %u %u %u\\n", SailorPt_Backend(), p.msaa, p.numSamples, p.maxBounces); return SailorPt_Run(0) == SAILOR_PT_ERR_ARG ? 0 : 3; }\n')
+    exe = tmp_path / "host"
+    inc = os.path.join(ROOT, "include")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", inc, str(src), "-o", str(exe), "-L", os.path.dirname(lib), "-lsailor_pt_cuda",
+                        "-Wl,-rpath," + os.path.dirname(lib)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.split() == ["cuda", "sm_100a", "8", "8", "3"], (r.returncode, r.stdout, r.stderr)
