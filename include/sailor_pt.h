@@ -59,7 +59,12 @@ typedef struct SailorPtParams {
 	uint64_t seed;                /* RNG stream key; the reference uses unseeded rand() */
 	uint32_t rowBegin, rowEnd;    /* render only image rows [rowBegin,rowEnd) of the task grid (multi-GPU shard); 0,0 = all */
 	uint32_t msaaBegin, msaaEnd;  /* render only primary-sample indices [msaaBegin,msaaEnd); 0,0 = all */
+	int32_t deviceCount;          /* SailorPt_Run / SailorPt_RenderMulti: CUDA devices to spread the frame over; 0 or 1 = the current device only */
+	uint32_t flags;               /* SAILOR_PT_FLAG_*; 0 = default */
 } SailorPtParams;
+
+/* SailorPtParams::flags */
+#define SAILOR_PT_FLAG_EXACT_TRAVERSAL 1u  /* trace every ray with the reference-visit-order kernel (binary tree); default: secondary rays walk the wide layout, ambiguous ones are replayed exactly */
 
 typedef struct SailorPtScene SailorPtScene; /* opaque */
 
@@ -89,7 +94,7 @@ typedef struct SailorPtStats {
 	uint64_t boxTests;        /* oracle (counting build) only: IntersectRayAABB calls */
 	uint64_t triTests;        /* oracle (counting build) only: IntersectRayTriangle calls */
 	double secondsTotal;      /* wall time of the last call (host clock) */
-	double secondsFlatten;    /* SceneLoad: flatten kernel. RenderResident: the whole call between two CUDA events on the launch stream */
+	double secondsFlatten;    /* SceneLoad: flatten kernel */
 	double secondsBvhBuild;
 	double secondsTraverse;   /* product: sum of traversal-kernel launches (CUDA events on the launch stream) */
 	double secondsShade;
@@ -106,6 +111,8 @@ typedef struct SailorPtStats {
 	double secondsClassify;   /* ClassifyKernel + TraceSky continuation kernels */
 	double secondsGather;     /* GatherKernel + resolve */
 	uint64_t fanOutSamples;   /* rays emitted by FanOutKernel */
+	double secondsCall;       /* product, RenderResident: the whole call between two CUDA events on the launch stream (BVH build + render + output stage) */
+	uint64_t replayedRays;    /* product: rays of the last call that the wide-layout walk handed to the exact (reference visit order) kernel */
 } SailorPtStats;
 
 /* ---- the reference entry points (PathTracer.h:34-36) ---- */
@@ -152,6 +159,15 @@ SAILOR_PT_API int32_t SailorPt_GetCamera(const SailorPtScene* scene, const Sailo
 /* BVH::IntersectBVH (BVH.cpp:122-191) for `count` rays: origin/dir 3 floats each, ignoreTri may be NULL. */
 SAILOR_PT_API int32_t SailorPt_IntersectRays(SailorPtScene* scene, uint32_t count, const float* origins,
 	const float* directions, const uint32_t* ignoreTri, SailorPtHit* hits);
+
+/* The same query through the traversal variants the integrator uses for secondary rays.  flags: SAILOR_PT_RAYS_WIDE = walk the
+ * wide layout and replay ambiguous rays exactly (results equal SailorPt_IntersectRays); SAILOR_PT_RAYS_ANY_HIT = hit-or-miss
+ * query: hits[i].triId != 0xFFFFFFFF iff BVH::IntersectBVH would return true (t, u, v, triId are those of SOME reachable hit,
+ * not necessarily the closest).  The oracle ignores SAILOR_PT_RAYS_WIDE and answers ANY_HIT with its closest hit. */
+#define SAILOR_PT_RAYS_WIDE 1u
+#define SAILOR_PT_RAYS_ANY_HIT 2u
+SAILOR_PT_API int32_t SailorPt_IntersectRaysEx(SailorPtScene* scene, uint32_t count, const float* origins,
+	const float* directions, const uint32_t* ignoreTri, uint32_t flags, SailorPtHit* hits);
 
 /* Primary ray of sample 0 (offset .5,.5; PathTracer.cpp:458-466) for every pixel, in task order
  * (index = y*width + x with y the task row, i.e. before the row flip of :449). */

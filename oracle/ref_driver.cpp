@@ -776,6 +776,12 @@ int32_t SailorPt_IntersectRays(SailorPtScene* s, uint32_t count, const float* o,
 	return SAILOR_PT_OK;
 }
 
+int32_t SailorPt_IntersectRaysEx(SailorPtScene* s, uint32_t count, const float* o, const float* d, const uint32_t* ignore, uint32_t, SailorPtHit* hits)
+{
+	// the reference has one traversal (closest hit, BVH.cpp:122-191): a hit-or-miss query is "did it return true"
+	return SailorPt_IntersectRays(s, count, o, d, ignore, hits);
+}
+
 int32_t SailorPt_PrimaryHits(SailorPtScene* s, const SailorPtParams* p, SailorPtHit* hits)
 {
 	if (!s || !p || !hits) return SAILOR_PT_ERR_ARG;

@@ -18,6 +18,8 @@ MATERIAL_WORDS = 32
 TRI_FLOATS = 51
 
 OK = 0
+FLAG_EXACT_TRAVERSAL = 1
+RAYS_WIDE, RAYS_ANY_HIT = 1, 2
 ERR_ARG, ERR_IO, ERR_FORMAT, ERR_NO_DEVICE, ERR_CUDA, ERR_LIMIT, ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6, -7
 
 
@@ -28,6 +30,7 @@ class SailorPtParams(C.Structure):
         ("maxBounces", C.c_uint32), ("msaa", C.c_uint32), ("ambient", C.c_float * 3),
         ("widthOverride", C.c_uint32), ("seed", C.c_uint64),
         ("rowBegin", C.c_uint32), ("rowEnd", C.c_uint32), ("msaaBegin", C.c_uint32), ("msaaEnd", C.c_uint32),
+        ("deviceCount", C.c_int32), ("flags", C.c_uint32),
     ]
 
 
@@ -39,7 +42,7 @@ class SailorPtStats(C.Structure):
         ("traverseLaunches", C.c_uint32), ("kernelLaunches", C.c_uint32), ("threads", C.c_uint32),
         ("batches", C.c_uint32), ("h2dBytes", C.c_uint64), ("d2hBytes", C.c_uint64),
         ("secondsExpand", C.c_double), ("secondsFanOut", C.c_double), ("secondsClassify", C.c_double), ("secondsGather", C.c_double),
-        ("fanOutSamples", C.c_uint64),
+        ("fanOutSamples", C.c_uint64), ("secondsCall", C.c_double), ("replayedRays", C.c_uint64),
     ]
 
     def as_dict(self):
@@ -57,7 +60,7 @@ SYMBOLS = [
     "SailorPt_OutputStage", "SailorPt_SampleTexture", "SailorPt_EvalLighting", "SailorPt_GetStats",
     "SailorPt_LastError", "SailorPt_Backend", "SailorPt_RenderResident", "SailorPt_ReadResident", "SailorPt_CopyResidentToDevice", "SailorPt_SetDevice", "SailorPt_OutputStageResident",
     "SailorPt_PinHostBuffer", "SailorPt_UnpinHostBuffer", "SailorPt_WriteImage", "SailorPt_CompareImages", "SailorPt_RenderProgressive",
-    "SailorPt_TrimMemory",
+    "SailorPt_TrimMemory", "SailorPt_IntersectRaysEx",
 ]
 
 
@@ -76,7 +79,7 @@ class Params:
 
     def __init__(self, path_to_model="", output="", camera="", height=512, num_samples=1, num_ambient_samples=1,
                  max_bounces=4, msaa=1, ambient=(0.0, 0.0, 0.0), width_override=0, seed=0,
-                 rows=(0, 0), msaa_range=(0, 0)):
+                 rows=(0, 0), msaa_range=(0, 0), device_count=0, flags=0):
         self.m_pathToModel = path_to_model
         self.m_output = output
         self.m_camera = camera
@@ -90,6 +93,8 @@ class Params:
         self.seed = seed
         self.rows = tuple(rows)
         self.msaa_range = tuple(msaa_range)
+        self.device_count = device_count
+        self.flags = flags
 
     def to_c(self):
         p = SailorPtParams()
@@ -101,6 +106,7 @@ class Params:
         p.widthOverride, p.seed = self.width_override, self.seed
         p.rowBegin, p.rowEnd = self.rows
         p.msaaBegin, p.msaaEnd = self.msaa_range
+        p.deviceCount, p.flags = self.device_count, self.flags
         return p
 
     @staticmethod
@@ -132,6 +138,7 @@ class Library:
         lib.SailorPt_GetBVH.argtypes = [C.c_void_p, C.c_void_p, P(C.c_uint32)]
         lib.SailorPt_GetCamera.argtypes = [C.c_void_p, P(SailorPtParams), P(C.c_uint32), P(C.c_uint32), P(C.c_float)]
         lib.SailorPt_IntersectRays.argtypes = [C.c_void_p, C.c_uint32, P(C.c_float), P(C.c_float), P(C.c_uint32), C.c_void_p]
+        lib.SailorPt_IntersectRaysEx.argtypes = [C.c_void_p, C.c_uint32, P(C.c_float), P(C.c_float), P(C.c_uint32), C.c_uint32, C.c_void_p]
         lib.SailorPt_PrimaryHits.argtypes = [C.c_void_p, P(SailorPtParams), C.c_void_p]
         lib.SailorPt_Render.argtypes = [C.c_void_p, P(SailorPtParams), P(C.c_float), P(C.c_uint8)]
         lib.SailorPt_RenderResident.argtypes = [C.c_void_p, P(SailorPtParams), C.c_uint32]
@@ -300,14 +307,20 @@ class Scene:
         self.L.check(self.L.lib.SailorPt_GetCamera(self.h, C.byref(cp), C.byref(w), C.byref(h), cam), "SailorPt_GetCamera")
         return w.value, h.value, np.array(list(cam), np.float32)
 
-    def intersect_rays(self, origins, directions, ignore=None):
+    def intersect_rays(self, origins, directions, ignore=None, wide=False, any_hit=False):
+        """BVH::IntersectBVH for a batch of rays.  wide / any_hit: SailorPt_IntersectRaysEx (the traversal variants the integrator
+        uses for secondary rays)."""
         o = np.ascontiguousarray(origins, dtype=np.float32)
         d = np.ascontiguousarray(directions, dtype=np.float32)
         n = o.shape[0]
         ig = np.ascontiguousarray(ignore, dtype=np.uint32) if ignore is not None else None
         hits = np.empty(n, HIT_DTYPE)
-        self.L.check(self.L.lib.SailorPt_IntersectRays(self.h, n, _ptr(o, C.c_float), _ptr(d, C.c_float),
-                                                      _ptr(ig, C.c_uint32), hits.ctypes.data), "SailorPt_IntersectRays")
+        if wide or any_hit:
+            self.L.check(self.L.lib.SailorPt_IntersectRaysEx(self.h, n, _ptr(o, C.c_float), _ptr(d, C.c_float), _ptr(ig, C.c_uint32),
+                                                            (RAYS_WIDE if wide else 0) | (RAYS_ANY_HIT if any_hit else 0), hits.ctypes.data), "SailorPt_IntersectRaysEx")
+        else:
+            self.L.check(self.L.lib.SailorPt_IntersectRays(self.h, n, _ptr(o, C.c_float), _ptr(d, C.c_float),
+                                                          _ptr(ig, C.c_uint32), hits.ctypes.data), "SailorPt_IntersectRays")
         return hits
 
     def primary_hits(self, params: Params):
@@ -355,6 +368,10 @@ class Scene:
         srgb = np.empty((h, w, 3), np.uint8) if want_srgb else None
         self.L.check(self.L.lib.SailorPt_ReadResident(self.h, _ptr(lin, C.c_float), _ptr(srgb, C.c_uint8)), "SailorPt_ReadResident")
         return lin, srgb
+
+    def read_resident_into(self, lin, srgb=None):
+        """SailorPt_ReadResident into caller-owned (possibly page-locked) host buffers."""
+        self.L.check(self.L.lib.SailorPt_ReadResident(self.h, _ptr(lin, C.c_float), _ptr(srgb, C.c_uint8)), "SailorPt_ReadResident")
 
     def copy_resident_to_device(self, device_ptr, nbytes):
         self.L.check(self.L.lib.SailorPt_CopyResidentToDevice(self.h, C.c_void_p(device_ptr), nbytes), "SailorPt_CopyResidentToDevice")

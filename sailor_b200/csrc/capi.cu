@@ -272,6 +272,11 @@ int32_t SailorPt_GetCamera(const SailorPtScene* s, const SailorPtParams* p, uint
 
 int32_t SailorPt_IntersectRays(SailorPtScene* s, uint32_t count, const float* o, const float* d, const uint32_t* ignore, SailorPtHit* hits)
 {
+	return SailorPt_IntersectRaysEx(s, count, o, d, ignore, 0u, hits);
+}
+
+int32_t SailorPt_IntersectRaysEx(SailorPtScene* s, uint32_t count, const float* o, const float* d, const uint32_t* ignore, uint32_t flags, SailorPtHit* hits)
+{
 	if (!s || !o || !d || !hits) return SAILOR_PT_ERR_ARG;
 	int rc = SailorPt_BuildBVH(s);
 	if (rc != SAILOR_PT_OK) return rc;
@@ -284,16 +289,23 @@ int32_t SailorPt_IntersectRays(SailorPtScene* s, uint32_t count, const float* o,
 	{
 		RayRec& r = rays[i];
 		r.ox = o[3 * i]; r.oy = o[3 * i + 1]; r.oz = o[3 * i + 2]; r.ignoreTri = ignore ? ignore[i] : kNoHit;
-		r.dx = d[3 * i]; r.dy = d[3 * i + 1]; r.dz = d[3 * i + 2]; r.tmax = kFltMax;
+		r.dx = d[3 * i]; r.dy = d[3 * i + 1]; r.dz = d[3 * i + 2]; r.tmax = (flags & SAILOR_PT_RAYS_ANY_HIT) ? -kFltMax : kFltMax;
 	}
+	const bool useWide = (flags & SAILOR_PT_RAYS_WIDE) && D.hasWide;
 	DevBuf<RayRec> dRays; DevBuf<Hit> dHits;
 	dRays.Upload(D.ctx, rays); dHits.Alloc(D.ctx, count);
 	if (!D.ctx.ok) return FromCtx(D, SAILOR_PT_ERR_CUDA);
+	if (useWide) { D.replayList.Ensure(D.ctx, count); DevMemset(D.ctx, D.counter.p + 15, 0, sizeof(uint32_t)); }
+	if (!D.ctx.ok) return FromCtx(D, SAILOR_PT_ERR_CUDA);
 	D.ctx.TimerStart();
-	LaunchTraceRays(D.ctx, D.View(), dRays.p, dHits.p, count, D.counter.p);
+	if (useWide) LaunchTraceRaysWide(D.ctx, D.Wide(), D.View(), D.WideBuffers(D.replayList.p, count), dRays.p, dHits.p, count);
+	else LaunchTraceRays(D.ctx, D.View(), dRays.p, dHits.p, count, D.counter.p);
 	const double tk = D.ctx.TimerStop();
 	dHits.Download(D.ctx, reinterpret_cast<Hit*>(hits), count);
+	uint32_t replayed = 0;
+	if (useWide) DevDownload(D.ctx, &replayed, D.counter.p + 15, 4);
 	g_stats = SailorPtStats{};
+	g_stats.replayedRays = replayed;
 	g_stats.rays = count; g_stats.secondsTraverse = tk; g_stats.traverseLaunches = 1; g_stats.kernelLaunches = D.ctx.kernelLaunches;
 	g_stats.secondsTotal = HostNow() - t0;
 	return FromCtx(D, SAILOR_PT_OK);
@@ -372,10 +384,10 @@ int32_t SailorPt_RenderResident(SailorPtScene* s, const SailorPtParams* p, uint3
 	D.ctx.Mark(Ctx::kMarkCall1);
 	D.ctx.Sync();
 	g_stats = SailorPtStats{};
-	g_stats.secondsFlatten = D.ctx.Between(Ctx::kMarkCall0, Ctx::kMarkCall1);         // whole call on the launch stream (CUDA events); field reused: no flatten here
+	g_stats.secondsCall = D.ctx.Between(Ctx::kMarkCall0, Ctx::kMarkCall1);            // whole call on the launch stream (CUDA events)
 	g_stats.rays = rs.rays; g_stats.primarySamples = rs.primarySamples; g_stats.secondsTraverse = rs.secondsTraverse;
 	g_stats.secondsShade = rs.secondsShade; g_stats.secondsExpand = rs.secondsStage[0]; g_stats.secondsFanOut = rs.secondsStage[1]; g_stats.secondsClassify = rs.secondsStage[2];
-	g_stats.secondsGather = rs.secondsStage[3]; g_stats.fanOutSamples = rs.fanOutSamples; g_stats.secondsOutput = tOut; g_stats.secondsBvhBuild = tBuild; g_stats.traverseLaunches = rs.traverseLaunches; g_stats.batches = rs.batches;
+	g_stats.secondsGather = rs.secondsStage[3]; g_stats.fanOutSamples = rs.fanOutSamples; g_stats.replayedRays = rs.replayedRays; g_stats.secondsOutput = tOut; g_stats.secondsBvhBuild = tBuild; g_stats.traverseLaunches = rs.traverseLaunches; g_stats.batches = rs.batches;
 	g_stats.kernelLaunches = D.ctx.kernelLaunches; g_stats.h2dBytes = D.ctx.h2dBytes; g_stats.d2hBytes = D.ctx.d2hBytes;
 	g_stats.secondsTotal = HostNow() - t0;
 	return FromCtx(D, SAILOR_PT_OK);

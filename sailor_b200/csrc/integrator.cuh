@@ -46,7 +46,7 @@ namespace spt
 	struct alignas(16) PrimaryHitRec { uint32_t pixel, sample, pad0, pad1; float t, u, v; uint32_t tri; };
 	static_assert(sizeof(PrimaryHitRec) == 32, "PrimaryHitRec layout");
 
-	struct RenderStats { uint64_t rays, primarySamples, fanOutSamples; double secondsTraverse, secondsShade, secondsStage[4]; uint32_t traverseLaunches, batches; };
+	struct RenderStats { uint64_t rays, primarySamples, fanOutSamples, replayedRays; double secondsTraverse, secondsShade, secondsStage[4]; uint32_t traverseLaunches, batches; };
 
 	constexpr uint32_t kNone = 0xFFFFFFFFu;
 #ifndef SPT_FAN_OUT_MIN

@@ -9,6 +9,7 @@
 #include "flatten.cuh"
 #include "bvh_build.cuh"
 #include "trace_kernels.cuh"
+#include "trace_wide.cuh"
 #include "bvh_build_small.cuh"
 #include "../../include/sailor_pt.h"
 
@@ -43,6 +44,11 @@ namespace spt
 		DevBuf<TNode> tnodes;
 		DevBuf<TTri> ttris;
 		uint32_t rootRef = 0;
+		// wide layout (wide_bvh.cuh): built for every scene the shared-memory kernel does not take
+		bool hasWide = false;
+		uint32_t numWideNodes = 0, numWideLevels = 0;
+		DevBuf<WNode> wnodes; DevBuf<TTri> wtris; DevBuf<V4> wleafBox; DevBuf<WDesc> wdesc; DevBuf<WideCounters> wcounters;
+		DevBuf<uint32_t> replayList;          // IntersectRays / sky queues; the wavefront levels use an arena of the frame
 
 		// results of the last RenderResident (stay on the device until read back or handed to NCCL)
 		DevBuf<float> residentLin; DevBuf<uint8_t> residentSrgb; uint32_t residentW = 0, residentH = 0;
@@ -56,6 +62,50 @@ namespace spt
 		SailorPtStats stats{};
 
 		BvhView View() const { BvhView v; v.nodes = tnodes.p; v.tris = ttris.p; v.rootRef = rootRef; v.numNodes = numInternal; v.numTris = numTris; return v; }
+		WideView Wide() const { WideView w; w.nodes = wnodes.p; w.tris = wtris.p; w.leafBox = wleafBox.p; w.numNodes = numWideNodes; return w; }
+		// [12] wide work counter, [13] replay count, [14] replay work counter, [15] rays replayed since the last reset
+		WideTraceBuffers WideBuffers(uint32_t* list, uint32_t cap) { WideTraceBuffers b; b.counters = counter.p + 12; b.replayList = list; b.replayCap = cap; return b; }
+
+		// Collapse the binary tree into the wide layout.  `refIdx` / `leafOffsetByRef`: build node -> reference node index, reference
+		// leaf -> first triangle slot (both still in the build scratch).
+		int BuildWide(const uint32_t* left, const uint32_t* count, const float* aabb, const uint32_t* refIdx, const uint32_t* leafOffsetByRef)
+		{
+			hasWide = false;
+			size_t smallBytes;
+			// scenes the shared-memory kernel takes walk the exact layout there (SAILOR_PT_FORCE_WIDE: tests build the wide layout anyway)
+			if ((SmallScene(View(), smallBytes) && !getenv("SAILOR_PT_FORCE_WIDE")) || getenv("SAILOR_PT_NO_WIDE")) return SAILOR_PT_OK;
+			const uint32_t N = numTris;
+			const uint32_t nodeCap = numInternal + N / kWideLeafMax + 2u;
+			wnodes.Ensure(ctx, nodeCap); wtris.Ensure(ctx, N); wleafBox.Ensure(ctx, (size_t)N * 2); wdesc.Ensure(ctx, nodeCap); wcounters.Ensure(ctx, 1);
+			if (!ctx.ok) return CudaStatus();
+			WideBuildArgs a;
+			a.left = left; a.count = count; a.aabb = aabb; a.refIdx = refIdx; a.leafOffsetByRef = leafOffsetByRef; a.ttris = ttris.p;
+			a.nodes = wnodes.p; a.wtris = wtris.p; a.leafBox = wleafBox.p; a.desc = wdesc.p; a.c = wcounters.p; a.nodeCap = nodeCap; a.numTris = N;
+			launch_for(ctx, 1, WideInitKernel{ a });
+			uint32_t levels = 0;
+			WideCounters c{};
+			for (;;)
+			{
+				// a wide level consumes at least one binary level: numLevels launches finish every tree without chunked leaves; the
+				// counters say whether anything is left
+				const uint32_t rounds = levels == 0 ? (numLevels < 6u ? numLevels + 1u : numLevels / 2u + 2u) : 4u;
+				for (uint32_t r = 0; r < rounds; r++)
+				{
+					launch_for_range(ctx, &wcounters.p->lvlBegin, &wcounters.p->lvlEnd, nodeCap, nodeCap, WideLevelKernel{ a });
+					launch_for(ctx, 1, WideAdvanceKernel{ wcounters.p, nodeCap });
+				}
+				levels += rounds;
+				DevDownload(ctx, &c, wcounters.p, sizeof(c));
+				if (!ctx.ok) return CudaStatus();
+				if (c.overflow) { ctx.error = "wide BVH: node arena overflow"; return SAILOR_PT_ERR_LIMIT; }
+				if (c.lvlBegin >= c.lvlEnd) break;
+				if (levels > 4096u) { ctx.error = "wide BVH: collapse did not terminate"; return SAILOR_PT_ERR_LIMIT; }
+			}
+			if (c.triCount != N) { ctx.error = "wide BVH: triangle count mismatch"; return SAILOR_PT_ERR_LIMIT; }
+			numWideNodes = c.nodeCount; numWideLevels = levels;
+			hasWide = true;
+			return SAILOR_PT_OK;
+		}
 
 		int Fail(int code) { return code; }
 		int CudaStatus() { return ctx.ok ? SAILOR_PT_OK : SAILOR_PT_ERR_CUDA; }
@@ -65,7 +115,7 @@ namespace spt
 		{
 			const double t0 = HostNow();
 			numTris = (uint32_t)host.numTriangles;
-			counter.Alloc(ctx, 16);
+			counter.Alloc(ctx, 16); counter.Zero(ctx);
 			if (numTris == 0) return CudaStatus();
 			// The primitive streams go to the device piece by piece, straight from the importer's vectors (no host-side concatenation:
 			// at 10 M triangles that was hundreds of MB of extra copies).  A stream a primitive lacks is never read (FlattenKernel
@@ -212,6 +262,8 @@ namespace spt
 				{
 					nodesUsed = res[0]; numInternal = res[1]; numLevels = res[2];
 					rootRef = numInternal ? 0u : kLeafBit;
+					const int rcw = BuildWide(s.left, s.count, s.aabb, refIdx.p, scan.p);
+					if (rcw != SAILOR_PT_OK) { ctx.TimerStop(); return rcw; }
 					stats.secondsBvhBuild = ctx.TimerStop();
 					stats.secondsTotal = HostNow() - t0;
 					built = ctx.ok;
@@ -273,6 +325,10 @@ namespace spt
 			launch_for(ctx, nodesUsed, PackNodesKernel{ s.left, rank.p, refIdx.p, leafOffsetByRef.p, s.aabb, tnodes.p });
 			launch_for(ctx, N, PackTrisKernel{ vtx.p, mapping.p, leafCountAtSlot.p, ttris.p, N });
 			rootRef = numInternal ? 0u : kLeafBit;      // a root that never split is one leaf at slot 0
+			{
+				const int rcw = BuildWide(s.left, s.count, s.aabb, refIdx.p, leafOffsetByRef.p);
+				if (rcw != SAILOR_PT_OK) { ctx.TimerStop(); return rcw; }
+			}
 			stats.secondsBvhBuild = ctx.TimerStop();
 			stats.secondsTotal = HostNow() - t0;
 			built = ctx.ok;

@@ -197,11 +197,11 @@ namespace spt
 	// Wavefront working set, shared by every scene object of the process on one device and kept for the life of the process (it
 	// only ever grows): 0 activation records, 1 RayAux arena, 2 rays, 3 hits, 4 per-sample results, 5 primary-hit queue, 6 batch
 	// counters, 7 blue-noise table, 8 fan-out contexts, 9 sky states, 10 sky rays, 11 sky hits, 12 ray status bytes, 13 slow list,
-	// 14 fan-out slot tables.  A host that creates one scene object per frame (the reference's PathTracer object per Run) would
+	// 14 fan-out slot tables, 15 replay list of the wide traversal.  A host that creates one scene object per frame (the reference's PathTracer object per Run) would
 	// otherwise allocate and free tens of GiB of arenas every frame (~1.5 ms per C2 frame even from the stream-ordered pool); plain
 	// cudaMalloc memory, because a stream-ordered allocation must be freed on a stream that may no longer exist.  One
 	// frame renders at a time per device (`frame` mutex); a frame saturates the GPU anyway.
-	struct SharedArenas { PlainBuf mem[15]; std::mutex frame; };
+	struct SharedArenas { PlainBuf mem[16]; std::mutex frame; };
 	inline SharedArenas& ArenasOfCurrentDevice()
 	{
 		static std::mutex m;
@@ -258,6 +258,11 @@ namespace spt
 
 		rs = RenderStats{};
 		const BvhView view = D.View();
+		// secondary rays walk the wide layout unless the caller asks for the reference visit order everywhere (or the scene is
+		// small enough for the shared-memory kernel, which has no wide layout)
+		const bool useWide = D.hasWide && !(p.flags & SAILOR_PT_FLAG_EXACT_TRAVERSAL);
+		const WideView wide = D.Wide();
+		DevMemset(ctx, D.counter.p + 15, 0, sizeof(uint32_t));
 		SpanTimer& tt = D.traceTimer;
 		SpanTimer* st = D.stageTimer;
 
@@ -285,7 +290,7 @@ namespace spt
 			uint32_t shrink = 0;
 			uint32_t done = 0;
 			uint64_t held = 0;
-			for (const int k : { 0, 1, 2, 3, 8, 9, 10, 11, 12, 13, 14 }) held += renderMem[k].n;
+			for (const int k : { 0, 1, 2, 3, 8, 9, 10, 11, 12, 13, 14, 15 }) held += renderMem[k].n;
 			const uint64_t budget = BatchBudget(held);
 			if (hostTrace) fprintf(stderr, "[sailor_pt] t=%.3f ms primary pass done: %u first hits\n", (HostNow() - tFrame0) * 1e3, hitCount);
 			while (done < hitCount && ctx.ok)
@@ -307,6 +312,9 @@ namespace spt
 				a.status = EnsureBytes<uint8_t>(ctx, renderMem[12], plan.auxCap); a.slowList = EnsureBytes<uint32_t>(ctx, renderMem[13], plan.rayCap);
 				a.fanCap = plan.firstHits + 1024u; a.fan = EnsureBytes<ShadeCtx>(ctx, renderMem[8], a.fanCap);
 				a.fanSlots[0] = EnsureBytes<uint32_t>(ctx, renderMem[14], (size_t)a.fanCap * 8u); a.fanSlots[1] = a.fanSlots[0] + (size_t)a.fanCap * 4u;
+				const uint32_t replayCap = plan.rayCap > a.skyCap ? plan.rayCap : a.skyCap;
+				uint32_t* replayList = useWide ? EnsureBytes<uint32_t>(ctx, renderMem[15], replayCap) : nullptr;
+				const WideTraceBuffers wb = D.WideBuffers(replayList, replayCap);
 				a.c = counters; a.sampleBuf = sampleBuf;
 				if (!ctx.ok) return SAILOR_PT_ERR_CUDA;
 				if (hostTrace) fprintf(stderr, "[sailor_pt] t=%.3f ms batch: first hits %u of %u (done %u), budget %.1f GiB, rayCap %u auxCap %u recCap %u shrink %u\n",
@@ -331,7 +339,8 @@ namespace spt
 					launch_for_range<SPT_FAN_MIN_BLOCKS>(ctx, &counters->zero, &counters->fanThreads[1], a.fanCap * 32u, a.fanCap * 32u, FanOutKernel{ a, level, 1u });
 					st[1].End(ctx);
 					tt.Begin(ctx);
-					LaunchTraceLevel(ctx, view, a.rays, a.hits, plan.rayCap, D.counter.p, &L->rayCount, WavefrontOut{ a.status, &L->auxBase, a.slowList, &counters->slowCount });
+					if (useWide) LaunchTraceLevelWide(ctx, wide, view, wb, a.rays, a.hits, plan.rayCap, &L->rayCount, WavefrontOut{ a.status, &L->auxBase, a.slowList, &counters->slowCount });
+					else LaunchTraceLevel(ctx, view, a.rays, a.hits, plan.rayCap, D.counter.p, &L->rayCount, WavefrontOut{ a.status, &L->auxBase, a.slowList, &counters->slowCount });
 					tt.End(ctx);
 					st[2].Begin(ctx);
 					launch_for_range(ctx, &counters->zero, &counters->slowCount, plan.rayCap, plan.rayCap, ClassifyKernel{ a, level });
@@ -342,7 +351,8 @@ namespace spt
 						for (uint32_t it = 0; it < p.maxBounces; it++, q ^= 1u)     // a TraceSky walk traces at most maxBounces rays (:581)
 						{
 							tt.Begin(ctx);
-							LaunchTraceRays(ctx, view, a.skyRays + (q ? a.skyCap : 0u), a.skyHits, a.skyCap, D.counter.p, &counters->skyCount[q]);
+							if (useWide) LaunchTraceRaysWide(ctx, wide, view, wb, a.skyRays + (q ? a.skyCap : 0u), a.skyHits, a.skyCap, &counters->skyCount[q]);
+							else LaunchTraceRays(ctx, view, a.skyRays + (q ? a.skyCap : 0u), a.skyHits, a.skyCap, D.counter.p, &counters->skyCount[q]);
 							tt.End(ctx);
 							st[2].Begin(ctx);
 							launch_for_range(ctx, &counters->zero, &counters->skyCount[q], a.skyCap, a.skyCap, SkyKernel{ a, q });
@@ -399,6 +409,7 @@ namespace spt
 		ctx.Mark(1);
 		ctx.Sync();
 		rs.traverseLaunches = tt.Spans();
+		{ uint32_t rep = 0; DevDownload(ctx, &rep, D.counter.p + 15, 4); rs.replayedRays = rep; }
 		rs.secondsTraverse = tt.Collect(ctx);
 		for (int k = 0; k < 4; k++) rs.secondsStage[k] = st[k].Collect(ctx);
 		rs.secondsShade = ctx.Between(0, 1) - rs.secondsTraverse;      // everything of the frame that is not a trace launch

@@ -538,6 +538,11 @@ namespace spt
 		SPT_CUDA_CHECK(ctx, cudaGetLastError());
 	}
 #else
+	inline bool SmallScene(const BvhView& bvh, size_t& bytes)
+	{
+		bytes = (size_t)bvh.numNodes * sizeof(TNode) + (size_t)bvh.numTris * sizeof(TTri);
+		return bytes <= 40u * 1024u;
+	}
 	inline void LaunchTraceRays(Ctx& ctx, const BvhView& bvh, const RayRec* rays, Hit* hits, uint32_t n, uint32_t*, const uint32_t* nPtr = nullptr)
 	{
 		LocalStack st;

@@ -74,13 +74,48 @@ def random_rays(n, seed, scale=1.5):
     return o, d
 
 
+def surface_rays(tris, n, seed):
+    """Rays as the integrator emits them: origins ON random triangles (offset 1e-6 along the face normal, like
+    PathTracer.cpp:667), random directions, the origin's triangle as `ignore`.  tris: (N, 51) flattened triangles."""
+    r = np.random.RandomState(seed)
+    k = r.randint(0, len(tris), n)
+    v = tris[k, 3:12].reshape(n, 3, 3).astype(np.float64)
+    b = r.dirichlet((1.0, 1.0, 1.0), n)
+    p = (v * b[:, :, None]).sum(axis=1)
+    fn = np.cross(v[:, 1] - v[:, 0], v[:, 2] - v[:, 0])
+    fn /= np.maximum(np.linalg.norm(fn, axis=1, keepdims=True), 1e-30)
+    d = r.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    o = p + 1e-6 * fn * np.where(r.uniform(size=(n, 1)) < 0.5, -1.0, 1.0)
+    return o.astype(np.float32), d.astype(np.float32), k.astype(np.uint32)
+
+
 def check_random_rays(lib, oracle, path, n=20000, seed=1):
     o, d = random_rays(n, seed)
     with lib.load_scene(path) as a, oracle.load_scene(path) as b:
         nt = a.counts()["triangles"]
         ignore = np.random.RandomState(seed + 1).randint(0, nt, n).astype(np.uint32)
-        assert_hits_equal(a.intersect_rays(o, d), b.intersect_rays(o, d))
-        assert_hits_equal(a.intersect_rays(o, d, ignore), b.intersect_rays(o, d, ignore))
+        # secondary-ray shaped queries: most of them hit something close by
+        so, sd, sk = surface_rays(b.triangles()[0], n, seed + 2)
+        sref = b.intersect_rays(so, sd, sk)
+        assert_hits_equal(a.intersect_rays(so, sd, sk), sref)
+        assert_hits_equal(a.intersect_rays(so, sd, sk, wide=True), sref)
+        sany = a.intersect_rays(so, sd, sk, wide=True, any_hit=True)
+        assert np.array_equal(sany["triId"] != NOHIT, sref["triId"] != NOHIT), "hit-or-miss differs on surface rays"
+        ref, ref_ig = b.intersect_rays(o, d), b.intersect_rays(o, d, ignore)
+        assert_hits_equal(a.intersect_rays(o, d), ref)
+        assert_hits_equal(a.intersect_rays(o, d, ignore), ref_ig)
+        # the traversal variants the integrator uses for secondary rays: the wide layout with exact replay of ambiguous rays
+        # (same bits as the reference), and hit-or-miss queries (same boolean; the hit reported is SOME reachable hit)
+        assert_hits_equal(a.intersect_rays(o, d, wide=True), ref)
+        replayed = lib.stats()["replayedRays"]
+        assert_hits_equal(a.intersect_rays(o, d, ignore, wide=True), ref_ig)
+        for ig, r in ((None, ref), (ignore, ref_ig)):
+            any_hits = a.intersect_rays(o, d, ig, wide=True, any_hit=True)
+            assert np.array_equal(any_hits["triId"] != NOHIT, r["triId"] != NOHIT), "hit-or-miss differs at %d rays" % int(((any_hits["triId"] != NOHIT) != (r["triId"] != NOHIT)).sum())
+            got = any_hits["triId"] != NOHIT
+            assert np.all(any_hits["t"][got] >= r["t"][got]), "a hit-or-miss query reported a hit nearer than the closest hit"
+    return replayed
 
 
 def check_textures(lib, path, uv, expected):

@@ -9,7 +9,7 @@ gpu = sailor_b200.library()
 w = bench.WORKLOADS[name]
 path = scenes.ensure(tempfile.mkdtemp(), w["scene"], **w["kw"])
 p = bench.make_params(w, seed=1)
-keys = ("secondsFlatten", "secondsTraverse", "secondsExpand", "secondsFanOut", "secondsClassify", "secondsGather")
+keys = ("secondsCall", "secondsTraverse", "secondsExpand", "secondsFanOut", "secondsClassify", "secondsGather")
 acc = {False: [], True: []}
 with gpu.load_scene(path) as s:
     for rep in range(3 + 12):

@@ -11,7 +11,7 @@ w = bench.WORKLOADS[name]
 path = scenes.ensure(tempfile.mkdtemp(), w["scene"], **w["kw"])
 p = bench.make_params(w, seed=1)
 sc = [L.load_scene(path) for L in libs]
-keys = ("secondsFlatten", "secondsTraverse", "secondsExpand", "secondsFanOut", "secondsClassify", "secondsGather")
+keys = ("secondsCall", "secondsTraverse", "secondsExpand", "secondsFanOut", "secondsClassify", "secondsGather")
 acc = [[] for _ in libs]
 # two copies of the library = two sets of shared arenas (40 GiB each on a 180 GB device: both get the full budget)
 for rep in range(3 + 12):

@@ -19,5 +19,5 @@ for name in sys.argv[1:] or ["c2", "c3"]:
         s.close(); t5 = time.perf_counter()
         print("%s rep%d load %.1f ms (flatten %.2f) | bvh %.1f ms (gpu %.1f, %d launches) | render %.1f ms (gpu %.1f trav %.1f, %d launches, %.1f Mrays) | read %.1f ms | free %.1f ms | total %.1f ms" % (
             name, rep, (t1 - t0) * 1e3, st_load["secondsFlatten"] * 1e3, (t2 - t1) * 1e3, st_b["secondsBvhBuild"] * 1e3, st_b["kernelLaunches"],
-            (t3 - t2) * 1e3, st_r["secondsFlatten"] * 1e3, st_r["secondsTraverse"] * 1e3, st_r["kernelLaunches"], st_r["rays"] / 1e6,
+            (t3 - t2) * 1e3, st_r["secondsCall"] * 1e3, st_r["secondsTraverse"] * 1e3, st_r["kernelLaunches"], st_r["rays"] / 1e6,
             (t4 - t3) * 1e3, (t5 - t4) * 1e3, (t5 - t0) * 1e3), flush=True)

@@ -67,7 +67,7 @@ else:
                 p = bench.make_params(w, seed=1)
                 tr = []
                 for _ in range(3):
-                    s.render_resident(p, rebuild_bvh=False, output_stage=False); st = L.stats(); tr.append((st["secondsTraverse"], st["secondsFlatten"], st["rays"]))
+                    s.render_resident(p, rebuild_bvh=False, output_stage=False); st = L.stats(); tr.append((st["secondsTraverse"], st["secondsCall"], st["rays"]))
                 best = min(tr)
                 row[tag + "_trace_ms"] = round(best[0] * 1e3, 2); row[tag + "_step_ms"] = round(best[1] * 1e3, 2); row[tag + "_trace_Grays"] = round(best[2] / best[0] / 1e9, 3)
         if hasattr(L.lib, "SailorPt_DebugTraceStats"):
