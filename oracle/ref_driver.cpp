@@ -214,6 +214,8 @@ namespace
 	vec3 ReadVec3(const Accessor& a, size_t i) { return vec3(ReadFloat(a, i, 0), ReadFloat(a, i, 1), ReadFloat(a, i, 2)); }
 	vec2 ReadVec2(const Accessor& a, size_t i) { return vec2(ReadFloat(a, i, 0), ReadFloat(a, i, 1)); }
 
+	static thread_local bool t_needDefaultMaterial = false;     // set while flattening: some primitive uses the default material
+
 	// ProcessMesh_Assimp (MaterialUtils.cpp:64-163) for one glTF primitive.
 	void FlattenPrimitive(const tinygltf::Model& model, const tinygltf::Primitive& prim, TVector<Triangle>& out, const mat4& matrix)
 	{
@@ -221,10 +223,12 @@ namespace
 		auto find = [&](const char* name) { auto it = prim.attributes.find(name); return it == prim.attributes.end() ? -1 : it->second; };
 		const Accessor pos = MakeAccessor(model, find("POSITION"));
 		if (!pos.valid) return;
-		const Accessor nrm = MakeAccessor(model, find("NORMAL"));
-		const Accessor tan = MakeAccessor(model, find("TANGENT"));
-		const Accessor uv0 = MakeAccessor(model, find("TEXCOORD_0"));
-		const Accessor uv1 = MakeAccessor(model, find("TEXCOORD_1"));
+		// an attribute stream whose element count differs from POSITION's is malformed: it is ignored (loader contract)
+		auto attr = [&](const char* name) { Accessor a = MakeAccessor(model, find(name)); if (a.valid && a.count != pos.count) a.valid = false; return a; };
+		const Accessor nrm = attr("NORMAL");
+		const Accessor tan = attr("TANGENT");
+		const Accessor uv0 = attr("TEXCOORD_0");
+		const Accessor uv1 = attr("TEXCOORD_1");
 		const Accessor idx = MakeAccessor(model, prim.indices);
 		const size_t numIdx = idx.valid ? idx.count : pos.count;
 		const size_t numFaces = numIdx / 3;
@@ -273,7 +277,12 @@ namespace
 				Raytracing::GenerateTangentBitangent(t, b, &tri.m_vertices[0], &tri.m_uvs[0]);
 				for (int k = 0; k < 3; k++) { tri.m_tangent[k] = t; tri.m_bitangent[k] = b; }
 			}
-			tri.m_materialIndex = (u8)(prim.material >= 0 ? prim.material : 0);                    // :159
+			// :159.  A primitive without a material (or with an index outside the array) gets the DEFAULT material, which Assimp's
+			// glTF2 importer appends after the file's own materials (index = their count)
+			const int nm = (int)model.materials.size();
+			const bool own = prim.material >= 0 && prim.material < nm;
+			if (!own) t_needDefaultMaterial = true;
+			tri.m_materialIndex = (u8)(own ? prim.material : nm);
 		}
 	}
 
@@ -393,6 +402,7 @@ namespace
 		loader.lightMatrix.assign(numLights, mat4(1));
 		loader.lightSeen.assign(numLights, 0);
 		const int sceneIndex = model.defaultScene >= 0 ? model.defaultScene : 0;
+		t_needDefaultMaterial = false;
 		if (sceneIndex < (int)model.scenes.size())
 		{
 			for (int root : model.scenes[sceneIndex].nodes) loader.Node(root, mat4(1.0f));   // PathTracer.cpp:161
@@ -401,14 +411,18 @@ namespace
 
 		// materials + textures (PathTracer.cpp:164-360)
 		auto& T = scene.tracer;
-		T.m_materials.Resize(model.materials.size());
-		T.m_textures.Resize(model.materials.size() * 5);
+		// the glTF default material (baseColor 1, metallic 1, roughness 1, opaque) is appended when a primitive needs it
+		std::vector<tinygltf::Material> mats = model.materials;
+		if (t_needDefaultMaterial) mats.push_back(tinygltf::Material());
+		if (mats.size() > 256) { t_lastError = "more than 256 materials (with the default material)"; return SAILOR_PT_ERR_LIMIT; }
+		T.m_materials.Resize(mats.size());
+		T.m_textures.Resize(mats.size() * 5);
 		uint32_t textureIndex = 0;
 		bool limit = false;
-		for (size_t i = 0; i < model.materials.size(); i++)
+		for (size_t i = 0; i < mats.size(); i++)
 		{
 			auto& material = T.m_materials[i];
-			const auto& gm = model.materials[i];
+			const auto& gm = mats[i];
 
 			material.m_blendMode = BlendMode::Opaque;                                        // :186-203
 			if (gm.alphaMode == "BLEND") material.m_blendMode = BlendMode::Blend;

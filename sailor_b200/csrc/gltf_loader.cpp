@@ -285,13 +285,19 @@ namespace spt
 				a.comps = CompsOf(acc.at("type").str);
 				a.componentType = acc.at("componentType").integer(0);
 				const size_t elem = (size_t)CompSize(a.componentType) * a.comps;
-				const size_t bs = (size_t)view.at("byteStride").number(0);
+				// sizes and offsets come from the file: negative or absurd numbers are rejected before any size_t arithmetic, and the
+				// range check is written so that it cannot wrap
+				const double lim = 1e15;
+				const double dbs = view.at("byteStride").number(0), dvo = view.at("byteOffset").number(0), dao = acc.at("byteOffset").number(0), dcount = acc.at("count").number(0);
+				if (!(dbs >= 0 && dbs <= 65536.0 && dvo >= 0 && dvo < lim && dao >= 0 && dao < lim && dcount >= 0 && dcount < lim)) return a;
+				const size_t bs = (size_t)dbs;
 				a.stride = bs ? bs : elem;
-				const size_t off = (size_t)view.at("byteOffset").number(0) + (size_t)acc.at("byteOffset").number(0);
-				a.count = (size_t)acc.at("count").number(0);
+				const size_t off = (size_t)dvo + (size_t)dao;
+				a.count = (size_t)dcount;
 				a.normalized = acc.at("normalized").type == Json::Bool && acc.at("normalized").b;
 				if (!elem || !a.count) return a;
-				if (off + a.stride * (a.count - 1) + elem > buffers[bi].size()) return a;
+				const size_t size = buffers[bi].size();
+				if (off > size || elem > size - off || a.stride == 0 || (a.count - 1) > (size - off - elem) / a.stride) return a;
 				a.base = buffers[bi].data() + off;
 				a.valid = true;
 				return a;
@@ -339,6 +345,7 @@ namespace spt
 			HostScene& scene;
 			std::vector<int> cameraSeen, lightSeen;
 			std::vector<std::vector<float>> lightMatrix;
+			bool needDefault = false;              // some primitive uses the default material
 
 			// node local matrix, reference convention = transpose of the mathematical matrix (MaterialUtils.cpp:186-191)
 			void LocalMatrix(const Json& n, float* out) const
@@ -373,13 +380,16 @@ namespace spt
 				scene.prims.emplace_back();
 				HostPrimitive& hp = scene.prims.back();
 				ReadStream(pos, 3, hp.pos);
-				const Accessor nrm = g.accessor(attrs.at("NORMAL").integer(-1));
+				// an attribute stream whose element count differs from POSITION's is malformed: it is ignored (the device buffers are
+				// sized by the position count, and FlattenKernel indexes every stream with position indices)
+				auto attr = [&](const char* name) { Accessor a = g.accessor(attrs.at(name).integer(-1)); if (a.valid && a.count != pos.count) a.valid = false; return a; };
+				const Accessor nrm = attr("NORMAL");
 				if (nrm.valid) ReadStream(nrm, 3, hp.nrm);
-				const Accessor tan = g.accessor(attrs.at("TANGENT").integer(-1));
+				const Accessor tan = attr("TANGENT");
 				if (tan.valid && tan.comps == 4) ReadStream(tan, 4, hp.tan);
-				const Accessor uv0 = g.accessor(attrs.at("TEXCOORD_0").integer(-1));
+				const Accessor uv0 = attr("TEXCOORD_0");
 				if (uv0.valid) ReadStream(uv0, 2, hp.uv0);
-				const Accessor uv1 = g.accessor(attrs.at("TEXCOORD_1").integer(-1));
+				const Accessor uv1 = attr("TEXCOORD_1");
 				if (uv1.valid) ReadStream(uv1, 2, hp.uv1);
 				const Accessor idx = g.accessor(prim.at("indices").integer(-1));
 				const size_t numIdx = idx.valid ? idx.count : pos.count;
@@ -396,8 +406,13 @@ namespace spt
 				const uint32_t limit = (uint32_t)(pos.count < 0xFFFFFFFFull ? pos.count : 0xFFFFFFFFull);
 				for (size_t i = 0; i < n3; i++) dst[i] = dst[i] < limit ? dst[i] : 0u;      // out-of-range indices read vertex 0 (no crash on bad files)
 				memcpy(hp.world, world, sizeof(hp.world));
+				// a primitive without a material (or with an index outside the array) gets the DEFAULT material, which Assimp's glTF2
+				// importer appends after the file's own materials (index = their count); LoadGltf appends it when `needDefault` is set
 				const int mat = prim.at("material").integer(-1);
-				hp.material = (uint32_t)(uint8_t)(mat >= 0 ? mat : 0);
+				const size_t nm = g.root.at("materials").size();
+				const bool own = mat >= 0 && (size_t)mat < nm;
+				if (!own) needDefault = true;
+				hp.material = (uint32_t)(own ? (size_t)mat : nm);
 				scene.numTriangles += faces;
 			}
 
@@ -585,11 +600,15 @@ namespace spt
 		std::vector<PendingImage> pendingImages;
 		struct Key { uint32_t slot; };
 		std::map<int, uint32_t> textureMapping; // "file" (= image index) -> slot, overwritten like m_textureMapping[file] = ...
-		scene.materials.resize(jmats.size());
+		// the glTF default material (an empty material object: baseColor 1, metallic 1, roughness 1, opaque) follows the file's own
+		const size_t numMaterials = jmats.size() + (b.needDefault ? 1u : 0u);
+		if (numMaterials > 256) { err = "more than 256 materials (with the default material)"; return SAILOR_PT_ERR_LIMIT; }
+		const Json defaultMaterial;
+		scene.materials.resize(numMaterials);
 		bool limit = false, badImage = false;
-		for (size_t i = 0; i < jmats.size(); i++)
+		for (size_t i = 0; i < numMaterials; i++)
 		{
-			const Json& jm = jmats.at(i);
+			const Json& jm = i < jmats.size() ? jmats.at(i) : defaultMaterial;
 			MaterialGpu& m = scene.materials[i];
 			memset(&m, 0, sizeof(m));
 			m.uvTransform[0] = 1; m.uvTransform[5] = 1; m.uvTransform[10] = 1;       // mat3(1)

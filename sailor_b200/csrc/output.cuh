@@ -5,10 +5,10 @@
 // (MaterialUtils.h:75-124, so u maps to u*(w-1)), G at uv+(a,0), B at uv+(a,a), R at uv-(a,a), a = 0.5/width; then
 // Utils::LinearToSRGB (Core/Utils.cpp:48-57), *255, clamp, truncate to u8.  One thread per pixel, coalesced RGB8
 // stores; the 12 accumulator texels a pixel touches are neighbours, so the stage streams the image once from L2.
-// powf is evaluated in fp64 and rounded once, which reproduces glibc's (nearly correctly rounded) powf far more
-// often than CUDA's fp32 powf would; the parity test allows 1 LSB on a 1e-5 fraction of the bytes.
+// powf is glibc's own algorithm restated (glibc_powf.h), so the bytes equal the reference's.
 #pragma once
 #include "backend.h"
+#include "glibc_powf.h"
 
 namespace spt
 {
@@ -29,7 +29,9 @@ namespace spt
 	SPT_HD float LinearToSrgb(float c)                 // Core/Utils.cpp:48-57
 	{
 		if (c < 0.0031308f) return c * 12.92f;
-		const float p = (float)pow((double)c, (double)(1.f / 2.4f));
+		// glm::pow -> glibc powf: restated bit for bit (glibc_powf.h); inf / NaN accumulators take the library function
+		const float e = 1.f / 2.4f;
+		const float p = (GlibcPowfMainPath(c, e) && c < 1e30f) ? GlibcPowf(c, e) : powf(c, e);
 		return 1.055f * p - 0.055f;
 	}
 

@@ -186,6 +186,33 @@ def cube(path):
     return g.write(path)
 
 
+def default_material_scene(path, with_materials=False):
+    """Three cubes that exercise the DEFAULT material and malformed attribute streams (the reference's Assimp front end appends
+    a default material; a primitive without `material`, or with an index outside the array, uses it):
+      with_materials=False  the file has NO `materials` array at all; one primitive also carries a NORMAL accessor whose count
+                            differs from POSITION's (ignored: flat normals are generated)
+      with_materials=True   one real material; the primitives use it, omit `material`, or point past the array."""
+    g = GlbBuilder()
+    pos, nrm, idx = _cube_arrays(0.3)
+    mats = [None, None, None]
+    if with_materials:
+        mats = [g.material(pbrMetallicRoughness={"baseColorFactor": [0.1, 0.6, 0.2, 1.0], "metallicFactor": 0.0, "roughnessFactor": 0.7}), None, 7]
+    else:
+        del g.j["materials"]
+    for k, m in enumerate(mats):
+        mesh = g.mesh(pos, idx, 0, nrm=(nrm[:-2] if (k == 1 and not with_materials) else nrm))
+        prim = g.j["meshes"][mesh]["primitives"][0]
+        if m is None:
+            del prim["material"]
+        else:
+            prim["material"] = m
+        g.node(mesh=mesh, translation=[(k - 1) * 0.8, 0.0, 0.0])
+    g.j["extensions"] = {"KHR_lights_punctual": {"lights": [{"type": "directional", "color": [1.0, 1.0, 1.0], "intensity": 1366.0}]}}
+    g.j["extensionsUsed"] = ["KHR_lights_punctual"]
+    g.node(name="sun", rotation=quat_from_to_neg_z((0.3, -1.0, -0.4)), extensions={"KHR_lights_punctual": {"light": 0}})
+    return g.write(path)
+
+
 def lcg_uniform(count, seed=12345):
     """U[0,1) floats from s = s*1664525 + 1013904223 (mod 2^32), value = s / 2^32."""
     out = np.empty(count, np.float64)
@@ -438,4 +465,8 @@ def ensure(directory, name, **kw):
         n, k = kw.get("n", 707), kw.get("instances", 10)
         p = os.path.join(directory, "instanced_%d_x%d.glb" % (n, k))
         return p if os.path.exists(p) else instanced_heightfield(p, n=n, instances=k)
+    if name == "nomat":
+        wm = bool(kw.get("with_materials", False))
+        p = os.path.join(directory, "nomat_%d.glb" % int(wm))
+        return p if os.path.exists(p) else default_material_scene(p, with_materials=wm)
     raise KeyError(name)

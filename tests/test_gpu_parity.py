@@ -54,6 +54,18 @@ def test_random_and_degenerate_rays_match_the_oracle(gpu, oracle, scene_dir, nam
     pc.check_random_rays(gpu, oracle, _scene(scene_dir, name, kw), n=n)
 
 
+@pytest.mark.parametrize("with_materials", [False, True])
+def test_default_material_and_malformed_attribute_streams(gpu, oracle, scene_dir, with_materials):
+    pc.check_default_material(gpu, oracle, scenes.ensure(scene_dir, "nomat", with_materials=with_materials), 1 if with_materials else 0)
+
+
+@pytest.mark.parametrize("name,kw", [("cube", {}), ("pbr", {})])
+def test_wide_layout_on_small_scenes(gpu, oracle, scene_dir, name, kw, monkeypatch):
+    """Scenes the shared-memory kernel normally takes, forced through the wide layout + exact replay."""
+    monkeypatch.setenv("SAILOR_PT_FORCE_WIDE", "1")
+    pc.check_random_rays(gpu, oracle, _scene(scene_dir, name, kw), n=50000)
+
+
 def test_bvh_of_ragged_scenes(gpu, oracle, tmp_path):
     for tag, count, dup in (("one", 1, False), ("four", 4, False), ("five", 5, False), ("dups", 40, True), ("many", 3000, False)):
         g = scenes.GlbBuilder()

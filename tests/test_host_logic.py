@@ -1,11 +1,15 @@
 """CPU-side tests of the product's host orchestration and kernel bodies (compiled for the host by tests/emu, every
 launch a serial loop) against the oracle and the goldens.  The same checks run against the real CUDA library in
 tests/test_gpu_parity.py; this file exists so logic errors are caught where there is no GPU."""
+import os
+
 import numpy as np
 import pytest
 
 import parity_checks as pc
 import scenes
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 from golden.make_golden import HIT_CASES
 from sailor_b200.capi import Params
 
@@ -72,6 +76,18 @@ def test_primary_hits_match_goldens(emu, G, scene_dir, case):
 
 @pytest.mark.parametrize("name,kw", [("cube", {}), ("pbr", {}), ("heightfield", {"n": 64})])
 def test_random_and_degenerate_rays_match_the_oracle(emu, oracle, scene_dir, name, kw):
+    pc.check_random_rays(emu, oracle, _scene(scene_dir, name, kw), n=6000)
+
+
+@pytest.mark.parametrize("with_materials", [False, True])
+def test_default_material_and_malformed_attribute_streams(emu, oracle, scene_dir, with_materials):
+    pc.check_default_material(emu, oracle, scenes.ensure(scene_dir, "nomat", with_materials=with_materials), 1 if with_materials else 0)
+
+
+@pytest.mark.parametrize("name,kw", [("cube", {}), ("pbr", {})])
+def test_wide_layout_on_small_scenes(emu, oracle, scene_dir, name, kw, monkeypatch):
+    """Scenes the shared-memory kernel normally takes, forced through the wide layout + exact replay."""
+    monkeypatch.setenv("SAILOR_PT_FORCE_WIDE", "1")
     pc.check_random_rays(emu, oracle, _scene(scene_dir, name, kw), n=6000)
 
 
@@ -145,3 +161,25 @@ def test_converged_image_tolerance_cpu(emu, G, scene_dir):
 
 def test_progressive_render_checkpoint_resume_and_linear_image_files(emu, scene_dir, tmp_path):
     pc.check_progressive_and_image_io(emu, _scene(scene_dir, "pbr", {}), tmp_path)
+
+
+def test_powf_restatement_equals_the_hosts_powf(tmp_path):
+    """csrc/glibc_powf.h (the power behind the sRGB transfer functions, Core/Utils.cpp:48-64) against the C library's powf on a dense
+    sweep of arguments, for both exponents the reference uses.  Bit-exact, every value."""
+    import subprocess
+    src = tmp_path / "powf_check.cpp"
+    src.write_text('''#include "glibc_powf.h"
+#include <cstdio>
+#include <cstring>
+int main() {
+  unsigned long long bad = 0, n = 0;
+  const float e1 = 1.f / 2.4f, e2 = 2.4f;
+  for (uint32_t u = spt::f2u(0.0031308f); u < spt::f2u(70000.0f); u += 29) { const float c = spt::u2f(u); n++; if (!spt::GlibcPowfMainPath(c, e1) || spt::f2u(spt::GlibcPowf(c, e1)) != spt::f2u(powf(c, e1))) bad++; }
+  for (uint32_t u = spt::f2u(0.003f); u < spt::f2u(1.2f); u += 11) { const float c = spt::u2f(u); n++; if (!spt::GlibcPowfMainPath(c, e2) || spt::f2u(spt::GlibcPowf(c, e2)) != spt::f2u(powf(c, e2))) bad++; }
+  std::printf("%llu %llu\\n", n, bad);
+  return 0; }
+''')
+    exe = tmp_path / "powf_check"
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-I", os.path.join(ROOT, "sailor_b200", "csrc"), str(src), "-o", str(exe), "-lm"], check=True)
+    n, bad = (int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split())
+    assert n > 8_000_000 and bad == 0, "%d of %d powf results differ from the C library" % (bad, n)
