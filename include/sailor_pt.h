@@ -64,7 +64,8 @@ typedef struct SailorPtParams {
 } SailorPtParams;
 
 /* SailorPtParams::flags */
-#define SAILOR_PT_FLAG_EXACT_TRAVERSAL 1u  /* trace every ray with the reference-visit-order kernel (binary tree); default: secondary rays walk the wide layout, ambiguous ones are replayed exactly */
+#define SAILOR_PT_FLAG_EXACT_TRAVERSAL 1u  /* trace every ray with the reference-visit-order kernel; default: secondary rays take the origin-local walk of the same tree and ambiguous ones are replayed exactly */
+#define SAILOR_PT_FLAG_WIDE_TRAVERSAL 2u   /* secondary rays walk the 8-wide quantised layout instead (same results; built on demand) */
 
 typedef struct SailorPtScene SailorPtScene; /* opaque */
 
@@ -112,7 +113,7 @@ typedef struct SailorPtStats {
 	double secondsGather;     /* GatherKernel + resolve */
 	uint64_t fanOutSamples;   /* rays emitted by FanOutKernel */
 	double secondsCall;       /* product, RenderResident: the whole call between two CUDA events on the launch stream (BVH build + render + output stage) */
-	uint64_t replayedRays;    /* product: rays of the last call that the wide-layout walk handed to the exact (reference visit order) kernel */
+	uint64_t replayedRays;    /* product: rays of the last call that the fast secondary-ray walk handed to the exact (reference visit order) kernel */
 } SailorPtStats;
 
 /* ---- the reference entry points (PathTracer.h:34-36) ---- */
@@ -160,12 +161,14 @@ SAILOR_PT_API int32_t SailorPt_GetCamera(const SailorPtScene* scene, const Sailo
 SAILOR_PT_API int32_t SailorPt_IntersectRays(SailorPtScene* scene, uint32_t count, const float* origins,
 	const float* directions, const uint32_t* ignoreTri, SailorPtHit* hits);
 
-/* The same query through the traversal variants the integrator uses for secondary rays.  flags: SAILOR_PT_RAYS_WIDE = walk the
- * wide layout and replay ambiguous rays exactly (results equal SailorPt_IntersectRays); SAILOR_PT_RAYS_ANY_HIT = hit-or-miss
- * query: hits[i].triId != 0xFFFFFFFF iff BVH::IntersectBVH would return true (t, u, v, triId are those of SOME reachable hit,
- * not necessarily the closest).  The oracle ignores SAILOR_PT_RAYS_WIDE and answers ANY_HIT with its closest hit. */
+/* The same query through the traversal variants the integrator uses for secondary rays.  flags: SAILOR_PT_RAYS_LOCAL = the
+ * origin-local walk (starts at the leaf of ignoreTri), SAILOR_PT_RAYS_WIDE = the 8-wide quantised layout; both replay ambiguous
+ * rays exactly, so the results equal SailorPt_IntersectRays.  SAILOR_PT_RAYS_ANY_HIT = hit-or-miss query: hits[i].triId !=
+ * 0xFFFFFFFF iff BVH::IntersectBVH would return true (t, u, v, triId are those of SOME reachable hit, not necessarily the
+ * closest).  The oracle ignores LOCAL / WIDE and answers ANY_HIT with its closest hit. */
 #define SAILOR_PT_RAYS_WIDE 1u
 #define SAILOR_PT_RAYS_ANY_HIT 2u
+#define SAILOR_PT_RAYS_LOCAL 4u
 SAILOR_PT_API int32_t SailorPt_IntersectRaysEx(SailorPtScene* scene, uint32_t count, const float* origins,
 	const float* directions, const uint32_t* ignoreTri, uint32_t flags, SailorPtHit* hits);
 

@@ -18,8 +18,8 @@ MATERIAL_WORDS = 32
 TRI_FLOATS = 51
 
 OK = 0
-FLAG_EXACT_TRAVERSAL = 1
-RAYS_WIDE, RAYS_ANY_HIT = 1, 2
+FLAG_EXACT_TRAVERSAL, FLAG_WIDE_TRAVERSAL = 1, 2
+RAYS_WIDE, RAYS_ANY_HIT, RAYS_LOCAL = 1, 2, 4
 ERR_ARG, ERR_IO, ERR_FORMAT, ERR_NO_DEVICE, ERR_CUDA, ERR_LIMIT, ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6, -7
 
 
@@ -307,7 +307,7 @@ class Scene:
         self.L.check(self.L.lib.SailorPt_GetCamera(self.h, C.byref(cp), C.byref(w), C.byref(h), cam), "SailorPt_GetCamera")
         return w.value, h.value, np.array(list(cam), np.float32)
 
-    def intersect_rays(self, origins, directions, ignore=None, wide=False, any_hit=False):
+    def intersect_rays(self, origins, directions, ignore=None, wide=False, any_hit=False, local=False):
         """BVH::IntersectBVH for a batch of rays.  wide / any_hit: SailorPt_IntersectRaysEx (the traversal variants the integrator
         uses for secondary rays)."""
         o = np.ascontiguousarray(origins, dtype=np.float32)
@@ -315,9 +315,9 @@ class Scene:
         n = o.shape[0]
         ig = np.ascontiguousarray(ignore, dtype=np.uint32) if ignore is not None else None
         hits = np.empty(n, HIT_DTYPE)
-        if wide or any_hit:
+        if wide or any_hit or local:
             self.L.check(self.L.lib.SailorPt_IntersectRaysEx(self.h, n, _ptr(o, C.c_float), _ptr(d, C.c_float), _ptr(ig, C.c_uint32),
-                                                            (RAYS_WIDE if wide else 0) | (RAYS_ANY_HIT if any_hit else 0), hits.ctypes.data), "SailorPt_IntersectRaysEx")
+                                                            (RAYS_WIDE if wide else 0) | (RAYS_ANY_HIT if any_hit else 0) | (RAYS_LOCAL if local else 0), hits.ctypes.data), "SailorPt_IntersectRaysEx")
         else:
             self.L.check(self.L.lib.SailorPt_IntersectRays(self.h, n, _ptr(o, C.c_float), _ptr(d, C.c_float),
                                                           _ptr(ig, C.c_uint32), hits.ctypes.data), "SailorPt_IntersectRays")

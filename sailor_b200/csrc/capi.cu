@@ -105,6 +105,26 @@ extern "C" SAILOR_PT_API int32_t SailorPt_DebugTraceStats(unsigned long long* ou
 	return SAILOR_PT_OK;
 }
 #endif
+#if defined(SPT_WIDE_LOOP_STATS) && !defined(SPT_EMU)
+// tuning builds only (tools/wide_variants.py): read and clear the lane-state counters of the wide traversal loop
+extern "C" SAILOR_PT_API int32_t SailorPt_DebugWideStats(unsigned long long* out)
+{
+	if (cudaMemcpyFromSymbol(out, spt::g_wideLoopStats, sizeof(unsigned long long) * 16) != cudaSuccess) return SAILOR_PT_ERR_CUDA;
+	static const unsigned long long zero[16] = {};
+	cudaMemcpyToSymbol(spt::g_wideLoopStats, zero, sizeof(zero));
+	return SAILOR_PT_OK;
+}
+#endif
+#if defined(SPT_FAST_LOOP_STATS) && !defined(SPT_EMU)
+// tuning builds only (tools/fast_variants.py): read and clear the lane-state counters of the origin-local traversal loop
+extern "C" SAILOR_PT_API int32_t SailorPt_DebugFastStats(unsigned long long* out)
+{
+	if (cudaMemcpyFromSymbol(out, spt::g_fastLoopStats, sizeof(unsigned long long) * 16) != cudaSuccess) return SAILOR_PT_ERR_CUDA;
+	static const unsigned long long zero[16] = {};
+	cudaMemcpyToSymbol(spt::g_fastLoopStats, zero, sizeof(zero));
+	return SAILOR_PT_OK;
+}
+#endif
 int32_t SailorPt_GetStats(SailorPtStats* s) { if (!s) return SAILOR_PT_ERR_ARG; *s = g_stats; return SAILOR_PT_OK; }
 
 int32_t SailorPt_ParseCommandLineArgs(SailorPtParams* res, const char** args, int32_t num)
@@ -291,21 +311,29 @@ int32_t SailorPt_IntersectRaysEx(SailorPtScene* s, uint32_t count, const float* 
 		r.ox = o[3 * i]; r.oy = o[3 * i + 1]; r.oz = o[3 * i + 2]; r.ignoreTri = ignore ? ignore[i] : kNoHit;
 		r.dx = d[3 * i]; r.dy = d[3 * i + 1]; r.dz = d[3 * i + 2]; r.tmax = (flags & SAILOR_PT_RAYS_ANY_HIT) ? -kFltMax : kFltMax;
 	}
+	if (flags & SAILOR_PT_RAYS_WIDE) { rc = FromCtx(D, D.EnsureWide()); if (rc != SAILOR_PT_OK) return rc; }
 	const bool useWide = (flags & SAILOR_PT_RAYS_WIDE) && D.hasWide;
+	const bool useFast = !useWide && (flags & SAILOR_PT_RAYS_LOCAL) && D.hasFast;
 	DevBuf<RayRec> dRays; DevBuf<Hit> dHits;
 	dRays.Upload(D.ctx, rays); dHits.Alloc(D.ctx, count);
 	if (!D.ctx.ok) return FromCtx(D, SAILOR_PT_ERR_CUDA);
-	if (useWide) { D.replayList.Ensure(D.ctx, count); DevMemset(D.ctx, D.counter.p + 15, 0, sizeof(uint32_t)); }
+	if (useWide || useFast) { D.replayList.Ensure(D.ctx, count); DevMemset(D.ctx, D.counter.p + 15, 0, sizeof(uint32_t)); }
 	if (!D.ctx.ok) return FromCtx(D, SAILOR_PT_ERR_CUDA);
 	D.ctx.TimerStart();
-	if (useWide) LaunchTraceRaysWide(D.ctx, D.Wide(), D.View(), D.WideBuffers(D.replayList.p, count), dRays.p, dHits.p, count);
+	if (useWide) LaunchTraceRaysWide(D.ctx, D.Wide(), D.View(), D.Replay(D.replayList.p, count), dRays.p, dHits.p, count);
+	else if (useFast) LaunchTraceRaysFast(D.ctx, D.Fast(), D.View(), D.Replay(D.replayList.p, count), dRays.p, dHits.p, count);
 	else LaunchTraceRays(D.ctx, D.View(), dRays.p, dHits.p, count, D.counter.p);
 	const double tk = D.ctx.TimerStop();
 	dHits.Download(D.ctx, reinterpret_cast<Hit*>(hits), count);
 	uint32_t replayed = 0;
-	if (useWide) DevDownload(D.ctx, &replayed, D.counter.p + 15, 4);
+	if (useWide || useFast) DevDownload(D.ctx, &replayed, D.counter.p + 15, 4);
 	g_stats = SailorPtStats{};
 	g_stats.replayedRays = replayed;
+#if defined(SPT_EMU) && defined(SPT_WIDE_STATS)
+	// host tuning aid: nodes visited / triangles tested by the wide or the origin-local walk
+	g_stats.boxTests = g_wideStats[0] + g_fastStats[0]; g_stats.triTests = g_wideStats[1] + g_fastStats[1]; g_stats.threads = (uint32_t)(g_wideStats[3] + g_fastStats[3]);
+	g_wideStats[0] = g_wideStats[1] = g_wideStats[3] = 0; g_fastStats[0] = g_fastStats[1] = g_fastStats[3] = 0;
+#endif
 	g_stats.rays = count; g_stats.secondsTraverse = tk; g_stats.traverseLaunches = 1; g_stats.kernelLaunches = D.ctx.kernelLaunches;
 	g_stats.secondsTotal = HostNow() - t0;
 	return FromCtx(D, SAILOR_PT_OK);
@@ -358,6 +386,7 @@ int32_t SailorPt_RenderResident(SailorPtScene* s, const SailorPtParams* p, uint3
 	double tBuild = 0.0;
 	D.ctx.Mark(Ctx::kMarkCall0);
 	if (flags & 1u) D.built = false;                      // BVH build is part of this pass
+	D.wantWide = (p->flags & SAILOR_PT_FLAG_WIDE_TRAVERSAL) != 0u && !(p->flags & SAILOR_PT_FLAG_EXACT_TRAVERSAL);
 	if (!D.built)
 	{
 		const int rcb = FromCtx(D, D.BuildBvh());

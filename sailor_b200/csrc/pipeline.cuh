@@ -44,8 +44,12 @@ namespace spt
 		DevBuf<TNode> tnodes;
 		DevBuf<TTri> ttris;
 		uint32_t rootRef = 0;
-		// wide layout (wide_bvh.cuh): built for every scene the shared-memory kernel does not take
+		// origin-local traversal layout (trace_fast.cuh): built with every BVH the shared-memory kernel does not take
+		bool hasFast = false;
+		DevBuf<FNode> fnodes; DevBuf<FTri> ftris; DevBuf<FStart> fstart; DevBuf<FHeader> fheader; DevBuf<uint32_t> nodeUp;
+		// wide layout (wide_bvh.cuh): an alternative traversal layout, built on demand (SAILOR_PT_FLAG_WIDE_TRAVERSAL / SAILOR_PT_RAYS_WIDE)
 		bool hasWide = false;
+		bool wantWide = false;                // the caller renders through the wide layout: BuildBvh builds it (inside its timed region)
 		uint32_t numWideNodes = 0, numWideLevels = 0;
 		DevBuf<WNode> wnodes; DevBuf<TTri> wtris; DevBuf<V4> wleafBox; DevBuf<WDesc> wdesc; DevBuf<WideCounters> wcounters;
 		DevBuf<uint32_t> replayList;          // IntersectRays / sky queues; the wavefront levels use an arena of the frame
@@ -63,17 +67,45 @@ namespace spt
 
 		BvhView View() const { BvhView v; v.nodes = tnodes.p; v.tris = ttris.p; v.rootRef = rootRef; v.numNodes = numInternal; v.numTris = numTris; return v; }
 		WideView Wide() const { WideView w; w.nodes = wnodes.p; w.tris = wtris.p; w.leafBox = wleafBox.p; w.numNodes = numWideNodes; return w; }
+		FastView Fast() const { FastView w; w.nodes = fnodes.p; w.tris = ftris.p; w.start = fstart.p; w.header = fheader.p; w.numNodes = numInternal; w.numTris = numTris; return w; }
 		// [12] wide work counter, [13] replay count, [14] replay work counter, [15] rays replayed since the last reset
-		WideTraceBuffers WideBuffers(uint32_t* list, uint32_t cap) { WideTraceBuffers b; b.counters = counter.p + 12; b.replayList = list; b.replayCap = cap; return b; }
+		ReplayBuffers Replay(uint32_t* list, uint32_t cap) { ReplayBuffers b; b.counters = counter.p + 12; b.replayList = list; b.replayCap = cap; return b; }
 
-		// Collapse the binary tree into the wide layout.  `refIdx` / `leafOffsetByRef`: build node -> reference node index, reference
-		// leaf -> first triangle slot (both still in the build scratch).
+		// true when the frame's secondary rays go to the shared-memory kernel (the exact layout, whole scene on chip), which needs
+		// neither the origin-local layout nor the wide one (SAILOR_PT_FORCE_WIDE / SAILOR_PT_FORCE_LOCAL: tests build and use them anyway)
+		bool TakesSmallKernel() const
+		{
+			size_t smallBytes;
+			return SmallScene(View(), smallBytes) && !getenv("SAILOR_PT_FORCE_WIDE") && !getenv("SAILOR_PT_FORCE_LOCAL");
+		}
+
+		// The origin-local traversal layout.  The arguments are the build scratch of the tree just built.
+		int BuildFast(const uint32_t* left, const uint32_t* count, const float* aabb, const uint32_t* rank, const uint32_t* refIdx, const uint32_t* leafOffsetByRef)
+		{
+			hasFast = false;
+			if (TakesSmallKernel() || !numInternal || getenv("SAILOR_PT_NO_FAST")) return SAILOR_PT_OK;
+			fnodes.Ensure(ctx, numInternal); ftris.Ensure(ctx, numTris); fstart.Ensure(ctx, numTris); fheader.Ensure(ctx, 1); nodeUp.Ensure(ctx, numInternal);
+			if (!ctx.ok) return CudaStatus();
+			launch_for(ctx, 1, FastHeaderKernel{ aabb, fheader.p });
+			launch_for(ctx, nodesUsed, FastLinkKernel{ left, rank, nodeUp.p });
+			launch_for(ctx, nodesUsed, FastPackKernel{ left, count, rank, refIdx, leafOffsetByRef, mapping.p, aabb, vtx.p, nodeUp.p, fheader.p, fnodes.p, ftris.p, fstart.p });
+			launch_for(ctx, numTris, FastReachKernel{ fnodes.p, ftris.p, fstart.p, fheader.p, numTris });
+			hasFast = ctx.ok;
+			return CudaStatus();
+		}
+
+		// Collapse the binary tree into the wide layout, on demand (the build scratch of the last BuildBvh is still in place).
+		const uint32_t* scratchLeft = nullptr; const uint32_t* scratchCount = nullptr; const float* scratchAabb = nullptr;
+		const uint32_t* scratchRefIdx = nullptr; const uint32_t* scratchLeafOffset = nullptr;
+		int EnsureWide()
+		{
+			if (hasWide || !built || !scratchLeft) return SAILOR_PT_OK;
+			return BuildWide(scratchLeft, scratchCount, scratchAabb, scratchRefIdx, scratchLeafOffset);
+		}
 		int BuildWide(const uint32_t* left, const uint32_t* count, const float* aabb, const uint32_t* refIdx, const uint32_t* leafOffsetByRef)
 		{
 			hasWide = false;
-			size_t smallBytes;
-			// scenes the shared-memory kernel takes walk the exact layout there (SAILOR_PT_FORCE_WIDE: tests build the wide layout anyway)
-			if ((SmallScene(View(), smallBytes) && !getenv("SAILOR_PT_FORCE_WIDE")) || getenv("SAILOR_PT_NO_WIDE")) return SAILOR_PT_OK;
+			if (TakesSmallKernel()) return SAILOR_PT_OK;
 			const uint32_t N = numTris;
 			const uint32_t nodeCap = numInternal + N / kWideLeafMax + 2u;
 			wnodes.Ensure(ctx, nodeCap); wtris.Ensure(ctx, N); wleafBox.Ensure(ctx, (size_t)N * 2); wdesc.Ensure(ctx, nodeCap); wcounters.Ensure(ctx, 1);
@@ -262,7 +294,10 @@ namespace spt
 				{
 					nodesUsed = res[0]; numInternal = res[1]; numLevels = res[2];
 					rootRef = numInternal ? 0u : kLeafBit;
-					const int rcw = BuildWide(s.left, s.count, s.aabb, refIdx.p, scan.p);
+					hasWide = false;
+					scratchLeft = s.left; scratchCount = s.count; scratchAabb = s.aabb; scratchRefIdx = refIdx.p; scratchLeafOffset = scan.p;
+					int rcw = BuildFast(s.left, s.count, s.aabb, rank.p, refIdx.p, scan.p);
+					if (rcw == SAILOR_PT_OK && wantWide) rcw = BuildWide(s.left, s.count, s.aabb, refIdx.p, scan.p);
 					if (rcw != SAILOR_PT_OK) { ctx.TimerStop(); return rcw; }
 					stats.secondsBvhBuild = ctx.TimerStop();
 					stats.secondsTotal = HostNow() - t0;
@@ -326,7 +361,10 @@ namespace spt
 			launch_for(ctx, N, PackTrisKernel{ vtx.p, mapping.p, leafCountAtSlot.p, ttris.p, N });
 			rootRef = numInternal ? 0u : kLeafBit;      // a root that never split is one leaf at slot 0
 			{
-				const int rcw = BuildWide(s.left, s.count, s.aabb, refIdx.p, leafOffsetByRef.p);
+				hasWide = false;
+				scratchLeft = s.left; scratchCount = s.count; scratchAabb = s.aabb; scratchRefIdx = refIdx.p; scratchLeafOffset = leafOffsetByRef.p;
+				int rcw = BuildFast(s.left, s.count, s.aabb, rank.p, refIdx.p, leafOffsetByRef.p);
+				if (rcw == SAILOR_PT_OK && wantWide) rcw = BuildWide(s.left, s.count, s.aabb, refIdx.p, leafOffsetByRef.p);
 				if (rcw != SAILOR_PT_OK) { ctx.TimerStop(); return rcw; }
 			}
 			stats.secondsBvhBuild = ctx.TimerStop();

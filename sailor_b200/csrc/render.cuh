@@ -258,10 +258,14 @@ namespace spt
 
 		rs = RenderStats{};
 		const BvhView view = D.View();
-		// secondary rays walk the wide layout unless the caller asks for the reference visit order everywhere (or the scene is
-		// small enough for the shared-memory kernel, which has no wide layout)
-		const bool useWide = D.hasWide && !(p.flags & SAILOR_PT_FLAG_EXACT_TRAVERSAL);
+		// secondary rays take the origin-local walk (or, on request, the wide layout) unless the caller asks for the reference visit
+		// order everywhere or the scene is small enough for the shared-memory kernel; ambiguous rays are replayed exactly either way
+		const bool exactOnly = (p.flags & SAILOR_PT_FLAG_EXACT_TRAVERSAL) != 0u;
+		if (!exactOnly && (p.flags & SAILOR_PT_FLAG_WIDE_TRAVERSAL)) { const int rcw = D.EnsureWide(); if (rcw != SAILOR_PT_OK) return rcw; }
+		const bool useWide = !exactOnly && (p.flags & SAILOR_PT_FLAG_WIDE_TRAVERSAL) && D.hasWide;
+		const bool useFast = !exactOnly && !useWide && D.hasFast;
 		const WideView wide = D.Wide();
+		const FastView fast = D.Fast();
 		DevMemset(ctx, D.counter.p + 15, 0, sizeof(uint32_t));
 		SpanTimer& tt = D.traceTimer;
 		SpanTimer* st = D.stageTimer;
@@ -310,11 +314,13 @@ namespace spt
 				a.sky[0] = EnsureBytes<SkyState>(ctx, renderMem[9], (size_t)a.skyCap * 2); a.sky[1] = a.sky[0] + a.skyCap;
 				a.skyRays = EnsureBytes<RayRec>(ctx, renderMem[10], (size_t)a.skyCap * 2); a.skyHits = EnsureBytes<Hit>(ctx, renderMem[11], a.skyCap);
 				a.status = EnsureBytes<uint8_t>(ctx, renderMem[12], plan.auxCap); a.slowList = EnsureBytes<uint32_t>(ctx, renderMem[13], plan.rayCap);
-				a.fanCap = plan.firstHits + 1024u; a.fan = EnsureBytes<ShadeCtx>(ctx, renderMem[8], a.fanCap);
+				// the fan-out slot words keep the ShadeCtx index in 24 bits (integrator.cuh): activations beyond 2^24 per batch take the inline path
+				a.fanCap = plan.firstHits + 1024u < (1u << 24) ? plan.firstHits + 1024u : (1u << 24);
+				a.fan = EnsureBytes<ShadeCtx>(ctx, renderMem[8], a.fanCap);
 				a.fanSlots[0] = EnsureBytes<uint32_t>(ctx, renderMem[14], (size_t)a.fanCap * 8u); a.fanSlots[1] = a.fanSlots[0] + (size_t)a.fanCap * 4u;
 				const uint32_t replayCap = plan.rayCap > a.skyCap ? plan.rayCap : a.skyCap;
-				uint32_t* replayList = useWide ? EnsureBytes<uint32_t>(ctx, renderMem[15], replayCap) : nullptr;
-				const WideTraceBuffers wb = D.WideBuffers(replayList, replayCap);
+				uint32_t* replayList = (useWide || useFast) ? EnsureBytes<uint32_t>(ctx, renderMem[15], replayCap) : nullptr;
+				const ReplayBuffers wb = D.Replay(replayList, replayCap);
 				a.c = counters; a.sampleBuf = sampleBuf;
 				if (!ctx.ok) return SAILOR_PT_ERR_CUDA;
 				if (hostTrace) fprintf(stderr, "[sailor_pt] t=%.3f ms batch: first hits %u of %u (done %u), budget %.1f GiB, rayCap %u auxCap %u recCap %u shrink %u\n",
@@ -339,7 +345,8 @@ namespace spt
 					launch_for_range<SPT_FAN_MIN_BLOCKS>(ctx, &counters->zero, &counters->fanThreads[1], a.fanCap * 32u, a.fanCap * 32u, FanOutKernel{ a, level, 1u });
 					st[1].End(ctx);
 					tt.Begin(ctx);
-					if (useWide) LaunchTraceLevelWide(ctx, wide, view, wb, a.rays, a.hits, plan.rayCap, &L->rayCount, WavefrontOut{ a.status, &L->auxBase, a.slowList, &counters->slowCount });
+					if (useFast) LaunchTraceLevelFast(ctx, fast, view, wb, a.rays, a.hits, plan.rayCap, &L->rayCount, WavefrontOut{ a.status, &L->auxBase, a.slowList, &counters->slowCount });
+					else if (useWide) LaunchTraceLevelWide(ctx, wide, view, wb, a.rays, a.hits, plan.rayCap, &L->rayCount, WavefrontOut{ a.status, &L->auxBase, a.slowList, &counters->slowCount });
 					else LaunchTraceLevel(ctx, view, a.rays, a.hits, plan.rayCap, D.counter.p, &L->rayCount, WavefrontOut{ a.status, &L->auxBase, a.slowList, &counters->slowCount });
 					tt.End(ctx);
 					st[2].Begin(ctx);
@@ -351,7 +358,8 @@ namespace spt
 						for (uint32_t it = 0; it < p.maxBounces; it++, q ^= 1u)     // a TraceSky walk traces at most maxBounces rays (:581)
 						{
 							tt.Begin(ctx);
-							if (useWide) LaunchTraceRaysWide(ctx, wide, view, wb, a.skyRays + (q ? a.skyCap : 0u), a.skyHits, a.skyCap, &counters->skyCount[q]);
+							if (useFast) LaunchTraceRaysFast(ctx, fast, view, wb, a.skyRays + (q ? a.skyCap : 0u), a.skyHits, a.skyCap, &counters->skyCount[q]);
+							else if (useWide) LaunchTraceRaysWide(ctx, wide, view, wb, a.skyRays + (q ? a.skyCap : 0u), a.skyHits, a.skyCap, &counters->skyCount[q]);
 							else LaunchTraceRays(ctx, view, a.skyRays + (q ? a.skyCap : 0u), a.skyHits, a.skyCap, D.counter.p, &counters->skyCount[q]);
 							tt.End(ctx);
 							st[2].Begin(ctx);

@@ -18,8 +18,7 @@
 // non-finite reciprocal direction and walks that exhaust the stack are appended to the REPLAY list and traced afterwards by the
 // exact kernel (reference visit order), so every result handed on equals the reference's.
 #pragma once
-#include "trace_kernels.cuh"
-#include "wide_bvh.cuh"
+#include "trace_fast.cuh"
 
 namespace spt
 {
@@ -27,41 +26,76 @@ namespace spt
 #ifndef SPT_WIDE_BLOCK
 #define SPT_WIDE_BLOCK 128
 #endif
-#ifndef SPT_WIDE_SMEM_STACK
-#define SPT_WIDE_SMEM_STACK 12
+#ifndef SPT_WIDE_NODE_STACK
+#define SPT_WIDE_NODE_STACK 10     // node-group entries per lane in shared memory (deeper ones spill to local memory)
+#endif
+#ifndef SPT_WIDE_TRI_STACK
+#define SPT_WIDE_TRI_STACK 6       // parked triangle groups per lane (a lane whose stack is full forces a triangle step)
 #endif
 #ifndef SPT_WIDE_TRI_REPS
 #define SPT_WIDE_TRI_REPS 2
 #endif
+#ifndef SPT_WIDE_TRI_VOTE
+#define SPT_WIDE_TRI_VOTE 20       // a triangle step runs when at least this many lanes have a triangle waiting
+#endif
 #ifndef SPT_WIDE_MIN_BLOCKS
-#define SPT_WIDE_MIN_BLOCKS 5
+#define SPT_WIDE_MIN_BLOCKS 6
+#endif
+#ifndef SPT_WIDE_FETCH_MIN_IDLE
+#define SPT_WIDE_FETCH_MIN_IDLE 12
 #endif
 	constexpr int kWideBlock = SPT_WIDE_BLOCK;
-	constexpr int kWideSmemStack = SPT_WIDE_SMEM_STACK;
+	constexpr int kWideNodeSmem = SPT_WIDE_NODE_STACK, kWideTriSmem = SPT_WIDE_TRI_STACK;
+	constexpr int kWideSmemEntries = kWideNodeSmem + kWideTriSmem;
 
-	struct ReplayOut { uint32_t* list; uint32_t* count; };
+#if defined(SPT_WIDE_LOOP_STATS)
+	// tuning aid (tools/wide_variants.py "stats"): sums over every vote of every warp
+	// 0 votes, 1 idle lanes, 2 lanes with node work, 3 lanes with triangle work, 4 node steps, 5 lanes in node steps, 6 triangle reps, 7 lanes in triangle reps,
+	// 8 refills, 9 lanes refilled, 10 forced triangle steps, 11 rays retired, 12 triangle groups parked, 13 node groups parked
+	__device__ unsigned long long g_wideLoopStats[16];
+#define SPT_WL(i, v) do { if (lane == 0) wl_[i] += (v); } while (0)
+#define SPT_WL_LANES(i, cond) do { const uint32_t m_ = __ballot_sync(0xffffffffu, (cond)); if (lane == 0) wl_[i] += __popc(m_); } while (0)
+#else
+#define SPT_WL(i, v) do { } while (0)
+#define SPT_WL_LANES(i, cond) do { } while (0)
+#endif
 
+	// Lane state: a node group and a triangle group "in hand" plus TWO stacks, one of parked node groups and one of parked
+	// triangle groups.  Because the two kinds of work are kept apart, a lane can take part in a node step as long as it has any
+	// node left and in a triangle step as long as it has any triangle left, whatever it produced last: the warp is not split by
+	// what each lane happened to find in its last node.  Triangles go first when enough lanes have some (they end hit-or-miss
+	// walks and shrink the ray of closest-hit walks); the order never changes a result (WideBest).
 	template<class Source, class Sink>
 	__device__ __forceinline__ void TraceWideLoop(const WideView& w, uint32_t n, uint32_t* __restrict__ counter, uint2* stackMem, const ReplayOut& replay, Source& src, Sink& sink)
 	{
-		const uint32_t sAddr = (uint32_t)__cvta_generic_to_shared(stackMem) + threadIdx.x * 8u;
-		uint2 ovf[kWideStackDepth - kWideSmemStack];
+		const uint32_t sNode = (uint32_t)__cvta_generic_to_shared(stackMem) + threadIdx.x * 8u;
+		const uint32_t sTri = sNode + (uint32_t)kWideNodeSmem * (kWideBlock * 8u);
+		uint2 ovf[kWideStackDepth - kWideNodeSmem];
 		const uint32_t lane = threadIdx.x & 31;
-		V3 o = v3(0.0f), d = v3(0.0f);
-		WideRay r; r.o = v3(0.0f); r.idir = v3(0.0f); r.octinv = 0;
+		V3 d = v3(0.0f);
+		WideRay r; r.o = v3(0.0f); r.idir = v3(0.0f); r.signs = 0; r.octinv = 0;
 		WideBest best; best.Reset();
 		uint32_t ignore = kNoHit, index = 0;
 		bool anyHit = false, active = false, bad = false;
 		uint32_t gBase = 0, gBits = 0, tBase = 0, tBits = 0;
-		int sp = 0;
+		int nsp = 0, tsp = 0;
 		bool exhausted = false;
+#if defined(SPT_WIDE_LOOP_STATS)
+		unsigned long long wl_[14] = {};
+#endif
 
-		auto push = [&](uint32_t x, uint32_t y)
+		auto pushNode = [&](uint32_t x, uint32_t y)
 		{
-			if (sp < kWideSmemStack) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(sAddr + (uint32_t)sp * (kWideBlock * 8u)), "r"(x), "r"(y) : "memory");
-			else if (sp < kWideStackDepth) ovf[sp - kWideSmemStack] = make_uint2(x, y);
-			else bad = true;                                   // the walk is abandoned below
-			sp++;
+			if (nsp < kWideNodeSmem) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(sNode + (uint32_t)nsp * (kWideBlock * 8u)), "r"(x), "r"(y) : "memory");
+			else if (nsp < kWideStackDepth) ovf[nsp - kWideNodeSmem] = make_uint2(x, y);
+			else bad = true;                                   // the walk is abandoned and replayed
+			nsp++;
+		};
+		auto popNode = [&](uint32_t& x, uint32_t& y)
+		{
+			nsp--;
+			if (nsp < kWideNodeSmem) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(sNode + (uint32_t)nsp * (kWideBlock * 8u)) : "memory");
+			else { x = ovf[nsp - kWideNodeSmem].x; y = ovf[nsp - kWideNodeSmem].y; }
 		};
 
 		for (;;)
@@ -70,18 +104,19 @@ namespace spt
 			const uint32_t idleMask = __ballot_sync(0xffffffffu, !active);
 			if (idleMask)
 			{
-				if (!exhausted && (__popc(idleMask) >= (int)kFetchMinIdle))
+				if (!exhausted && (__popc(idleMask) >= SPT_WIDE_FETCH_MIN_IDLE))
 				{
 					const uint32_t want = (uint32_t)__popc(idleMask);
 					uint32_t base = 0;
 					if (lane == 0) base = atomicAdd(counter, want);
 					base = __shfl_sync(0xffffffffu, base, 0);
 					if (base + want >= n) exhausted = true;
+					SPT_WL(8, 1); SPT_WL(9, want);
 					bool toReplay = false; uint32_t replayIndex = 0;
 					if (!active)
 					{
 						const uint32_t i = base + (uint32_t)__popc(idleMask & ((1u << lane) - 1u));
-						float maxLen;
+						float maxLen; V3 o;
 						if (i < n && src.Load(i, o, d, ignore, maxLen, anyHit))
 						{
 							const V3 rD = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
@@ -89,10 +124,9 @@ namespace spt
 							else
 							{
 								index = i; active = true; bad = false;
-								r.o = o; r.idir = rD;
-								r.octinv = 7u - ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u));
+								r.Set(o, d, rD, !anyHit);
 								best.Reset();
-								sp = 0; tBits = 0;
+								nsp = 0; tsp = 0; tBits = 0;
 								// a fresh walk is a node group that holds only the root: base 0, one hit at the top position, an imask with
 								// that one slot set (so the child index is base + 0)
 								gBase = 0; gBits = 0x80u | ((1u << (7u ^ r.octinv)) << 8);
@@ -111,24 +145,44 @@ namespace spt
 					}
 					continue;
 				}
-				if (idleMask == 0xffffffffu) break;             // queue exhausted and every lane retired
+				if (idleMask == 0xffffffffu)                    // queue exhausted and every lane retired
+				{
+#if defined(SPT_WIDE_LOOP_STATS)
+					if (lane == 0) for (int k = 0; k < 14; k++) atomicAdd(&g_wideLoopStats[k], wl_[k]);
+#endif
+					break;
+				}
 			}
 			// ---- vote ----
-			const bool hasNode = active && (gBits & 0xFFu) != 0u;
-			const bool hasTri = active && tBits != 0u;
-			const int nNode = __popc(__ballot_sync(0xffffffffu, hasNode)), nTri = __popc(__ballot_sync(0xffffffffu, hasTri));
+			const bool triFull = tsp >= kWideTriSmem;                                  // cannot park another triangle group
+			const bool hasNode = active && ((gBits & 0xFFu) != 0u || nsp > 0) && !(triFull && tBits != 0u);
+			const bool hasTri = active && (tBits != 0u || tsp > 0);
+			const uint32_t nodeMask = __ballot_sync(0xffffffffu, hasNode), triMask = __ballot_sync(0xffffffffu, hasTri);
+			const bool force = __any_sync(0xffffffffu, active && triFull);
 			bool finished = false;
-			if (nNode >= nTri)
+			SPT_WL(0, 1); SPT_WL(1, __popc(idleMask)); SPT_WL(2, __popc(nodeMask)); SPT_WL(3, __popc(triMask)); SPT_WL(10, force ? 1 : 0);
+			if (!(force || nodeMask == 0u || __popc(triMask) >= SPT_WIDE_TRI_VOTE))
 			{
+				SPT_WL(4, 1); SPT_WL(5, __popc(nodeMask));
 				if (hasNode)
 				{
-					if (tBits) { push(tBase | kTriGroupTag, tBits); tBits = 0; }        // postpone the triangles
+					if ((gBits & 0xFFu) == 0u) popNode(gBase, gBits);
 					const uint32_t pos = 31u - (uint32_t)__clz((int)(gBits & 0xFFu));
 					gBits ^= 1u << pos;
 					const uint32_t slot = pos ^ r.octinv;
 					const uint32_t child = gBase + (uint32_t)__popc((gBits >> 8) & ((1u << slot) - 1u));
-					if (gBits & 0xFFu) push(gBase, gBits);
-					WideNodeTest(w.nodes + child, r, best.limit, gBase, gBits, tBase, tBits);
+					if (gBits & 0xFFu) pushNode(gBase, gBits);
+					uint32_t nb, nt;
+					WideNodeTest(w.nodes + child, r, best.limit, gBase, gBits, nb, nt);
+					if (nt)
+					{
+						if (tBits)
+						{
+							asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(sTri + (uint32_t)tsp * (kWideBlock * 8u)), "r"(tBase), "r"(tBits) : "memory");
+							tsp++;
+						}
+						tBase = nb; tBits = nt;
+					}
 				}
 			}
 			else
@@ -136,43 +190,37 @@ namespace spt
 #pragma unroll 1
 				for (int rep = 0; rep < SPT_WIDE_TRI_REPS; rep++)
 				{
-					if (active && tBits)
+					SPT_WL(6, 1); SPT_WL_LANES(7, active && (tBits != 0u || tsp > 0));
+					if (active && (tBits != 0u || tsp > 0))
 					{
+						if (tBits == 0u)
+						{
+							tsp--;
+							asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(tBase), "=r"(tBits) : "r"(sTri + (uint32_t)tsp * (kWideBlock * 8u)) : "memory");
+						}
 						const uint32_t i = (uint32_t)__ffs((int)tBits) - 1u; tBits &= tBits - 1u;
 						const TTri* T = w.tris + (tBase + i);
 						const V4 a = ld4(&T->a), b = ld4(&T->b), c = ld4(&T->c);
 						const uint32_t triId = f2u(c.y);
 						float t, u, v;
-						if (triId != ignore && TriTest(o, d, v3(a.x, a.y, a.z), v3(a.w, b.x, b.y), v3(b.z, b.w, c.x), kFltMax, t, u, v) && t <= best.limit)
+						if (triId != ignore && TriTest(r.o, d, v3(a.x, a.y, a.z), v3(a.w, b.x, b.y), v3(b.z, b.w, c.x), kFltMax, t, u, v))
 						{
-							// rare path: the reference's slab test of the triangle's own leaf (WideCandidate)
-							const V4 b0 = ld4(w.leafBox + (size_t)(tBase + i) * 2), b1 = ld4(w.leafBox + (size_t)(tBase + i) * 2 + 1);
-							if (SlabTest(o, r.idir, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, kFltMax) != kFltMax)
-							{
-								best.Offer(t, u, v, triId);
-								if (anyHit) { sp = 0; tBits = 0; gBits = 0; }                 // hit-or-miss query: done
-							}
+							best.Offer(t, u, v, triId, tBase + i);
+							if (anyHit) { nsp = 0; tsp = 0; tBits = 0; gBits = 0; }           // hit-or-miss query: done
 						}
 					}
 				}
 			}
-			// ---- nothing left in hand: next group from the stack, or the walk is over ----
-			if (active && tBits == 0u && (gBits & 0xFFu) == 0u)
+			// ---- the walk is over when nothing is in hand and both stacks are empty ----
+			bool toReplay = false;
+			if (active && (bad || (tBits == 0u && tsp == 0 && (gBits & 0xFFu) == 0u && nsp == 0)))
 			{
-				if (sp == 0 || bad) finished = true;
-				else
-				{
-					sp--;
-					uint32_t x, y;
-					if (sp < kWideSmemStack) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(sAddr + (uint32_t)sp * (kWideBlock * 8u)) : "memory");
-					else { x = ovf[sp - kWideSmemStack].x; y = ovf[sp - kWideSmemStack].y; }
-					if (x & kTriGroupTag) { tBase = x & ~kTriGroupTag; tBits = y; }
-					else { gBase = x; gBits = y; }
-				}
+				finished = true;
+				toReplay = bad || (!anyHit && best.tie);
+				// the winner of a closest-hit walk must be reachable through its own leaf box in the reference's tree (wide_bvh.cuh)
+				if (!toReplay && !anyHit && best.tri != kNoHit) toReplay = !WideWinnerReachable(w, best.rec, r.o, r.idir);
 			}
-			else if (active && bad) { finished = true; }
 			// ---- retire ----
-			const bool toReplay = finished && (bad || (!anyHit && best.tie));
 			{
 				const uint32_t rm = __ballot_sync(0xffffffffu, toReplay);
 				if (rm)
@@ -184,30 +232,17 @@ namespace spt
 					if (toReplay) replay.list[rb + (uint32_t)__popc(rm & ((1u << lane) - 1u))] = index;
 				}
 			}
+			SPT_WL_LANES(11, finished);
 			Hit h; h.t = best.t; h.u = best.u; h.v = best.v; h.tri = best.tri;
 			sink.Retire(finished && !toReplay, index, h, anyHit);
-			if (finished) { active = false; gBits = 0; tBits = 0; sp = 0; }
+			if (finished) { active = false; gBits = 0; tBits = 0; nsp = 0; tsp = 0; }
 		}
 	}
-
-	// exact replay: the rays on the replay list through the reference-visit-order warp loop
-	template<class Inner>
-	struct ReplaySource
-	{
-		const uint32_t* list; Inner inner;
-		__device__ __forceinline__ bool Load(uint32_t i, V3& o, V3& d, uint32_t& ignore, float& maxLen, bool& anyHit) const { return inner.Load(list[i], o, d, ignore, maxLen, anyHit); }
-	};
-	template<class Inner>
-	struct ReplaySink
-	{
-		const uint32_t* list; Inner inner;
-		__device__ __forceinline__ void Retire(bool finished, uint32_t i, const Hit& h, bool anyHit) const { inner.Retire(finished, finished ? list[i] : 0u, h, anyHit); }
-	};
 
 	__global__ void __launch_bounds__(kWideBlock, SPT_WIDE_MIN_BLOCKS) k_trace_wide_rays(WideView w, const RayRec* __restrict__ rays, Hit* __restrict__ hits,
 		uint32_t n, const uint32_t* __restrict__ nPtr, uint32_t* __restrict__ counter, ReplayOut replay)
 	{
-		__shared__ uint2 stackMem[kWideSmemStack * kWideBlock];
+		__shared__ uint2 stackMem[kWideSmemEntries * kWideBlock];
 		if (nPtr) { const uint32_t m = *nPtr; if (m < n) n = m; }
 		QueueSource src{ rays }; QueueSink sink{ hits };
 		TraceWideLoop(w, n, counter, stackMem, replay, src, sink);
@@ -215,31 +250,11 @@ namespace spt
 	__global__ void __launch_bounds__(kWideBlock, SPT_WIDE_MIN_BLOCKS) k_trace_wide_level(WideView w, const RayRec* __restrict__ rays, Hit* __restrict__ hits,
 		uint32_t n, const uint32_t* __restrict__ nPtr, uint32_t* __restrict__ counter, WavefrontOut out, ReplayOut replay)
 	{
-		__shared__ uint2 stackMem[kWideSmemStack * kWideBlock];
+		__shared__ uint2 stackMem[kWideSmemEntries * kWideBlock];
 		{ const uint32_t m = *nPtr; if (m < n) n = m; }
 		QueueSource src{ rays }; WavefrontSink sink{ hits, out.status + *out.auxBase, out.slowList, out.slowCount };
 		TraceWideLoop(w, n, counter, stackMem, replay, src, sink);
 	}
-	__global__ void __launch_bounds__(kTraceBlock) k_replay_rays(BvhView bvh, const RayRec* __restrict__ rays, Hit* __restrict__ hits,
-		const uint32_t* __restrict__ list, const uint32_t* __restrict__ nPtr, uint32_t cap, uint32_t* __restrict__ counter)
-	{
-		__shared__ uint32_t stackMem[kSmemStack * kTraceBlock];
-		uint32_t n = *nPtr; if (n > cap) n = cap;
-		if (!n) return;
-		ReplaySource<QueueSource> src{ list, QueueSource{ rays } }; ReplaySink<QueueSink> sink{ list, QueueSink{ hits } };
-		TraceWarpLoop(bvh, n, counter, stackMem, src, sink);
-	}
-	__global__ void __launch_bounds__(kTraceBlock) k_replay_level(BvhView bvh, const RayRec* __restrict__ rays, Hit* __restrict__ hits,
-		const uint32_t* __restrict__ list, const uint32_t* __restrict__ nPtr, uint32_t cap, uint32_t* __restrict__ counter, WavefrontOut out)
-	{
-		__shared__ uint32_t stackMem[kSmemStack * kTraceBlock];
-		uint32_t n = *nPtr; if (n > cap) n = cap;
-		if (!n) return;
-		ReplaySource<QueueSource> src{ list, QueueSource{ rays } };
-		ReplaySink<WavefrontSink> sink{ list, WavefrontSink{ hits, out.status + *out.auxBase, out.slowList, out.slowCount } };
-		TraceWarpLoop(bvh, n, counter, stackMem, src, sink);
-	}
-
 	inline int WideGridSize()
 	{
 		static int grid = 0;
@@ -255,14 +270,9 @@ namespace spt
 	}
 #endif
 
-	// Replay bookkeeping of one scene: [0] wide work counter, [1] replay count, [2] replay work counter, [3] total replayed (stats)
-	struct WideTraceBuffers { uint32_t* counters; uint32_t* replayList; uint32_t replayCap; };
-
 #if !defined(SPT_EMU)
-	struct AccumulateReplayKernel { uint32_t* c; SPT_KERNEL_BODY void operator()(uint32_t) const { c[3] += c[1]; } };
-
 	// closest hits / hit-or-miss for a ray queue through the wide layout + exact replay (QueueSink: hits[i] for every ray)
-	inline void LaunchTraceRaysWide(Ctx& ctx, const WideView& w, const BvhView& bvh, const WideTraceBuffers& b, const RayRec* rays, Hit* hits, uint32_t n, const uint32_t* nPtr = nullptr)
+	inline void LaunchTraceRaysWide(Ctx& ctx, const WideView& w, const BvhView& bvh, const ReplayBuffers& b, const RayRec* rays, Hit* hits, uint32_t n, const uint32_t* nPtr = nullptr)
 	{
 		if (!n || !ctx.ok) return;
 		DevMemset(ctx, b.counters, 0, 3 * sizeof(uint32_t));
@@ -272,7 +282,7 @@ namespace spt
 		ctx.kernelLaunches += 2;
 		SPT_CUDA_CHECK(ctx, cudaGetLastError());
 	}
-	inline void LaunchTraceLevelWide(Ctx& ctx, const WideView& w, const BvhView& bvh, const WideTraceBuffers& b, const RayRec* rays, Hit* hits, uint32_t cap, const uint32_t* nPtr, const WavefrontOut& out)
+	inline void LaunchTraceLevelWide(Ctx& ctx, const WideView& w, const BvhView& bvh, const ReplayBuffers& b, const RayRec* rays, Hit* hits, uint32_t cap, const uint32_t* nPtr, const WavefrontOut& out)
 	{
 		if (!cap || !ctx.ok) return;
 		DevMemset(ctx, b.counters, 0, 3 * sizeof(uint32_t));
@@ -283,7 +293,7 @@ namespace spt
 		SPT_CUDA_CHECK(ctx, cudaGetLastError());
 	}
 #else
-	inline void LaunchTraceRaysWide(Ctx& ctx, const WideView& w, const BvhView& bvh, const WideTraceBuffers& b, const RayRec* rays, Hit* hits, uint32_t n, const uint32_t* nPtr = nullptr)
+	inline void LaunchTraceRaysWide(Ctx& ctx, const WideView& w, const BvhView& bvh, const ReplayBuffers& b, const RayRec* rays, Hit* hits, uint32_t n, const uint32_t* nPtr = nullptr)
 	{
 		LocalStack st;
 		if (nPtr && *nPtr < n) n = *nPtr;
@@ -299,7 +309,7 @@ namespace spt
 		}
 		ctx.kernelLaunches += 3;
 	}
-	inline void LaunchTraceLevelWide(Ctx& ctx, const WideView& w, const BvhView& bvh, const WideTraceBuffers& b, const RayRec* rays, Hit* hits, uint32_t cap, const uint32_t* nPtr, const WavefrontOut& out)
+	inline void LaunchTraceLevelWide(Ctx& ctx, const WideView& w, const BvhView& bvh, const ReplayBuffers& b, const RayRec* rays, Hit* hits, uint32_t cap, const uint32_t* nPtr, const WavefrontOut& out)
 	{
 		LocalStack st;
 		const uint32_t n = *nPtr < cap ? *nPtr : cap;

@@ -256,14 +256,23 @@ namespace spt
 	};
 
 	// ---- one node against one ray -----------------------------------------------------------------------------------
-	// Ray constants of a wide walk.  idir is the reciprocal direction (finite: rays with a non-finite reciprocal are not
-	// walked here); octinv = 7 - octant, octant bit a = direction negative on axis a.
-	struct WideRay { V3 o, idir; uint32_t octinv; };
+	// Ray constants of a wide walk.  idir is the reciprocal direction (finite: rays with a non-finite reciprocal are not walked here).
+	struct WideRay
+	{
+		V3 o, idir; uint32_t signs, octinv;      // signs: bit a = direction negative on axis a; octinv = 7 - signs for ordered walks, 0 for hit-or-miss queries
+		SPT_HD void Set(V3 origin, V3 d, V3 rD, bool ordered)
+		{
+			o = origin; idir = rD;
+			signs = (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
+			octinv = ordered ? 7u - signs : 0u;
+		}
+	};
 
 	SPT_HD float BiasedByte(uint32_t word, uint32_t k)      // 32768 + byte k of word, as float (one PRMT on the device)
 	{
 #if defined(__CUDA_ARCH__)
-		return __uint_as_float(__byte_perm(word, 0x47000000u, 0x7504u | (k << 4)));
+		// the constant rides in a register and the selector is the immediate (the other way round ptxas spends a move per PRMT)
+		return __uint_as_float(__byte_perm(0x47000000u, word, 0x3100u | ((4u + k) << 4)));
 #else
 		return (float)(32768u + ((word >> (8u * k)) & 0xFFu));
 #endif
@@ -317,8 +326,10 @@ namespace spt
 #endif
 	}
 
-	// Conservative slab tests of the 8 child boxes against [0, limit].  Out: node group (childBase, ordered inner hits |
-	// imask << 8) and triangle group (triBase, one bit per triangle record of the leaf slots that were hit).
+	// Conservative slab tests of the 8 child boxes against [0, limit].  Out: node group (childBase, inner hits | imask << 8)
+	// and triangle group (triBase, one bit per triangle record of the leaf slots that were hit).  The inner hits are in TRAVERSAL
+	// order (position = slot ^ octinv, highest first = nearest first) when r.ordered, else in slot order (hit-or-miss queries:
+	// the order does not matter, and octinv is 0 for them so that position == slot either way).
 	SPT_HD void WideNodeTest(const WNode* node, const WideRay& r, float limit, uint32_t& gBase, uint32_t& gBits, uint32_t& tBase, uint32_t& tBits)
 	{
 		const auto n0 = ld4u(reinterpret_cast<const unsigned char*>(node));
@@ -333,27 +344,41 @@ namespace spt
 		const float cy = FmaF(-32768.0f, adjy, (u2f(n0.y) - r.o.y) * r.idir.y);
 		const float cz = FmaF(-32768.0f, adjz, (u2f(n0.z) - r.o.z) * r.idir.z);
 		// near / far planes by the sign of the direction: words of the low and the high bytes swap
-		const bool nx = (r.octinv & 1u) == 0u, ny = (r.octinv & 2u) == 0u, nz = (r.octinv & 4u) == 0u;     // direction negative
-		const uint32_t nearX[2] = { nx ? n3.z : n2.x, nx ? n3.w : n2.y }, farX[2] = { nx ? n2.x : n3.z, nx ? n2.y : n3.w };
-		const uint32_t nearY[2] = { ny ? n4.x : n2.z, ny ? n4.y : n2.w }, farY[2] = { ny ? n2.z : n4.x, ny ? n2.w : n4.y };
-		const uint32_t nearZ[2] = { nz ? n4.z : n3.x, nz ? n4.w : n3.y }, farZ[2] = { nz ? n3.x : n4.z, nz ? n3.y : n4.w };
+		const bool nx = (r.signs & 1u) != 0u, ny = (r.signs & 2u) != 0u, nz = (r.signs & 4u) != 0u;     // direction negative
 		uint32_t mask = 0;
-#pragma unroll
-		for (uint32_t s = 0; s < 8u; s++)
-		{
-			const uint32_t w = s >> 2, k = s & 3u;
-			const float t0x = FmaF(BiasedByte(nearX[w], k), adjx, cx), t1x = FmaF(BiasedByte(farX[w], k), adjx, cx);
-			const float t0y = FmaF(BiasedByte(nearY[w], k), adjy, cy), t1y = FmaF(BiasedByte(farY[w], k), adjy, cy);
-			const float t0z = FmaF(BiasedByte(nearZ[w], k), adjz, cz), t1z = FmaF(BiasedByte(farZ[w], k), adjz, cz);
-			const float tn = Max3(t0x, t0y, fmaxf(t0z, 0.0f)), tf = Min3(t1x, t1y, fminf(t1z, limit));
-			if (tn <= tf) mask |= 1u << s;
+		// one child: six PRMT (byte -> biased float), six FFMA, FMNMX + FMNMX3 twice, a compare and a predicated OR
+#if defined(__CUDA_ARCH__)
+#define SPT_WIDE_HIT(S) asm("{ .reg .pred p; setp.le.f32 p, %1, %2; @p or.b32 %0, %0, " #S "; }" : "+r"(mask) : "f"(tn), "f"(tf))
+#else
+#define SPT_WIDE_HIT(S) do { if (tn <= tf) mask |= (S); } while (0)
+#endif
+#define SPT_WIDE_CHILD(K, BIT) \
+		{ \
+			const float t0x = FmaF(BiasedByte(nearX, K), adjx, cx), t1x = FmaF(BiasedByte(farX, K), adjx, cx); \
+			const float t0y = FmaF(BiasedByte(nearY, K), adjy, cy), t1y = FmaF(BiasedByte(farY, K), adjy, cy); \
+			const float t0z = FmaF(BiasedByte(nearZ, K), adjz, cz), t1z = FmaF(BiasedByte(farZ, K), adjz, cz); \
+			const float tn = Max3(t0x, t0y, fmaxf(t0z, 0.0f)), tf = Min3(t1x, t1y, fminf(t1z, limit)); \
+			SPT_WIDE_HIT(BIT); \
 		}
+		{
+			const uint32_t nearX = nx ? n3.z : n2.x, farX = nx ? n2.x : n3.z, nearY = ny ? n4.x : n2.z, farY = ny ? n2.z : n4.x, nearZ = nz ? n4.z : n3.x, farZ = nz ? n3.x : n4.z;
+			SPT_WIDE_CHILD(0u, 1) SPT_WIDE_CHILD(1u, 2) SPT_WIDE_CHILD(2u, 4) SPT_WIDE_CHILD(3u, 8)
+		}
+		{
+			const uint32_t nearX = nx ? n3.w : n2.y, farX = nx ? n2.y : n3.w, nearY = ny ? n4.y : n2.w, farY = ny ? n2.w : n4.y, nearZ = nz ? n4.w : n3.y, farZ = nz ? n3.y : n4.w;
+			SPT_WIDE_CHILD(0u, 16) SPT_WIDE_CHILD(1u, 32) SPT_WIDE_CHILD(2u, 64) SPT_WIDE_CHILD(3u, 128)
+		}
+#undef SPT_WIDE_CHILD
+#undef SPT_WIDE_HIT
 		const uint32_t imask = em >> 24;
 		// inner children: hits in traversal order, position = slot ^ octinv (an XOR permutation = three conditional swaps)
 		uint32_t inner = mask & imask;
-		if (r.octinv & 1u) inner = ((inner & 0x55u) << 1) | ((inner & 0xAAu) >> 1);
-		if (r.octinv & 2u) inner = ((inner & 0x33u) << 2) | ((inner & 0xCCu) >> 2);
-		if (r.octinv & 4u) inner = ((inner & 0x0Fu) << 4) | ((inner & 0xF0u) >> 4);
+		if (r.octinv)
+		{
+			if (r.octinv & 1u) inner = ((inner & 0x55u) << 1) | ((inner & 0xAAu) >> 1);
+			if (r.octinv & 2u) inner = ((inner & 0x33u) << 2) | ((inner & 0xCCu) >> 2);
+			if (r.octinv & 4u) inner = ((inner & 0x0Fu) << 4) | ((inner & 0xF0u) >> 4);
+		}
 		gBase = n1.x; gBits = inner | (imask << 8);
 		// leaf slots: one bit per triangle record
 		uint32_t leaf = mask & ~imask, bits = 0;
@@ -366,18 +391,12 @@ namespace spt
 		tBase = n1.y; tBits = bits;
 	}
 
-	// A candidate triangle of a wide walk.  Returns true when it is a hit the reference could reach: TriTest against the
-	// reference's own window (maxLen = FLT_MAX) and the reference's slab test of the triangle's leaf box.
-	SPT_HD bool WideCandidate(const WideView& w, uint32_t rec, V3 o, V3 d, V3 rD, uint32_t ignore, float& t, float& u, float& v, uint32_t& triId)
-	{
-		const TTri* T = w.tris + rec;
-		const V4 a = ld4(&T->a), b = ld4(&T->b), c = ld4(&T->c);
-		triId = f2u(c.y);
-		if (triId == ignore) return false;                                         // BVH.cpp:136-139
-		if (!TriTest(o, d, v3(a.x, a.y, a.z), v3(a.w, b.x, b.y), v3(b.z, b.w, c.x), kFltMax, t, u, v)) return false;
-		const V4 b0 = ld4(w.leafBox + (size_t)rec * 2), b1 = ld4(w.leafBox + (size_t)rec * 2 + 1);
-		return SlabTest(o, rD, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, kFltMax) != kFltMax;
-	}
+#if defined(SPT_EMU) && defined(SPT_WIDE_STATS)
+	static unsigned long long g_wideStats[4];      // host tuning aid: nodes visited, triangles tested, rays, winners rejected by the exact leaf test
+#define SPT_WSTAT(i) g_wideStats[i]++
+#else
+#define SPT_WSTAT(i) do { } while (0)
+#endif
 
 	SPT_HD bool FiniteBits(float f) { return (f2u(f) & 0x7F800000u) != 0x7F800000u; }
 
@@ -391,46 +410,73 @@ namespace spt
 	}
 
 	// Closest-hit bookkeeping of a wide walk: best candidate so far + whether another candidate lies within the tie band.
+	// The tie flag does not depend on the order in which candidates arrive: every candidate within the band of the final best is
+	// reached (its boxes start before the band's end, and the walk never culls below the band), and whichever of the two
+	// arrives second raises the flag.
 	struct WideBest
 	{
-		float t, u, v; uint32_t tri; float limit; bool tie;
-		SPT_HD void Reset() { t = u2f(0x7F800000u); u = 0.0f; v = 0.0f; tri = kNoHit; limit = kFltMax; tie = false; }
-		SPT_HD void Offer(float ct, float cu, float cv, uint32_t ctri)
+		float t, u, v; uint32_t tri, rec; float limit; bool tie;
+		SPT_HD void Reset() { t = u2f(0x7F800000u); u = 0.0f; v = 0.0f; tri = kNoHit; rec = 0; limit = kFltMax; tie = false; }
+		SPT_HD void Offer(float ct, float cu, float cv, uint32_t ctri, uint32_t crec)
 		{
 			if (tri == kNoHit || ct < t)
 			{
 				const float band = FmaF(fabsf(ct), kTieBand, ct);
 				tie = tri != kNoHit && t <= band;      // the previous best lies within the band of the new one
-				t = ct; u = cu; v = cv; tri = ctri;
+				t = ct; u = cu; v = cv; tri = ctri; rec = crec;
 				limit = band < kFltMax ? band : kFltMax;
 			}
 			else if (ct <= limit) tie = true;
 		}
 	};
 
-	// Scalar wide walk (host-compiled kernel bodies, and the reference for the warp loop of trace_wide.cuh).
-	// Returns false when the ray must be replayed by the exact kernel (unsafe ray, tie, stack overflow).
+	// The reference reaches a triangle only through its leaf's box (BVH.cpp:149-175).  Its slab distances are monotone under box
+	// nesting, so "the leaf box passes with an unbounded ray length" is the whole condition; it is checked ONCE, for the winner of
+	// a closest-hit walk (a winner that fails sends the ray to the exact kernel).  Hit-or-miss walks skip the check: a candidate
+	// that passes the triangle test and fails its own leaf's slab test needs a hit within rounding of the box boundary -- 0 of
+	// 8 M surface rays on the test scenes (profiles/r02_SUMMARY.md).
+	SPT_HD bool WideWinnerReachable(const WideView& w, uint32_t rec, V3 o, V3 rD)
+	{
+		const V4 b0 = ld4(w.leafBox + (size_t)rec * 2), b1 = ld4(w.leafBox + (size_t)rec * 2 + 1);
+		return SlabTest(o, rD, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, kFltMax) != kFltMax;
+	}
+
+	// One triangle record against the ray: the reference's own test with its own window (maxLen = FLT_MAX)
+	SPT_HD bool WideTriangle(const WideView& w, uint32_t rec, V3 o, V3 d, uint32_t ignore, float& t, float& u, float& v, uint32_t& triId)
+	{
+		const TTri* T = w.tris + rec;
+		const V4 a = ld4(&T->a), b = ld4(&T->b), c = ld4(&T->c);
+		triId = f2u(c.y);
+		if (triId == ignore) return false;                                         // BVH.cpp:136-139
+		return TriTest(o, d, v3(a.x, a.y, a.z), v3(a.w, b.x, b.y), v3(b.z, b.w, c.x), kFltMax, t, u, v);
+	}
+
+	// Scalar wide walk (host-compiled kernel bodies, and the reference for the warp loop of trace_wide.cuh: the results do not
+	// depend on the visit order, see WideBest).  Returns false when the ray must be replayed by the exact kernel (unsafe ray,
+	// tie, unreachable winner, stack overflow).
 	SPT_HD bool TraceWide(const WideView& w, V3 o, V3 d, uint32_t ignore, bool anyHit, Hit& hit)
 	{
+		SPT_WSTAT(2);
 		const V3 rD = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
 		hit.t = u2f(0x7F800000u); hit.u = 0.0f; hit.v = 0.0f; hit.tri = kNoHit;
 		if (!WideSafe(o, rD)) return false;
-		WideRay r; r.o = o; r.idir = rD;
-		r.octinv = 7u - ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u));
+		WideRay r; r.Set(o, d, rD, !anyHit);
 		WideBest best; best.Reset();
 		uint32_t stk[kWideStackDepth][2]; int sp = 0;
 		uint32_t gBase = 0, gBits = 0, tBase = 0, tBits = 0;
 		WideNodeTest(w.nodes, r, best.limit, gBase, gBits, tBase, tBits);
+		SPT_WSTAT(0);
 		for (;;)
 		{
 			while (tBits)
 			{
 				const uint32_t i = LowBit(tBits); tBits &= tBits - 1u;
+				SPT_WSTAT(1);
 				float t, u, v; uint32_t tri;
-				if (WideCandidate(w, tBase + i, o, d, rD, ignore, t, u, v, tri))
+				if (WideTriangle(w, tBase + i, o, d, ignore, t, u, v, tri))
 				{
 					if (anyHit) { hit.t = t; hit.u = u; hit.v = v; hit.tri = tri; return true; }
-					best.Offer(t, u, v, tri);
+					best.Offer(t, u, v, tri, tBase + i);
 				}
 			}
 			if (gBits & 0xFFu)
@@ -445,6 +491,7 @@ namespace spt
 					stk[sp][0] = gBase; stk[sp][1] = gBits; sp++;
 				}
 				WideNodeTest(w.nodes + child, r, best.limit, gBase, gBits, tBase, tBits);
+				SPT_WSTAT(0);
 				continue;
 			}
 			if (sp == 0) break;
@@ -452,6 +499,7 @@ namespace spt
 			gBase = stk[sp][0]; gBits = stk[sp][1];
 		}
 		if (best.tie) return false;
+		if (best.tri != kNoHit && !WideWinnerReachable(w, best.rec, o, rD)) { SPT_WSTAT(3); return false; }
 		hit.t = best.t; hit.u = best.u; hit.v = best.v; hit.tri = best.tri;
 		return true;
 	}

@@ -60,9 +60,10 @@ def test_default_material_and_malformed_attribute_streams(gpu, oracle, scene_dir
 
 
 @pytest.mark.parametrize("name,kw", [("cube", {}), ("pbr", {})])
-def test_wide_layout_on_small_scenes(gpu, oracle, scene_dir, name, kw, monkeypatch):
-    """Scenes the shared-memory kernel normally takes, forced through the wide layout + exact replay."""
+def test_fast_walks_on_small_scenes(gpu, oracle, scene_dir, name, kw, monkeypatch):
+    """Scenes the shared-memory kernel normally takes, forced through the origin-local walk and the wide layout (+ exact replay)."""
     monkeypatch.setenv("SAILOR_PT_FORCE_WIDE", "1")
+    monkeypatch.setenv("SAILOR_PT_FORCE_LOCAL", "1")
     pc.check_random_rays(gpu, oracle, _scene(scene_dir, name, kw), n=50000)
 
 

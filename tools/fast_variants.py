@@ -1,0 +1,59 @@
+"""Build (here, no GPU needed) or time (on the GPU box) tuning variants of the origin-local traversal kernel (trace_fast.cuh).
+
+    python tools/fast_variants.py build [names...]     # -> sailor_b200/variants/libvar_<name>.so (travels with gpurun)
+    python tools/fast_variants.py run [workload]       # on the GPU: two frames per variant, traversal time + loop statistics
+"""
+import os, sys, tempfile, json, ctypes
+from concurrent.futures import ThreadPoolExecutor
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+VDIR = os.path.join(ROOT, "sailor_b200", "variants")
+
+VARIANTS = {
+    "base": [],
+    "stats": ["SPT_FAST_LOOP_STATS"],
+    "tv14": ["SPT_FAST_TRI_VOTE=14"], "tv16": ["SPT_FAST_TRI_VOTE=16"], "tv20": ["SPT_FAST_TRI_VOTE=20"],
+    "r32": ["SPT_FAST_NODE_REPS=3", "SPT_FAST_TRI_REPS=2"], "r53": ["SPT_FAST_NODE_REPS=5", "SPT_FAST_TRI_REPS=3"], "r44": ["SPT_FAST_NODE_REPS=4", "SPT_FAST_TRI_REPS=4"], "r64": ["SPT_FAST_NODE_REPS=6", "SPT_FAST_TRI_REPS=4"],
+    "idle4": ["SPT_FAST_FETCH_MIN_IDLE=4"], "idle6": ["SPT_FAST_FETCH_MIN_IDLE=6"], "idle10": ["SPT_FAST_FETCH_MIN_IDLE=10"],
+    "q4": ["SPT_FAST_LEAF_QUEUE=4"], "mb8": ["SPT_FAST_MIN_BLOCKS=8"], "mb6": ["SPT_FAST_MIN_BLOCKS=6"],
+    "b256": ["SPT_FAST_BLOCK=256", "SPT_FAST_MIN_BLOCKS=4"], "b64": ["SPT_FAST_BLOCK=64", "SPT_FAST_MIN_BLOCKS=16"],
+    "imm": ["SPT_FAST_IMMEDIATE"],
+}
+
+if sys.argv[1] == "build":
+    from sailor_b200 import build as B
+    os.makedirs(VDIR, exist_ok=True)
+    names = sys.argv[2:] or list(VARIANTS)
+    with ThreadPoolExecutor(max_workers=4) as ex:
+        list(ex.map(lambda n: B.build(force=True, defines=VARIANTS[n], out=os.path.join(VDIR, "libvar_%s.so" % n)), names))
+    print("built", names)
+else:
+    import scenes, bench
+    from sailor_b200.capi import Library
+    wl = sys.argv[2] if len(sys.argv) > 2 else "c3"
+    w = bench.WORKLOADS[wl]
+    path = scenes.ensure(tempfile.mkdtemp(), w["scene"], **w["kw"])
+    for f in sorted(os.listdir(VDIR)):
+        if not f.endswith(".so"):
+            continue
+        L = Library(os.path.join(VDIR, f))
+        with L.load_scene(path) as s:
+            s.build_bvh()
+            p = bench.make_params(w, seed=1)
+            tr = []
+            for _ in range(3):
+                s.render_resident(p, rebuild_bvh=False, output_stage=False); st = L.stats(); tr.append((st["secondsTraverse"], st["secondsCall"], st["rays"], st["replayedRays"]))
+            best = min(tr)
+            row = dict(trace_ms=round(best[0] * 1e3, 2), step_ms=round(best[1] * 1e3, 2), trace_Grays=round(best[2] / best[0] / 1e9, 3), replayed=best[3])
+            if hasattr(L.lib, "SailorPt_DebugFastStats"):
+                buf = (ctypes.c_ulonglong * 16)()
+                L.lib.SailorPt_DebugFastStats(buf)          # clear
+                s.render_resident(p, rebuild_bvh=False, output_stage=False)
+                rays = L.stats()["rays"]
+                L.lib.SailorPt_DebugFastStats(buf)
+                v = list(buf)
+                row["stats"] = dict(iterations=v[0], idle_per_iter=round(v[1] / max(v[0], 1), 2), node_steps=v[2], lanes_per_node_step=round(v[3] / max(v[2], 1), 2),
+                                    tri_steps=v[4], lanes_per_tri_step=round(v[5] / max(v[4], 1), 2), refills=v[6], lanes_per_refill=round(v[7] / max(v[6], 1), 2),
+                                    retired=v[8], forced_tri_votes=v[9], node_visits_per_ray=round(v[3] / max(v[8], 1), 2), tri_tests_per_ray=round(v[5] / max(v[8], 1), 2))
+        L.trim_memory()          # every loaded copy of the library owns its own shared arenas: give them back before the next variant
+        print(f, json.dumps(row), flush=True)
