@@ -59,7 +59,9 @@ typedef struct SailorPtParams {
 	uint64_t seed;                /* RNG stream key; the reference uses unseeded rand() */
 	uint32_t rowBegin, rowEnd;    /* render only image rows [rowBegin,rowEnd) of the task grid (multi-GPU shard); 0,0 = all */
 	uint32_t msaaBegin, msaaEnd;  /* render only primary-sample indices [msaaBegin,msaaEnd); 0,0 = all */
-	int32_t deviceCount;          /* SailorPt_Run / SailorPt_RenderMulti: CUDA devices to spread the frame over; 0 or 1 = the current device only */
+	int32_t deviceCount;          /* SailorPt_Run / SailorPt_Render / SailorPt_RenderResident: CUDA devices to spread the frame over, starting at the
+	                                 scene's own device; clamped to the devices of the box; 0 or 1 = the scene's device only.  Row bands are handed out
+	                                 dynamically, the frame is bit-identical to the single-device one (replaces the tile loop of PathTracer.cpp:418-487) */
 	uint32_t flags;               /* SAILOR_PT_FLAG_*; 0 = default */
 } SailorPtParams;
 
@@ -114,6 +116,8 @@ typedef struct SailorPtStats {
 	uint64_t fanOutSamples;   /* rays emitted by FanOutKernel */
 	double secondsCall;       /* product, RenderResident: the whole call between two CUDA events on the launch stream (BVH build + render + output stage) */
 	uint64_t replayedRays;    /* product: rays of the last call that the fast secondary-ray walk handed to the exact (reference visit order) kernel */
+	uint32_t devicesUsed;     /* product, render calls: CUDA devices the frame was spread over (SailorPtParams::deviceCount, clamped to what the box has) */
+	uint32_t reserved0;
 } SailorPtStats;
 
 /* ---- the reference entry points (PathTracer.h:34-36) ---- */

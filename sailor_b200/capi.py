@@ -43,6 +43,7 @@ class SailorPtStats(C.Structure):
         ("batches", C.c_uint32), ("h2dBytes", C.c_uint64), ("d2hBytes", C.c_uint64),
         ("secondsExpand", C.c_double), ("secondsFanOut", C.c_double), ("secondsClassify", C.c_double), ("secondsGather", C.c_double),
         ("fanOutSamples", C.c_uint64), ("secondsCall", C.c_double), ("replayedRays", C.c_uint64),
+        ("devicesUsed", C.c_uint32), ("reserved0", C.c_uint32),
     ]
 
     def as_dict(self):

@@ -3,6 +3,7 @@
 #include "../../include/sailor_pt.h"
 #include <chrono>
 #include <stdio.h>
+#include <array>
 #include <mutex>
 #include <unordered_map>
 #include <thread>
@@ -123,19 +124,20 @@ namespace spt
 	{
 		std::mutex g_allocMutex;
 		std::unordered_map<void*, cudaStream_t> g_allocStream;
-		bool g_poolReady = false;
+		uint64_t g_poolReady = 0;            // bit d: the release threshold of device d's default pool has been lifted
 
 		void EnsurePool()
 		{
-			if (g_poolReady) return;
 			int dev = 0; cudaMemPool_t pool = nullptr;
-			if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
+			if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return; }
+			if (dev < 64 && (g_poolReady >> dev & 1u)) return;
+			if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
 			{
 				uint64_t threshold = UINT64_MAX;
 				cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
 			}
 			cudaGetLastError();
-			g_poolReady = true;
+			if (dev < 64) g_poolReady |= 1ull << dev;
 		}
 	}
 
@@ -151,6 +153,14 @@ namespace spt
 		return p;
 	}
 	int DevCurrent() { int d = 0; if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); d = 0; } return d; }
+	int DevCount() { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); n = 0; } return n; }
+	bool DevSetCurrent(int device) { if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return false; } return true; }
+	void DevCopyPeer(Ctx& ctx, void* dst, int dstDevice, const void* src, int srcDevice, size_t bytes)
+	{
+		if (!ctx.ok || !bytes) return;
+		if (dstDevice == srcDevice) SPT_CUDA_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx.stream));
+		else SPT_CUDA_CHECK(ctx, cudaMemcpyPeerAsync(dst, dstDevice, src, srcDevice, bytes, ctx.stream));
+	}
 	void TrimDevicePool()
 	{
 		int dev = 0; cudaMemPool_t pool = nullptr;
@@ -198,20 +208,28 @@ namespace spt
 		constexpr size_t kStageChunk = 8u << 20;
 		std::mutex g_stageMutex;
 		unsigned char* g_stage[2] = { nullptr, nullptr };
-		cudaEvent_t g_stageEv[2] = { nullptr, nullptr };
+		std::unordered_map<int, std::array<cudaEvent_t, 2>> g_stageEvByDevice;     // an event belongs to the device it was created on
+		cudaEvent_t* g_stageEv = nullptr;          // the current device's pair (valid under g_stageMutex after EnsureStage)
 
 		bool EnsureStage()
 		{
-			if (g_stage[0]) return true;
-			for (int k = 0; k < 2; k++)
+			if (!g_stage[0])
+				for (int k = 0; k < 2; k++)
+					if (cudaHostAlloc((void**)&g_stage[k], kStageChunk, cudaHostAllocPortable) != cudaSuccess)
+					{
+						cudaGetLastError();
+						for (int j = 0; j < 2; j++) { if (g_stage[j]) cudaFreeHost(g_stage[j]); g_stage[j] = nullptr; }
+						return false;
+					}
+			const int dev = DevCurrent();
+			auto it = g_stageEvByDevice.find(dev);
+			if (it == g_stageEvByDevice.end())
 			{
-				if (cudaHostAlloc((void**)&g_stage[k], kStageChunk, cudaHostAllocDefault) != cudaSuccess || cudaEventCreateWithFlags(&g_stageEv[k], cudaEventDisableTiming) != cudaSuccess)
-				{
-					cudaGetLastError();
-					for (int j = 0; j < 2; j++) { if (g_stage[j]) cudaFreeHost(g_stage[j]); g_stage[j] = nullptr; }
-					return false;
-				}
+				std::array<cudaEvent_t, 2> ev{ nullptr, nullptr };
+				for (int k = 0; k < 2; k++) if (cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return false; }
+				it = g_stageEvByDevice.emplace(dev, ev).first;
 			}
+			g_stageEv = it->second.data();
 			return true;
 		}
 
@@ -335,14 +353,8 @@ namespace spt
 
 	int RangeGridBlocks()
 	{
-		static int blocks = 0;
-		if (!blocks)
-		{
-			int dev = 0, sms = 148;
-			cudaGetDevice(&dev);
-			cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-			blocks = sms * 8;
-		}
+		// one value per process: the devices of one box are identical (initialised once, thread-safe)
+		static const int blocks = [] { int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); return sms * 8; }();
 		return blocks;
 	}
 
@@ -498,6 +510,9 @@ namespace spt
 	void DevFreeBytes(void* p) { free(p); }
 	size_t DevMemAvailable() { return (size_t)4 << 30; }
 	int DevCurrent() { return 0; }
+	int DevCount() { return 1; }
+	bool DevSetCurrent(int device) { return device == 0; }
+	void DevCopyPeer(Ctx&, void* dst, int, const void* src, int, size_t bytes) { memcpy(dst, src, bytes); }
 	void TrimDevicePool() {}
 	void* DevAllocPlain(Ctx&, size_t bytes) { return malloc(bytes ? bytes : 1); }
 	void DevFreePlain(void* p) { free(p); }

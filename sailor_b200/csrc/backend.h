@@ -63,6 +63,10 @@ namespace spt
 
 	void* DevAllocBytes(Ctx& ctx, size_t bytes);
 	int DevCurrent();                  // index of the current CUDA device (emu: 0)
+	int DevCount();                    // CUDA devices visible to the process (emu: 1)
+	bool DevSetCurrent(int device);    // make `device` current for the calling host thread
+	// copy between two devices on ctx.stream (falls back to a staged copy inside the driver when the pair has no peer access)
+	void DevCopyPeer(Ctx& ctx, void* dst, int dstDevice, const void* src, int srcDevice, size_t bytes);
 	void TrimDevicePool();             // hand the stream-ordered pool's cached memory back to the driver (emu: no-op)
 	// allocations that outlive the context (stream) they were made from: plain cudaMalloc / cudaFree, not stream-ordered
 	void* DevAllocPlain(Ctx& ctx, size_t bytes);

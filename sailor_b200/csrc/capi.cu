@@ -9,13 +9,19 @@
 #include "render.cuh"
 #include "output.cuh"
 
+#include <atomic>
 #include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
+#include <sys/stat.h>
 
 using namespace spt;
 
-struct SailorPtScene { SceneDevice dev; };
+// `dev` is the scene on the device it was loaded on; `replicas` are copies on further devices, made on demand by a multi-device
+// render (SailorPtParams::deviceCount > 1) from the same parsed file and kept for the following frames.
+struct SailorPtScene { SceneDevice dev; std::vector<std::unique_ptr<SceneDevice>> replicas; };
 
 namespace
 {
@@ -23,6 +29,49 @@ namespace
 	SailorPtStats g_stats{};
 
 	int SetError(int code, const std::string& msg) { t_lastError = msg; return code; }
+
+	// ---- parsed-scene cache --------------------------------------------------------------------------------------------------
+	// A host that renders the same file frame after frame (the reference's PathTracer::Run loads its model on every call,
+	// PathTracer.cpp:84-100) pays the glTF parse and the image decodes once: entries are keyed by (real path, mtime, size) of the
+	// scene file, at most two are kept, SailorPt_TrimMemory drops them, SAILOR_PT_SCENE_CACHE=0 turns the cache off.  Only the HOST
+	// side is cached: every SceneLoad still uploads and flattens on the device.  External .bin / image files are not part of the key.
+	struct CachedScene { std::string key; std::shared_ptr<const HostScene> scene; };
+	std::mutex g_sceneCacheMutex;
+	std::vector<CachedScene> g_sceneCache;
+
+	std::string SceneKey(const char* path)
+	{
+		struct stat st;
+		if (stat(path, &st) != 0) return std::string();
+		char real[4096];
+		const char* rp = realpath(path, real);
+		char buf[96];
+		snprintf(buf, sizeof(buf), "|%lld.%09ld|%lld", (long long)st.st_mtim.tv_sec, (long)st.st_mtim.tv_nsec, (long long)st.st_size);
+		return std::string(rp ? rp : path) + buf;
+	}
+	std::shared_ptr<const HostScene> AcquireHostScene(const char* path, int& rc, std::string& err, bool& fromCache)
+	{
+		const char* env = getenv("SAILOR_PT_SCENE_CACHE");
+		const bool enabled = !(env && env[0] == '0');
+		const std::string key = enabled ? SceneKey(path) : std::string();
+		fromCache = false;
+		if (!key.empty())
+		{
+			std::lock_guard<std::mutex> lock(g_sceneCacheMutex);
+			for (const CachedScene& c : g_sceneCache) if (c.key == key) { rc = SAILOR_PT_OK; fromCache = true; return c.scene; }
+		}
+		std::shared_ptr<HostScene> fresh(new HostScene());
+		rc = LoadGltf(path, *fresh, err);
+		if (rc != SAILOR_PT_OK) return nullptr;
+		if (!key.empty())
+		{
+			std::lock_guard<std::mutex> lock(g_sceneCacheMutex);
+			if (g_sceneCache.size() >= 2u) g_sceneCache.erase(g_sceneCache.begin());
+			g_sceneCache.push_back(CachedScene{ key, fresh });
+		}
+		return fresh;
+	}
+	void DropSceneCache() { std::lock_guard<std::mutex> lock(g_sceneCacheMutex); g_sceneCache.clear(); }
 	int FromCtx(SceneDevice& d, int rc)
 	{
 		if (!d.ctx.ok) { t_lastError = d.ctx.error; return rc == SAILOR_PT_OK ? SAILOR_PT_ERR_CUDA : rc; }
@@ -42,7 +91,7 @@ namespace
 	CameraSetup CameraOf(const SceneDevice& d, const SailorPtParams* p)
 	{
 		SailorPtParamsView v; v.camera = p->camera; v.height = p->height; v.widthOverride = p->widthOverride;
-		return SetupCamera(d.host, v);
+		return SetupCamera(d.Host(), v);
 	}
 
 	// standalone context for entry points that take no scene (OutputStage, EvalLighting)
@@ -83,6 +132,7 @@ int32_t SailorPt_TrimMemory(void)
 	if (sc.rc != SAILOR_PT_OK) return SetError(sc.rc, sc.ctx.error);
 	ReleaseSharedArenas(sc.ctx);
 	TrimDevicePool();
+	DropSceneCache();
 	return sc.ctx.ok ? SAILOR_PT_OK : SetError(SAILOR_PT_ERR_CUDA, sc.ctx.error);
 }
 int32_t SailorPt_PinHostBuffer(void* hostBuffer, uint64_t bytes)
@@ -119,8 +169,8 @@ extern "C" SAILOR_PT_API int32_t SailorPt_DebugWideStats(unsigned long long* out
 // tuning builds only (tools/fast_variants.py): read and clear the lane-state counters of the origin-local traversal loop
 extern "C" SAILOR_PT_API int32_t SailorPt_DebugFastStats(unsigned long long* out)
 {
-	if (cudaMemcpyFromSymbol(out, spt::g_fastLoopStats, sizeof(unsigned long long) * 16) != cudaSuccess) return SAILOR_PT_ERR_CUDA;
-	static const unsigned long long zero[16] = {};
+	if (cudaMemcpyFromSymbol(out, spt::g_fastLoopStats, sizeof(unsigned long long) * 64) != cudaSuccess) return SAILOR_PT_ERR_CUDA;
+	static const unsigned long long zero[64] = {};
 	cudaMemcpyToSymbol(spt::g_fastLoopStats, zero, sizeof(zero));
 	return SAILOR_PT_OK;
 }
@@ -177,7 +227,9 @@ int32_t SailorPt_SceneLoad(const char* path, SailorPtScene** outScene)
 	int rc = s->dev.ctx.Init();
 	if (rc != SAILOR_PT_OK) return SetError(rc, s->dev.ctx.error);
 	std::string err;
-	rc = LoadGltf(path, s->dev.host, err);
+	bool cached = false;
+	s->dev.device = DevCurrent();
+	s->dev.hostPtr = AcquireHostScene(path, rc, err, cached);
 	if (rc != SAILOR_PT_OK) { s->dev.ctx.Destroy(); return SetError(rc, err); }
 	s->dev.ctx.kernelLaunches = 0;
 	rc = FromCtx(s->dev, s->dev.Upload());
@@ -190,28 +242,42 @@ int32_t SailorPt_SceneLoad(const char* path, SailorPtScene** outScene)
 void SailorPt_SceneFree(SailorPtScene* s)
 {
 	if (!s) return;
+	const int home = DevCurrent();
+	for (auto& r : s->replicas)
+	{
+		if (!r) continue;
+		DevSetCurrent(r->device);             // a replica's buffers, stream and events belong to its own device
+		r->ctx.Sync();
+		r->traceTimer.Destroy();
+		for (SpanTimer& t : r->stageTimer) t.Destroy();
+		Ctx keepR = r->ctx;
+		r.reset();
+		keepR.Destroy();
+	}
+	DevSetCurrent(s->dev.device);
 	s->dev.ctx.Sync();
 	s->dev.traceTimer.Destroy();
 	for (SpanTimer& t : s->dev.stageTimer) t.Destroy();
 	Ctx keep = s->dev.ctx;
 	delete s;
 	keep.Destroy();
+	DevSetCurrent(home);
 }
 
 int32_t SailorPt_SceneCounts(const SailorPtScene* s, uint32_t c[6])
 {
 	if (!s || !c) return SAILOR_PT_ERR_ARG;
-	c[0] = s->dev.numTris; c[1] = (uint32_t)s->dev.host.materials.size(); c[2] = (uint32_t)s->dev.host.textures.size();
-	c[3] = (uint32_t)s->dev.host.lights.size(); c[4] = (uint32_t)s->dev.host.cameras.size(); c[5] = s->dev.built ? s->dev.nodesUsed : 0;
+	c[0] = s->dev.numTris; c[1] = (uint32_t)s->dev.Host().materials.size(); c[2] = (uint32_t)s->dev.Host().textures.size();
+	c[3] = (uint32_t)s->dev.Host().lights.size(); c[4] = (uint32_t)s->dev.Host().cameras.size(); c[5] = s->dev.built ? s->dev.nodesUsed : 0;
 	return SAILOR_PT_OK;
 }
 
 int32_t SailorPt_SceneGetMaterials(const SailorPtScene* s, uint32_t* words)
 {
 	if (!s || !words) return SAILOR_PT_ERR_ARG;
-	for (size_t i = 0; i < s->dev.host.materials.size(); i++)
+	for (size_t i = 0; i < s->dev.Host().materials.size(); i++)
 	{
-		const MaterialGpu& m = s->dev.host.materials[i];
+		const MaterialGpu& m = s->dev.Host().materials[i];
 		uint32_t* w = words + i * SAILOR_PT_MATERIAL_WORDS;
 		float f[26];
 		for (int c = 0; c < 3; c++) for (int r = 0; r < 3; r++) f[c * 3 + r] = m.uvTransform[c * 4 + r];
@@ -227,8 +293,8 @@ int32_t SailorPt_SceneGetMaterials(const SailorPtScene* s, uint32_t* words)
 int32_t SailorPt_SceneGetLights(const SailorPtScene* s, float* out)
 {
 	if (!s || !out) return SAILOR_PT_ERR_ARG;
-	for (size_t i = 0; i < s->dev.host.lights.size(); i++)
-		for (int k = 0; k < 3; k++) { out[i * 6 + k] = s->dev.host.lights[i].direction[k]; out[i * 6 + 3 + k] = s->dev.host.lights[i].intensity[k]; }
+	for (size_t i = 0; i < s->dev.Host().lights.size(); i++)
+		for (int k = 0; k < 3; k++) { out[i * 6 + k] = s->dev.Host().lights[i].direction[k]; out[i * 6 + 3 + k] = s->dev.Host().lights[i].intensity[k]; }
 	return SAILOR_PT_OK;
 }
 
@@ -377,9 +443,160 @@ int32_t SailorPt_OutputStage(uint32_t width, uint32_t height, const float* linea
 	return SAILOR_PT_OK;
 }
 
+} // extern "C"
+
+namespace
+{
+	// ---- one frame over several devices (SailorPtParams::deviceCount > 1) ------------------------------------------------------
+	// Replaces the reference's tile loop (PathTracer.cpp:418-487: tasks of 32x32 pixels handed to the worker threads) one level up:
+	// the rows of the frame are cut into 4 bands per device, one host thread per device takes bands from a shared counter (so a
+	// device that draws cheap rows simply takes more of them), renders each band with the ordinary single-device frame and copies it
+	// into the frame of the scene's own device over NVLink (peer copy).  The scene is replicated: every device keeps its own copy of
+	// the flattened triangles and builds its own BVH.  RNG streams are keyed by (pixel, primary sample) and a pixel's samples are
+	// summed in index order by whichever device owns its row, so the frame has the bit pattern of the single-device render whatever
+	// the band assignment was (tests/test_multi_device.py).  The output stage runs afterwards on the scene's own device (its
+	// aberration taps cross band borders).  SAILOR_PT_MULTI_SAME_DEVICE=1 puts every replica on the scene's own device (tests on a
+	// one-GPU box and the host-compiled build).
+	constexpr int kNotMulti = 1;
+	constexpr uint32_t kBandsPerDevice = 4;
+	struct MultiWorker
+	{
+		SceneDevice* D = nullptr; int device = 0; int rc = SAILOR_PT_OK; std::string error;
+		RenderStats rs{}; double tBuild = 0.0; uint32_t launches = 0, bands = 0; uint64_t h2d = 0;
+	};
+
+	int RenderMulti(SailorPtScene* s, const SailorPtParams* p, uint32_t flags)
+	{
+		SceneDevice& P = s->dev;
+		const bool same = getenv("SAILOR_PT_MULTI_SAME_DEVICE") != nullptr;
+		const int avail = same ? p->deviceCount : DevCount();
+		const CameraSetup c = CameraOf(P, p);
+		const size_t n = (size_t)c.width * c.height;
+		if (!n) return SAILOR_PT_ERR_ARG;
+		const uint32_t R0 = p->rowEnd ? p->rowBegin : 0u, R1 = p->rowEnd ? (p->rowEnd < c.height ? p->rowEnd : c.height) : c.height;
+		if (R0 >= R1) return SetError(SAILOR_PT_ERR_ARG, "empty shard");
+		const uint32_t rows = R1 - R0;
+		int N = p->deviceCount < avail ? p->deviceCount : avail;
+		if ((uint32_t)N > rows) N = (int)rows;
+		if (N <= 1) return kNotMulti;
+		const double t0 = HostNow();
+		const int home = DevCurrent();
+		if (!DevSetCurrent(P.device)) return SetError(SAILOR_PT_ERR_CUDA, "cannot select the scene's device");
+		if (s->replicas.size() < (size_t)(N - 1)) s->replicas.resize((size_t)(N - 1));
+		std::vector<MultiWorker> W((size_t)N);
+		W[0].D = &P; W[0].device = P.device;
+		for (int i = 1; i < N; i++) W[(size_t)i].device = same ? P.device : (P.device + i) % avail;
+
+		P.residentLin.Ensure(P.ctx, n * 3);
+		P.residentW = c.width; P.residentH = c.height;
+		if (R0 > 0 || R1 < c.height) P.residentLin.Zero(P.ctx, n * 3);          // rows outside the shard stay 0
+		P.ctx.Sync();                                                            // the frame exists before any peer writes into it
+		if (!P.ctx.ok) { DevSetCurrent(home); return FromCtx(P, SAILOR_PT_ERR_CUDA); }
+
+		const uint32_t nBands = rows < (uint32_t)N * kBandsPerDevice ? rows : (uint32_t)N * kBandsPerDevice;
+		const CameraGpu cam = ToGpuCamera(c);
+		std::atomic<uint32_t> next{ 0u };
+		const bool wantWide = (p->flags & SAILOR_PT_FLAG_WIDE_TRAVERSAL) != 0u && !(p->flags & SAILOR_PT_FLAG_EXACT_TRAVERSAL);
+		auto work = [&](int wi)
+		{
+			MultiWorker& w = W[(size_t)wi];
+			if (!DevSetCurrent(w.device)) { w.rc = SAILOR_PT_ERR_CUDA; w.error = "cannot select device " + std::to_string(w.device); return; }
+			if (wi > 0)
+			{
+				std::unique_ptr<SceneDevice>& rep = s->replicas[(size_t)(wi - 1)];
+				if (!rep)
+				{
+					rep.reset(new SceneDevice());
+					rep->device = w.device; rep->hostPtr = P.hostPtr;
+					w.rc = rep->ctx.Init();
+					if (w.rc == SAILOR_PT_OK) w.rc = rep->Upload();
+					if (w.rc == SAILOR_PT_OK && !rep->ctx.ok) w.rc = SAILOR_PT_ERR_CUDA;
+					w.h2d += rep->ctx.h2dBytes;
+					if (w.rc != SAILOR_PT_OK) { w.error = rep->ctx.error; return; }
+				}
+				w.D = rep.get();
+			}
+			SceneDevice& D = *w.D;
+			D.ctx.kernelLaunches = 0; D.ctx.h2dBytes = D.ctx.d2hBytes = 0;
+			if (flags & 1u) D.built = false;
+			D.wantWide = wantWide;
+			if (!D.built)
+			{
+				w.rc = D.BuildBvh();
+				if (w.rc == SAILOR_PT_OK && !D.ctx.ok) w.rc = SAILOR_PT_ERR_CUDA;
+				if (w.rc != SAILOR_PT_OK) { w.error = D.ctx.error; return; }
+				w.tBuild = D.stats.secondsBvhBuild;
+			}
+			if (wi > 0) D.residentLin.Ensure(D.ctx, n * 3);
+			for (;;)
+			{
+				const uint32_t b = next.fetch_add(1u);
+				if (b >= nBands) break;
+				SailorPtParams q = *p;
+				q.deviceCount = 0;
+				q.rowBegin = R0 + (uint32_t)((uint64_t)rows * b / nBands); q.rowEnd = R0 + (uint32_t)((uint64_t)rows * (b + 1u) / nBands);
+				RenderStats rs{};
+				w.rc = RenderFrame(D, cam, q, D.residentLin.p, rs);
+				if (w.rc == SAILOR_PT_OK && !D.ctx.ok) w.rc = SAILOR_PT_ERR_CUDA;
+				if (w.rc != SAILOR_PT_OK) { w.error = D.ctx.error; return; }
+				if (wi > 0)
+				{
+					// task row y lands in image row height-1-y (PathTracer.cpp:449): the band is the image rows [height-rowEnd, height-rowBegin)
+					const size_t off = (size_t)(c.height - q.rowEnd) * c.width * 3, cnt = (size_t)(q.rowEnd - q.rowBegin) * c.width * 3;
+					DevCopyPeer(D.ctx, P.residentLin.p + off, P.device, D.residentLin.p + off, w.device, cnt * sizeof(float));
+				}
+				w.rs.rays += rs.rays; w.rs.primarySamples += rs.primarySamples; w.rs.secondsTraverse += rs.secondsTraverse; w.rs.secondsShade += rs.secondsShade;
+				for (int k = 0; k < 4; k++) w.rs.secondsStage[k] += rs.secondsStage[k];
+				w.rs.fanOutSamples += rs.fanOutSamples; w.rs.replayedRays += rs.replayedRays; w.rs.traverseLaunches += rs.traverseLaunches; w.rs.batches += rs.batches;
+				w.bands++;
+			}
+			D.ctx.Sync();
+			if (!D.ctx.ok) { w.rc = SAILOR_PT_ERR_CUDA; w.error = D.ctx.error; }
+			w.launches = D.ctx.kernelLaunches; w.h2d += D.ctx.h2dBytes;
+		};
+		std::vector<std::thread> threads;
+		for (int i = 1; i < N; i++) threads.emplace_back(work, i);
+		work(0);
+		for (std::thread& t : threads) t.join();
+		DevSetCurrent(P.device);
+		for (const MultiWorker& w : W) if (w.rc != SAILOR_PT_OK) { DevSetCurrent(home); return SetError(w.rc, "device " + std::to_string(w.device) + ": " + w.error); }
+		double tOut = 0.0;
+		if (flags & 2u)
+		{
+			P.residentSrgb.Ensure(P.ctx, n * 3);
+			P.ctx.TimerStart();
+			RunOutputStage(P.ctx, c.width, c.height, P.residentLin.p, P.residentSrgb.p);
+			tOut = P.ctx.TimerStop();
+		}
+		P.ctx.Sync();
+		g_stats = SailorPtStats{};
+		for (const MultiWorker& w : W)
+		{
+			g_stats.rays += w.rs.rays; g_stats.primarySamples += w.rs.primarySamples; g_stats.fanOutSamples += w.rs.fanOutSamples; g_stats.replayedRays += w.rs.replayedRays;
+			g_stats.traverseLaunches += w.rs.traverseLaunches; g_stats.batches += w.rs.batches; g_stats.kernelLaunches += w.launches; g_stats.h2dBytes += w.h2d;
+			// per-stage device time: the busiest device's
+			if (w.rs.secondsTraverse > g_stats.secondsTraverse) g_stats.secondsTraverse = w.rs.secondsTraverse;
+			if (w.rs.secondsShade > g_stats.secondsShade) g_stats.secondsShade = w.rs.secondsShade;
+			if (w.rs.secondsStage[0] > g_stats.secondsExpand) g_stats.secondsExpand = w.rs.secondsStage[0];
+			if (w.rs.secondsStage[1] > g_stats.secondsFanOut) g_stats.secondsFanOut = w.rs.secondsStage[1];
+			if (w.rs.secondsStage[2] > g_stats.secondsClassify) g_stats.secondsClassify = w.rs.secondsStage[2];
+			if (w.rs.secondsStage[3] > g_stats.secondsGather) g_stats.secondsGather = w.rs.secondsStage[3];
+			if (w.tBuild > g_stats.secondsBvhBuild) g_stats.secondsBvhBuild = w.tBuild;
+		}
+		g_stats.secondsOutput = tOut;
+		g_stats.devicesUsed = (uint32_t)N;
+		g_stats.secondsCall = g_stats.secondsTotal = HostNow() - t0;      // several devices: no common CUDA clock, host clock around the whole call
+		DevSetCurrent(home);
+		return FromCtx(P, SAILOR_PT_OK);
+	}
+}
+
+extern "C" {
+
 int32_t SailorPt_RenderResident(SailorPtScene* s, const SailorPtParams* p, uint32_t flags)
 {
 	if (!s || !p || !p->height || !p->msaa) return SAILOR_PT_ERR_ARG;
+	if (p->deviceCount > 1) { const int rcm = RenderMulti(s, p, flags); if (rcm != kNotMulti) return rcm; }
 	SceneDevice& D = s->dev;
 	const double t0 = HostNow();
 	D.ctx.kernelLaunches = 0; D.ctx.h2dBytes = D.ctx.d2hBytes = 0;
@@ -418,6 +635,7 @@ int32_t SailorPt_RenderResident(SailorPtScene* s, const SailorPtParams* p, uint3
 	g_stats.secondsShade = rs.secondsShade; g_stats.secondsExpand = rs.secondsStage[0]; g_stats.secondsFanOut = rs.secondsStage[1]; g_stats.secondsClassify = rs.secondsStage[2];
 	g_stats.secondsGather = rs.secondsStage[3]; g_stats.fanOutSamples = rs.fanOutSamples; g_stats.replayedRays = rs.replayedRays; g_stats.secondsOutput = tOut; g_stats.secondsBvhBuild = tBuild; g_stats.traverseLaunches = rs.traverseLaunches; g_stats.batches = rs.batches;
 	g_stats.kernelLaunches = D.ctx.kernelLaunches; g_stats.h2dBytes = D.ctx.h2dBytes; g_stats.d2hBytes = D.ctx.d2hBytes;
+	g_stats.devicesUsed = 1u;
 	g_stats.secondsTotal = HostNow() - t0;
 	return FromCtx(D, SAILOR_PT_OK);
 }

@@ -5,7 +5,7 @@
 // This is that missing caller, against include/sailor_pt.h only (no CUDA, no torch in sight): the same flags, the same
 // defaults (PathTracer.h:21-32), plus the extensions of the drop-in:
 //     --passes N --checkpoint FILE [--resume]   progressive render, N primary-sample indices per pass (SailorPt_RenderProgressive)
-//     --seed S --width W --device D
+//     --seed S --width W --device D --devices N     (N: CUDA devices to spread the frame over, SailorPtParams::deviceCount)
 // Exit code: 0, or the negated SAILOR_PT_ERR_* code (the reference logs and returns, :94-98).
 #include "../../include/sailor_pt.h"
 
@@ -23,7 +23,7 @@ int main(int argc, char** argv)
 	if (argc < 2)
 	{
 		fprintf(stderr, "usage: %s --in scene.gltf|.glb --out image.png|.pfm|.hdr [--height H] [--samples N] [--bounces B] [--camera NAME] [--ambient RRGGBB]\n"
-			"       [--passes N --checkpoint FILE [--resume]] [--seed S] [--width W] [--device D]\n   backend: %s\n", argv[0], SailorPt_Backend());
+			"       [--passes N --checkpoint FILE [--resume]] [--seed S] [--width W] [--device D] [--devices N]\n   backend: %s\n", argv[0], SailorPt_Backend());
 		return 1;
 	}
 	int32_t rc = SailorPt_ParseCommandLineArgs(&p, const_cast<const char**>(argv), argc);
@@ -39,6 +39,7 @@ int main(int argc, char** argv)
 		else if (a == "--seed" && i + 1 < argc) p.seed = strtoull(argv[++i], nullptr, 10);
 		else if (a == "--width" && i + 1 < argc) p.widthOverride = (uint32_t)atoi(argv[++i]);
 		else if (a == "--device" && i + 1 < argc) device = atoi(argv[++i]);
+		else if (a == "--devices" && i + 1 < argc) p.deviceCount = atoi(argv[++i]);
 	}
 	if (!p.pathToModel || !p.pathToModel[0]) { fprintf(stderr, "--in is required\n"); return 1; }
 	rc = SailorPt_SetDevice(device);
@@ -62,6 +63,6 @@ int main(int argc, char** argv)
 	if (rc != SAILOR_PT_OK) { fprintf(stderr, "path tracer failed (%d): %s\n", rc, SailorPt_LastError()); return -rc; }
 	SailorPtStats st;
 	if (SailorPt_GetStats(&st) == SAILOR_PT_OK && st.secondsTotal > 0.0)
-		fprintf(stderr, "%s: %.1f M rays in %.3f s (%.1f Mrays/s)\n", SailorPt_Backend(), (double)st.rays / 1e6, st.secondsTotal, (double)st.rays / st.secondsTotal / 1e6);
+		fprintf(stderr, "%s: %.1f M rays in %.3f s (%.1f Mrays/s) on %u device(s)\n", SailorPt_Backend(), (double)st.rays / 1e6, st.secondsTotal, (double)st.rays / st.secondsTotal / 1e6, st.devicesUsed ? st.devicesUsed : 1u);
 	return 0;
 }

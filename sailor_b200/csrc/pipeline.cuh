@@ -14,6 +14,7 @@
 #include "../../include/sailor_pt.h"
 
 #include <chrono>
+#include <memory>
 
 namespace spt
 {
@@ -24,7 +25,9 @@ namespace spt
 	struct SceneDevice
 	{
 		Ctx ctx;
-		HostScene host;
+		int device = 0;                       // CUDA device this replica of the scene lives on
+		std::shared_ptr<const HostScene> hostPtr;     // the parsed file: shared by the scene cache (capi.cu) and by the per-device replicas of a multi-device render
+		const HostScene& Host() const { return *hostPtr; }
 		uint32_t numTris = 0;
 
 		// flattened triangles
@@ -146,18 +149,18 @@ namespace spt
 		int Upload()
 		{
 			const double t0 = HostNow();
-			numTris = (uint32_t)host.numTriangles;
+			numTris = (uint32_t)Host().numTriangles;
 			counter.Alloc(ctx, 16); counter.Zero(ctx);
 			if (numTris == 0) return CudaStatus();
 			// The primitive streams go to the device piece by piece, straight from the importer's vectors (no host-side concatenation:
 			// at 10 M triangles that was hundreds of MB of extra copies).  A stream a primitive lacks is never read (FlattenKernel
 			// looks at PrimDesc::has*), so its part of the device buffer stays uninitialised.
-			std::vector<PrimDesc> descs(host.prims.size());
+			std::vector<PrimDesc> descs(Host().prims.size());
 			uint32_t triStart = 0, vtxOffset = 0, idxOffset = 0;
 			bool anyNrm = false, anyUv0 = false, anyUv1 = false, anyTan = false;
-			for (size_t i = 0; i < host.prims.size(); i++)
+			for (size_t i = 0; i < Host().prims.size(); i++)
 			{
-				const HostPrimitive& hp = host.prims[i];
+				const HostPrimitive& hp = Host().prims[i];
 				PrimDesc& d = descs[i];
 				memset(&d, 0, sizeof(d));
 				memcpy(d.world, hp.world, sizeof(d.world));
@@ -179,14 +182,14 @@ namespace spt
 			dNrm.Alloc(ctx, anyNrm ? (size_t)vtxOffset * 3 : 1); dUv0.Alloc(ctx, anyUv0 ? (size_t)vtxOffset * 2 : 1);
 			dUv1.Alloc(ctx, anyUv1 ? (size_t)vtxOffset * 2 : 1); dTan.Alloc(ctx, anyTan ? (size_t)vtxOffset * 4 : 1);
 			if (!ctx.ok) return CudaStatus();
-			if (host.prims.size() > 32)
+			if (Host().prims.size() > 32)
 			{
 				// many small primitives: one copy per stream from a host-side concatenation beats thousands of tiny transfers
 				std::vector<float> pos((size_t)vtxOffset * 3), nrm(anyNrm ? (size_t)vtxOffset * 3 : 0), uv0(anyUv0 ? (size_t)vtxOffset * 2 : 0), uv1(anyUv1 ? (size_t)vtxOffset * 2 : 0), tan(anyTan ? (size_t)vtxOffset * 4 : 0);
 				std::vector<uint32_t> idx(idxOffset);
-				for (size_t i = 0; i < host.prims.size(); i++)
+				for (size_t i = 0; i < Host().prims.size(); i++)
 				{
-					const HostPrimitive& hp = host.prims[i];
+					const HostPrimitive& hp = Host().prims[i];
 					const PrimDesc& d = descs[i];
 					if (!hp.pos.empty()) memcpy(pos.data() + (size_t)d.vtxOffset * 3, hp.pos.data(), hp.pos.size() * sizeof(float));
 					if (!hp.idx.empty()) memcpy(idx.data() + d.idxOffset, hp.idx.data(), hp.idx.size() * sizeof(uint32_t));
@@ -203,9 +206,9 @@ namespace spt
 				if (!tan.empty()) DevUpload(ctx, dTan.p, tan.data(), tan.size() * sizeof(float));
 				ctx.Sync();                                   // the staging vectors die at the end of this block
 			}
-			else for (size_t i = 0; i < host.prims.size(); i++)
+			else for (size_t i = 0; i < Host().prims.size(); i++)
 			{
-				const HostPrimitive& hp = host.prims[i];
+				const HostPrimitive& hp = Host().prims[i];
 				const PrimDesc& d = descs[i];
 				if (!hp.pos.empty()) DevUpload(ctx, dPos.p + (size_t)d.vtxOffset * 3, hp.pos.data(), hp.pos.size() * sizeof(float));
 				if (!hp.idx.empty()) DevUpload(ctx, dIdx.p + d.idxOffset, hp.idx.data(), hp.idx.size() * sizeof(uint32_t));
@@ -225,9 +228,9 @@ namespace spt
 			launch_for(ctx, numTris, fk);
 			stats.secondsFlatten = ctx.TimerStop();
 
-			materials.Upload(ctx, host.materials);
+			materials.Upload(ctx, Host().materials);
 			std::vector<V4> lightData;
-			for (const auto& l : host.lights) { lightData.push_back(v4(l.direction[0], l.direction[1], l.direction[2], 0.0f)); lightData.push_back(v4(l.intensity[0], l.intensity[1], l.intensity[2], 0.0f)); }
+			for (const auto& l : Host().lights) { lightData.push_back(v4(l.direction[0], l.direction[1], l.direction[2], 0.0f)); lightData.push_back(v4(l.intensity[0], l.intensity[1], l.intensity[2], 0.0f)); }
 			lights.Upload(ctx, lightData);
 			const int rc = UploadTextures();
 			ctx.Sync();

@@ -160,9 +160,16 @@ namespace spt
 		uint64_t budget = 40960ull << 20;
 		// cudaMemGetInfo goes through the driver's resource-manager lock and was seen to block for tens of milliseconds on a busy
 		// box (profiles/r01g_SUMMARY.md): ask at most once every few seconds
-		static uint64_t cachedFree = 0; static double cachedAt = -1e30;
+		// (one cache entry per device: a multi-device render asks from one host thread per device)
+		static std::mutex m; static uint64_t cachedFreeOf[64] = {}; static double cachedAtOf[64] = {};
+		const int dev = DevCurrent() & 63;
 		const double now = HostNow();
-		if (now - cachedAt > 5.0) { cachedFree = (uint64_t)DevMemAvailable() + held; cachedAt = now; }
+		uint64_t cachedFree;
+		{
+			std::lock_guard<std::mutex> lock(m);
+			if (cachedAtOf[dev] == 0.0 || now - cachedAtOf[dev] > 5.0) { cachedFreeOf[dev] = (uint64_t)DevMemAvailable() + held; cachedAtOf[dev] = now; }
+			cachedFree = cachedFreeOf[dev];
+		}
 		const uint64_t avail = cachedFree / 3u;
 		if (avail && budget > avail) budget = avail;
 		if (budget < (256ull << 20)) budget = 256ull << 20;
@@ -287,9 +294,9 @@ namespace spt
 
 		if (hitCount && ctx.ok)
 		{
-			const uint32_t numLights = (uint32_t)D.host.lights.size();
+			const uint32_t numLights = (uint32_t)D.Host().lights.size();
 			const bool ambientOn = pa.ambient.x + pa.ambient.y + pa.ambient.z > 0.0f;
-			const bool hasSky = ambientOn && SceneHasThickTransmission(D.host);
+			const bool hasSky = ambientOn && SceneHasThickTransmission(D.Host());
 			const uint32_t levels = p.maxBounces + 1u;
 			uint32_t shrink = 0;
 			uint32_t done = 0;

@@ -46,7 +46,7 @@ namespace spt
 	{
 		hostTextures.clear();
 		uint64_t total = 0;
-		for (const auto& t : host.textures)
+		for (const auto& t : Host().textures)
 		{
 			DeviceTexture d; d.width = (uint32_t)t.width; d.height = (uint32_t)t.height; d.channels = t.channels; d.clamping = t.clamping; d.offset = total;
 			total += (uint64_t)t.width * t.height;
@@ -60,9 +60,9 @@ namespace spt
 		texels.Alloc(ctx, total);
 		textures.Upload(ctx, hostTextures);
 		if (!ctx.ok) return SAILOR_PT_ERR_CUDA;
-		for (size_t i = 0; i < host.textures.size(); i++)
+		for (size_t i = 0; i < Host().textures.size(); i++)
 		{
-			const HostTexture& t = host.textures[i];
+			const HostTexture& t = Host().textures[i];
 			const uint32_t n = (uint32_t)t.width * (uint32_t)t.height;
 			if (!n) continue;
 			staging.Ensure(ctx, n);

@@ -338,12 +338,14 @@ namespace spt
 #if defined(SPT_FAST_LOOP_STATS)
 	// tuning aid: 0 iterations, 1 idle lanes, 2 node steps, 3 lanes in node steps, 4 triangle steps, 5 lanes in triangle steps, 6 refills, 7 lanes refilled,
 	// 8 rays retired, 9 triangle votes with no node work left
-	__device__ unsigned long long g_fastLoopStats[16];
+	__device__ unsigned long long g_fastLoopStats[64];
 #define SPT_FL(i, v) do { if (lane == 0) fl_[i] += (v); } while (0)
 #define SPT_FL_LANES(i, cond) do { const uint32_t m_ = __ballot_sync(0xffffffffu, (cond)); if (lane == 0) fl_[i] += __popc(m_); } while (0)
+#define SPT_FL_MINE(v, cond) do { v += (cond) ? 1u : 0u; } while (0)
 #else
 #define SPT_FL(i, v) do { } while (0)
 #define SPT_FL_LANES(i, cond) do { } while (0)
+#define SPT_FL_MINE(v, cond) do { } while (0)
 #endif
 
 	__device__ __forceinline__ void ld256(const void* p, uint32_t (&r)[8])     // LDG.E.256 through the read-only path
@@ -394,7 +396,7 @@ namespace spt
 		uint32_t qw = 0, qr = 0;          // leaf queue: entries written / read (first in, first out: the leaves nearest to the origin are found first)
 		bool exhausted = false;
 #if defined(SPT_FAST_LOOP_STATS)
-		unsigned long long fl_[12] = {};
+		unsigned long long fl_[16] = {}; uint32_t myNode = 0, myTri = 0;
 #endif
 		auto pushLeaf = [&](bool yes, uint32_t slot)
 		{
@@ -438,7 +440,17 @@ namespace spt
 						rb = __shfl_sync(0xffffffffu, rb, leader);
 						if (toReplay) replay.list[rb + (uint32_t)__popc(rm & ((1u << lane) - 1u))] = index;
 					}
-					SPT_FL(8, __popc(doneMask));
+					SPT_FL(8, __popc(doneMask)); SPT_FL_LANES(13, done && anyHit); SPT_FL_LANES(14, done && anyHit && best.tri != kNoHit); SPT_FL_LANES(15, done && !anyHit && best.tri != kNoHit);
+#if defined(SPT_FAST_LOOP_STATS)
+					if (done)
+					{
+						const int cls = (anyHit ? 0 : 2) + (best.tri != kNoHit ? 0 : 1);
+						atomicAdd(&g_fastLoopStats[16 + cls], (unsigned long long)myNode); atomicAdd(&g_fastLoopStats[20 + cls], (unsigned long long)myTri); atomicAdd(&g_fastLoopStats[24 + cls], 1ull);
+						if (cls == 0) atomicAdd(&g_fastLoopStats[28 + (myNode < 17u ? myNode : 17u)], 1ull);
+						if (cls == 0) atomicAdd(&g_fastLoopStats[46 + (myTri < 17u ? myTri : 17u)], 1ull);
+						myNode = 0; myTri = 0;
+					}
+#endif
 					Hit h; h.t = best.t; h.u = best.u; h.v = best.v; h.tri = best.tri;
 					sink.Retire(done && !toReplay, index, h, anyHit);
 					if (done) active = false;
@@ -506,7 +518,7 @@ namespace spt
 				for (int rep = 0; rep < SPT_FAST_NODE_REPS; rep++)
 				{
 					const bool take = SPT_FAST_CAN_NODE;
-					SPT_FL(2, 1); SPT_FL_LANES(3, take);
+					SPT_FL(2, 1); SPT_FL_LANES(3, take); SPT_FL_LANES(10, take && cur == kFastClimb); SPT_FL_LANES(11, take && anyHit); SPT_FL_MINE(myNode, take);
 					if (take)
 					{
 						// DOWN: both halves of node `cur`.  UP: the sibling's half of the parent; the finished side never hits.
@@ -553,7 +565,7 @@ namespace spt
 				for (int rep = 0; rep < SPT_FAST_TRI_REPS; rep++)
 				{
 					const bool take = active && tcur != kFastNone;
-					SPT_FL(4, 1); SPT_FL_LANES(5, take);
+					SPT_FL(4, 1); SPT_FL_LANES(5, take); SPT_FL_LANES(12, take && anyHit); SPT_FL_MINE(myTri, take);
 					if (take)
 					{
 						const unsigned char* T = reinterpret_cast<const unsigned char*>(w.tris) + (size_t)tcur * 64u;
@@ -587,7 +599,7 @@ namespace spt
 			}
 		}
 #if defined(SPT_FAST_LOOP_STATS)
-		if (lane == 0) for (int k = 0; k < 12; k++) atomicAdd(&g_fastLoopStats[k], fl_[k]);
+		if (lane == 0) for (int k = 0; k < 16; k++) atomicAdd(&g_fastLoopStats[k], fl_[k]);
 #endif
 #undef SPT_FAST_CAN_NODE
 	}

@@ -245,3 +245,27 @@ def check_progressive_and_image_io(lib, path, tmpdir):
 def pytest_raises(exc):
     import pytest
     return pytest.raises(exc)
+
+
+def check_multi_device_frame(lib, path, devices=3, **base):
+    """SailorPtParams::deviceCount: the frame spread over several devices (one host thread per device inside the library, dynamic row
+    bands, peer copies into the scene's own device, output stage there) has the bit pattern of the single-device frame, for the
+    float accumulator AND the sRGB8 image, with a row shard and with a second frame that reuses the replicas (PathTracer.cpp:418-487)."""
+    kw = dict(height=23, num_samples=2, num_ambient_samples=2, max_bounces=3, msaa=4, ambient=(1, 1, 1), seed=9)
+    kw.update(base)
+    with lib.load_scene(path) as s:
+        one_lin, one_srgb = s.render(Params(**kw))
+        for n in (2, devices):
+            lin, srgb = s.render(Params(device_count=n, **kw))
+            st = lib.stats()
+            assert np.array_equal(lin.view(np.uint32), one_lin.view(np.uint32)) and np.array_equal(srgb, one_srgb)
+            assert 1 <= st["devicesUsed"] <= n and st["rays"] > 0
+        h = one_lin.shape[0]
+        part, _ = s.render(Params(rows=(3, h - 5), **kw))
+        part_n, _ = s.render(Params(rows=(3, h - 5), device_count=devices, **kw))
+        assert np.array_equal(part.view(np.uint32), part_n.view(np.uint32))
+        # a second frame with other parameters through the same replicas
+        kw2 = dict(kw, seed=10, msaa=2)
+        a, _ = s.render(Params(**kw2)); b, _ = s.render(Params(device_count=devices, **kw2))
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    return st["devicesUsed"]

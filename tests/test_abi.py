@@ -42,7 +42,7 @@ def test_struct_layouts_match_the_header():
     # 3 pointers + 5 u32 + 3 f32 + u32 + (pad) u64 + 4 u32
     assert C.sizeof(SailorPtParams) == 96
     assert SailorPtParams.seed.offset == 64 and SailorPtParams.rowBegin.offset == 72
-    assert C.sizeof(SailorPtStats) == 168
+    assert C.sizeof(SailorPtStats) == 176 and SailorPtStats.devicesUsed.offset == 168
 
 
 def test_product_fails_loudly_without_a_cuda_device(scene_dir):

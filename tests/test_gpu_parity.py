@@ -212,6 +212,12 @@ def test_cpp_host_renders_like_the_library(gpu, scene_dir, tmp_path):
     with gpu.load_scene(scene) as s:
         lin, _ = s.render(p)
     assert np.array_equal(pc.bits(pc.read_pfm(pfm)), pc.bits(lin))
+    # SailorPt_Run with deviceCount > 1 (--devices): the same bits from however many devices the box has
+    pfm2 = str(tmp_path / "b.pfm")
+    r = subprocess.run([exe] + common + ["--out", pfm2, "--devices", "8"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "device(s)" in r.stderr
+    assert np.array_equal(pc.bits(pc.read_pfm(pfm2)), pc.bits(lin))
 
 
 def test_trim_memory_releases_the_working_set_and_rendering_goes_on(gpu, scene_dir):

@@ -46,7 +46,7 @@ else:
             best = min(tr)
             row = dict(trace_ms=round(best[0] * 1e3, 2), step_ms=round(best[1] * 1e3, 2), trace_Grays=round(best[2] / best[0] / 1e9, 3), replayed=best[3])
             if hasattr(L.lib, "SailorPt_DebugFastStats"):
-                buf = (ctypes.c_ulonglong * 16)()
+                buf = (ctypes.c_ulonglong * 64)()
                 L.lib.SailorPt_DebugFastStats(buf)          # clear
                 s.render_resident(p, rebuild_bvh=False, output_stage=False)
                 rays = L.stats()["rays"]
@@ -54,6 +54,9 @@ else:
                 v = list(buf)
                 row["stats"] = dict(iterations=v[0], idle_per_iter=round(v[1] / max(v[0], 1), 2), node_steps=v[2], lanes_per_node_step=round(v[3] / max(v[2], 1), 2),
                                     tri_steps=v[4], lanes_per_tri_step=round(v[5] / max(v[4], 1), 2), refills=v[6], lanes_per_refill=round(v[7] / max(v[6], 1), 2),
-                                    retired=v[8], forced_tri_votes=v[9], node_visits_per_ray=round(v[3] / max(v[8], 1), 2), tri_tests_per_ray=round(v[5] / max(v[8], 1), 2))
+                                    retired=v[8], forced_tri_votes=v[9], node_visits_per_ray=round(v[3] / max(v[8], 1), 2), tri_tests_per_ray=round(v[5] / max(v[8], 1), 2),
+                                    up_lane_steps=v[10], anyhit_node_lane_steps=v[11], anyhit_tri_lane_steps=v[12], retired_anyhit=v[13], retired_anyhit_hit=v[14], retired_closest_hit=v[15],
+                                    per_class={n: dict(rays=v[24 + c], node_per_ray=round(v[16 + c] / max(v[24 + c], 1), 2), tri_per_ray=round(v[20 + c] / max(v[24 + c], 1), 2)) for c, n in enumerate(("anyhit_hit", "anyhit_miss", "closest_hit", "closest_miss"))},
+                                    anyhit_hit_node_hist=v[28:46], anyhit_hit_tri_hist=v[46:64])
         L.trim_memory()          # every loaded copy of the library owns its own shared arenas: give them back before the next variant
         print(f, json.dumps(row), flush=True)
