@@ -246,6 +246,22 @@ SAILOR_PT_API int32_t SailorPt_SampleTexture(SailorPtScene* scene, uint32_t text
  * record layout (in: 24 floats, out: 28 floats). */
 SAILOR_PT_API int32_t SailorPt_EvalLighting(uint32_t count, const float* in, float* out);
 
+/* The shading context the integrator builds at a hit, value for value (parity hook for rows a13/a15 of SURVEY.md 8):
+ * PathTracer::Raytrace lines 636-661 (interpolated frame, face normal turned against the ray, uv through the material's
+ * uvTransform, world normal, alpha-scaled sample counts) around PathTracer::GetMaterialData (PathTracer.cpp:881-927).
+ * in:  triIds[count] (original triangle ids), baryUV[2*count] (SailorPtHit::baryU, baryV), rayDirs[3*count]
+ * out: SAILOR_PT_SHADE_FLOATS per hit: baseColor(4) orm(3) emissive(3) sampled normal(3) transmission ior thickness opaque(0/1)
+ *      worldNormal(3) faceNormal(3) uvTransformed(2) oppositeRay(0/1) numSamples numAmbientSamples (after the alpha rule, as floats) */
+#define SAILOR_PT_SHADE_FLOATS 28
+SAILOR_PT_API int32_t SailorPt_ShadeHits(SailorPtScene* scene, uint32_t count, const uint32_t* triIds, const float* baryUV, const float* rayDirs,
+	uint32_t numSamples, uint32_t numAmbientSamples, float* out);
+
+/* The product's counter-based sample generators (product only; the reference draws from unseeded rand()), for
+ * distribution tests against glm::linearRand on rand() % 255 bytes (glm/gtc/random.inl:19-27,176-183) and the blue-noise table walk
+ * (PathTracer.cpp:934-1077).  kind 0: `count` raw 32-bit draws (out = uint32 bit patterns); kind 1: `count` linearRand(0,1) floats;
+ * kind 2: `count` draws of one NextVec2_BlueNoise walk, 4 floats each: x, y, table index of x, table index of y. */
+SAILOR_PT_API int32_t SailorPt_SampleGenerators(uint64_t streamKey, uint32_t kind, uint32_t count, float* out);
+
 SAILOR_PT_API int32_t SailorPt_GetStats(SailorPtStats* stats);
 SAILOR_PT_API const char* SailorPt_LastError(void);
 /* Product: make CUDA device `device` current for the calling thread (one process per GPU sets its LOCAL_RANK before

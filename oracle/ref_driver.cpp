@@ -103,6 +103,7 @@ namespace
 		using PathTracer::m_textures;
 		using PathTracer::m_directionalLights;
 		using PathTracer::m_textureMapping;
+		using PathTracer::GetMaterialData;
 		vec3 DoRaytrace(const Ray& r, const BVH& bvh, uint32_t bounces, const Params& p) const
 		{
 			return Raytrace(r, bvh, bounces, (uint32_t)(-1), p, 1.0f, 1.0f);
@@ -953,6 +954,46 @@ int32_t SailorPt_SampleTexture(SailorPtScene* s, uint32_t textureIndex, uint32_t
 	}
 	return SAILOR_PT_OK;
 }
+
+int32_t SailorPt_ShadeHits(SailorPtScene* s, uint32_t count, const uint32_t* triIds, const float* baryUV, const float* rayDirs, uint32_t numSamples, uint32_t numAmbient, float* out)
+{
+	// The head of PathTracer::Raytrace after a hit (PathTracer.cpp:636-661), statement for statement, around the reference's OWN
+	// GetMaterialData (:881-927, called here through the compiled reference source)
+	if (!s || !triIds || !baryUV || !rayDirs || !out) return SAILOR_PT_ERR_ARG;
+	const RefTracer& T = s->tracer;
+	for (uint32_t i = 0; i < count; i++)
+	{
+		float* o = out + (size_t)i * SAILOR_PT_SHADE_FLOATS;
+		if (triIds[i] >= T.m_triangles.Num()) { for (int k = 0; k < SAILOR_PT_SHADE_FLOATS; k++) o[k] = 0.0f; continue; }
+		const Math::Triangle& tri = T.m_triangles[triIds[i]];
+		const float bu = baryUV[2 * i], bv = baryUV[2 * i + 1];
+		const vec3 bc(1.0f - bu - bv, bu, bv);                                      // RaycastHit::m_barycentricCoordinate (Bounds.cpp:521-523)
+		const vec3 dir(rayDirs[3 * i], rayDirs[3 * i + 1], rayDirs[3 * i + 2]);
+		vec3 faceNormal = vec3(bc.x * tri.m_normals[0] + bc.y * tri.m_normals[1] + bc.z * tri.m_normals[2]);
+		const vec3 tangent = vec3(bc.x * tri.m_tangent[0] + bc.y * tri.m_tangent[1] + bc.z * tri.m_tangent[2]);
+		const vec3 bitangent = vec3(bc.x * tri.m_bitangent[0] + bc.y * tri.m_bitangent[1] + bc.z * tri.m_bitangent[2]);
+		const bool bIsOppositeRay = dot(faceNormal, dir) < 0.0f;
+		if (!bIsOppositeRay) faceNormal *= -1.0f;
+		const mat3 tbn(tangent, bitangent, faceNormal);
+		const vec2 uv = bc.x * tri.m_uvs[0] + bc.y * tri.m_uvs[1] + bc.z * tri.m_uvs[2];
+		const auto material = T.m_materials[tri.m_materialIndex];
+		const vec2 uvTransformed = (material.m_uvTransform * vec3(uv, 1));
+		const LightingModel::SampledData sample = T.GetMaterialData(tri.m_materialIndex, uvTransformed);
+		const vec3 worldNormal = normalize(tbn * sample.m_normal);
+		const bool bHasAlphaBlending = !sample.m_bIsOpaque && sample.m_baseColor.a < 1.0f;
+		const uint32_t nS = bHasAlphaBlending ? std::max(1u, (uint32_t)round(sample.m_baseColor.a * (float)numSamples)) : numSamples;
+		const uint32_t nA = bHasAlphaBlending ? std::max(1u, (uint32_t)round(sample.m_baseColor.a * (float)numAmbient)) : numAmbient;
+		o[0] = sample.m_baseColor.x; o[1] = sample.m_baseColor.y; o[2] = sample.m_baseColor.z; o[3] = sample.m_baseColor.w;
+		o[4] = sample.m_orm.x; o[5] = sample.m_orm.y; o[6] = sample.m_orm.z; o[7] = sample.m_emissive.x; o[8] = sample.m_emissive.y; o[9] = sample.m_emissive.z;
+		o[10] = sample.m_normal.x; o[11] = sample.m_normal.y; o[12] = sample.m_normal.z; o[13] = sample.m_transmission; o[14] = sample.m_ior; o[15] = sample.m_thicknessFactor;
+		o[16] = sample.m_bIsOpaque ? 1.0f : 0.0f;
+		o[17] = worldNormal.x; o[18] = worldNormal.y; o[19] = worldNormal.z; o[20] = faceNormal.x; o[21] = faceNormal.y; o[22] = faceNormal.z;
+		o[23] = uvTransformed.x; o[24] = uvTransformed.y; o[25] = bIsOppositeRay ? 1.0f : 0.0f; o[26] = (float)nS; o[27] = (float)nA;
+	}
+	return SAILOR_PT_OK;
+}
+
+int32_t SailorPt_SampleGenerators(uint64_t, uint32_t, uint32_t, float*) { return SAILOR_PT_ERR_UNSUPPORTED; }      // product only: the reference draws from unseeded rand()
 
 int32_t SailorPt_EvalLighting(uint32_t count, const float* in, float* out)
 {

@@ -61,7 +61,7 @@ SYMBOLS = [
     "SailorPt_OutputStage", "SailorPt_SampleTexture", "SailorPt_EvalLighting", "SailorPt_GetStats",
     "SailorPt_LastError", "SailorPt_Backend", "SailorPt_RenderResident", "SailorPt_ReadResident", "SailorPt_CopyResidentToDevice", "SailorPt_SetDevice", "SailorPt_OutputStageResident",
     "SailorPt_PinHostBuffer", "SailorPt_UnpinHostBuffer", "SailorPt_WriteImage", "SailorPt_CompareImages", "SailorPt_RenderProgressive",
-    "SailorPt_TrimMemory", "SailorPt_IntersectRaysEx",
+    "SailorPt_TrimMemory", "SailorPt_IntersectRaysEx", "SailorPt_ShadeHits", "SailorPt_SampleGenerators",
 ]
 
 
@@ -148,6 +148,8 @@ class Library:
         lib.SailorPt_OutputStage.argtypes = [C.c_uint32, C.c_uint32, P(C.c_float), P(C.c_uint8)]
         lib.SailorPt_SampleTexture.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, P(C.c_float), P(C.c_float)]
         lib.SailorPt_EvalLighting.argtypes = [C.c_uint32, P(C.c_float), P(C.c_float)]
+        lib.SailorPt_ShadeHits.argtypes = [C.c_void_p, C.c_uint32, P(C.c_uint32), P(C.c_float), P(C.c_float), C.c_uint32, C.c_uint32, P(C.c_float)]
+        lib.SailorPt_SampleGenerators.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, P(C.c_float)]
         lib.SailorPt_GetStats.argtypes = [P(SailorPtStats)]
         lib.SailorPt_SetDevice.argtypes = [C.c_int32]
         lib.SailorPt_OutputStageResident.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
@@ -231,6 +233,12 @@ class Library:
         out = np.empty((h, w, 3), np.uint8)
         self.check(self.lib.SailorPt_OutputStage(w, h, _ptr(linear, C.c_float), _ptr(out, C.c_uint8)), "SailorPt_OutputStage")
         return out
+
+    def sample_generators(self, key, kind, count):
+        """SailorPt_SampleGenerators: kind 0 -> uint32[count], 1 -> float32[count], 2 -> float32[count, 4] (x, y, index of x, index of y)."""
+        out = np.empty((count, 4) if kind == 2 else (count,), np.float32)
+        self.check(self.lib.SailorPt_SampleGenerators(C.c_uint64(key), kind, count, _ptr(out, C.c_float)), "SailorPt_SampleGenerators")
+        return out.view(np.uint32) if kind == 0 else out
 
     def eval_lighting(self, records):
         records = np.ascontiguousarray(records, dtype=np.float32)
@@ -379,6 +387,14 @@ class Scene:
 
     def output_stage_resident(self, device_ptr=None, nbytes=0):
         self.L.check(self.L.lib.SailorPt_OutputStageResident(self.h, C.c_void_p(device_ptr) if device_ptr else None, nbytes), "SailorPt_OutputStageResident")
+
+    def shade_hits(self, tri_ids, bary_uv, ray_dirs, num_samples=4, num_ambient_samples=4):
+        """SailorPt_ShadeHits: float32[count, 28] (layout in include/sailor_pt.h)."""
+        tri = np.ascontiguousarray(tri_ids, dtype=np.uint32); uv = np.ascontiguousarray(bary_uv, dtype=np.float32); d = np.ascontiguousarray(ray_dirs, dtype=np.float32)
+        assert uv.shape == (tri.shape[0], 2) and d.shape == (tri.shape[0], 3)
+        out = np.empty((tri.shape[0], 28), np.float32)
+        self.L.check(self.L.lib.SailorPt_ShadeHits(self.h, tri.shape[0], _ptr(tri, C.c_uint32), _ptr(uv, C.c_float), _ptr(d, C.c_float), num_samples, num_ambient_samples, _ptr(out, C.c_float)), "SailorPt_ShadeHits")
+        return out
 
     def sample_texture(self, index, uv):
         uv = np.ascontiguousarray(uv, dtype=np.float32)

@@ -856,12 +856,44 @@ int32_t SailorPt_SampleTexture(SailorPtScene* s, uint32_t textureIndex, uint32_t
 	DevBuf<V2> dUv; DevBuf<V4> dOut;
 	dUv.Upload(D.ctx, reinterpret_cast<const V2*>(uv), count); dOut.Alloc(D.ctx, count);
 	if (!D.ctx.ok) return FromCtx(D, SAILOR_PT_ERR_CUDA);
-	SampleTextureKernel k; k.ts.texels = D.texels.p; k.ts.textures = D.textures.p; k.index = textureIndex; k.uv = dUv.p; k.out = dOut.p;
+	SampleTextureKernel k; k.ts.texels = D.texels.p; k.ts.textures = D.textures.p; k.ts.srgbLut = D.srgbLut.p; k.index = textureIndex; k.uv = dUv.p; k.out = dOut.p;
 	launch_for(D.ctx, count, k);
 	std::vector<V4> host(count);
 	dOut.Download(D.ctx, host.data(), count);
 	for (uint32_t i = 0; i < count; i++) { out[4 * i] = host[i].x; out[4 * i + 1] = host[i].y; out[4 * i + 2] = host[i].z; out[4 * i + 3] = host[i].w; }
 	return FromCtx(D, SAILOR_PT_OK);
+}
+
+int32_t SailorPt_ShadeHits(SailorPtScene* s, uint32_t count, const uint32_t* triIds, const float* baryUV, const float* rayDirs, uint32_t numSamples, uint32_t numAmbient, float* out)
+{
+	if (!s || !triIds || !baryUV || !rayDirs || !out) return SAILOR_PT_ERR_ARG;
+	if (!count) return SAILOR_PT_OK;
+	SceneDevice& D = s->dev;
+	DevBuf<uint32_t> dTri; DevBuf<float> dUv, dDir, dOut;
+	dTri.Upload(D.ctx, triIds, count); dUv.Upload(D.ctx, baryUV, (size_t)count * 2); dDir.Upload(D.ctx, rayDirs, (size_t)count * 3); dOut.Alloc(D.ctx, (size_t)count * SAILOR_PT_SHADE_FLOATS);
+	if (!D.ctx.ok) return FromCtx(D, SAILOR_PT_ERR_CUDA);
+	ShadeHitsKernel k;
+	k.shade = D.shade.p; k.materials = D.materials.p; k.tex.texels = D.texels.p; k.tex.textures = D.textures.p; k.tex.srgbLut = D.srgbLut.p;
+	k.tri = dTri.p; k.uv = dUv.p; k.dir = dDir.p; k.out = dOut.p; k.numTris = D.numTris; k.numSamples = numSamples; k.numAmbient = numAmbient;
+	launch_for(D.ctx, count, k);
+	dOut.Download(D.ctx, out, (size_t)count * SAILOR_PT_SHADE_FLOATS);
+	return FromCtx(D, SAILOR_PT_OK);
+}
+
+int32_t SailorPt_SampleGenerators(uint64_t streamKey, uint32_t kind, uint32_t count, float* out)
+{
+	if (!out || kind > 2u) return SAILOR_PT_ERR_ARG;
+	if (!count) return SAILOR_PT_OK;
+	ScopedCtx sc;
+	if (sc.rc != SAILOR_PT_OK) return SetError(sc.rc, sc.ctx.error);
+	const size_t n = (size_t)count * (kind == 2u ? 4u : 1u);
+	DevBuf<float> dOut; DevBuf<uint16_t> dBlue;
+	dOut.Alloc(sc.ctx, n); dBlue.Upload(sc.ctx, kBlueNoiseK, (size_t)kBlueNoiseCount);
+	if (!sc.ctx.ok) return SetError(SAILOR_PT_ERR_CUDA, sc.ctx.error);
+	launch_for(sc.ctx, 1, SampleGeneratorsKernel{ streamKey, kind, count, dBlue.p, dOut.p });
+	dOut.Download(sc.ctx, out, n);
+	if (!sc.ctx.ok) return SetError(SAILOR_PT_ERR_CUDA, sc.ctx.error);
+	return SAILOR_PT_OK;
 }
 
 int32_t SailorPt_EvalLighting(uint32_t count, const float* in, float* out)

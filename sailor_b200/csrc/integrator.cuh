@@ -392,6 +392,100 @@ namespace spt
 	};
 
 	// ---- expand: shade one activation and emit all of its rays ----------------------------------------------------
+	// The shading context of a hit (PathTracer.cpp:636-661) and GetMaterialData (:881-927): interpolated frame, the face normal turned
+	// against the ray, transformed uv, the material's factors times its textures.  One definition for the integrator (ExpandKernel) and for the
+	// parity hook SailorPt_ShadeHits, which compares it value for value with the reference's own GetMaterialData.
+	struct HitShading { SampledData s; V3 faceNormal, tangent, bitangent; V2 uvT; uint32_t matIdx; bool opposite; };
+	SPT_HD void ShadeHit(const V4* shade, const MaterialGpu* materials, const TextureSet& tex, uint32_t tri, float bu, float bv, V3 rayD, HitShading& h)
+	{
+		const V4* S = shade + (size_t)tri * 9;
+		const V4 s0 = ld4(S), s1 = ld4(S + 1), s2 = ld4(S + 2), s3 = ld4(S + 3), s4 = ld4(S + 4), s5 = ld4(S + 5), s6 = ld4(S + 6), s7 = ld4(S + 7), s8 = ld4(S + 8);
+		const float bw = 1.0f - bu - bv;
+		V3 faceNormal = bw * v3(s0.x, s0.y, s0.z) + bu * v3(s1.x, s1.y, s1.z) + bv * v3(s2.x, s2.y, s2.z);
+		h.tangent = bw * v3(s3.x, s3.y, s3.z) + bu * v3(s4.x, s4.y, s4.z) + bv * v3(s5.x, s5.y, s5.z);
+		h.bitangent = bw * v3(s6.x, s6.y, s6.z) + bu * v3(s7.x, s7.y, s7.z) + bv * v3(s8.x, s8.y, s8.z);
+		h.opposite = dot(faceNormal, rayD) < 0.0f;
+		if (!h.opposite) faceNormal = faceNormal * -1.0f;
+		h.faceNormal = faceNormal;
+		const V2 uv = bw * v2(s0.w, s1.w) + bu * v2(s2.w, s3.w) + bv * v2(s4.w, s5.w);
+		h.matIdx = f2u(s6.w);
+		const MaterialGpu& m = materials[h.matIdx];
+		const float* T = m.uvTransform;
+		const float tu = T[0] * uv.x + T[4] * uv.y + T[8] * 1.0f, tv = T[1] * uv.x + T[5] * uv.y + T[9] * 1.0f;
+		h.uvT = v2(tu, tv);
+		// GetMaterialData (:881-927)
+		SampledData& s = h.s;
+		s.baseColor = v4(m.baseColor[0], m.baseColor[1], m.baseColor[2], m.baseColor[3]);
+		V3 nrm = v3(0.0f, 0.0f, 1.0f);
+		s.orm = v3(0.0f, m.roughness, m.metallic);
+		s.emissive = v3(m.emissive[0], m.emissive[1], m.emissive[2]);
+		s.transmission = m.transmission;
+		if (m.texBase != kNoTexture) { const V4 t = SampleTexture(tex, m.texBase, tu, tv); s.baseColor = v4(s.baseColor.x * t.x, s.baseColor.y * t.y, s.baseColor.z * t.z, s.baseColor.w * t.w); }
+		if (m.texEmissive != kNoTexture) { const V4 t = SampleTexture(tex, m.texEmissive, tu, tv); s.emissive = s.emissive * v3(t.x, t.y, t.z); }
+		if (m.texMetallicRoughness != kNoTexture) { const V4 t = SampleTexture(tex, m.texMetallicRoughness, tu, tv); s.orm = v3(t.x, s.orm.y * t.y, s.orm.z * t.z); }
+		if (m.texNormal != kNoTexture) { const V4 t = SampleTexture(tex, m.texNormal, tu, tv); nrm = v3(t.x, t.y, t.z); }
+		if (m.texTransmission != kNoTexture) { const V4 t = SampleTexture(tex, m.texTransmission, tu, tv); s.transmission *= t.x; }
+		if (m.blendMode == kMask) s.baseColor.w = (s.baseColor.w > m.alphaCutoff) ? 1.0f : 0.0f;
+		s.opaque = m.blendMode == kOpaque;
+		s.normal = nrm; s.ior = m.ior; s.thickness = m.thickness;
+	}
+	// normalize(tbn * normal), glm mat3 * vec3 order (type_mat3x3.inl:468-474), PathTracer.cpp:655
+	SPT_HD V3 WorldNormal(const HitShading& h)
+	{
+		const V3 nrm = h.s.normal;
+		return normalize(v3(h.tangent.x * nrm.x + h.bitangent.x * nrm.y + h.faceNormal.x * nrm.z,
+			h.tangent.y * nrm.x + h.bitangent.y * nrm.y + h.faceNormal.y * nrm.z,
+			h.tangent.z * nrm.x + h.bitangent.z * nrm.y + h.faceNormal.z * nrm.z));
+	}
+	// :657-659: alpha-blended surfaces scale the sample counts
+	SPT_HD uint32_t AlphaScaledCount(const SampledData& s, uint32_t count)
+	{
+		const bool alphaBlend = !s.opaque && s.baseColor.w < 1.0f;
+		const uint32_t r = (uint32_t)roundf(s.baseColor.w * (float)count);
+		return alphaBlend ? (r > 1u ? r : 1u) : count;
+	}
+
+	// SailorPt_SampleGenerators (include/sailor_pt.h): the generators exactly as the kernels call them
+	struct SampleGeneratorsKernel
+	{
+		uint64_t key; uint32_t kind, count; const uint16_t* blueNoise; float* out;
+		SPT_KERNEL_BODY void operator()(uint32_t) const
+		{
+			Rng r; r.key = key; r.counter = 0;
+			if (kind == 0u) for (uint32_t i = 0; i < count; i++) out[i] = u2f(r.U32());
+			else if (kind == 1u) for (uint32_t i = 0; i < count; i++) out[i] = r.Float01();
+			else
+			{
+				const uint32_t seedX = r.Seed681(), seedY = r.Seed681();                   // PathTracer.cpp:626-627
+				for (uint32_t m = 0; m < count; m++)
+				{
+					const uint32_t ix = BlueNoiseIndex(key, 0, seedX, m), iy = BlueNoiseIndex(key, 1, seedY, m);
+					out[4 * m] = (float)blueNoise[ix] * (1.0f / 1024.0f); out[4 * m + 1] = (float)blueNoise[iy] * (1.0f / 1024.0f);
+					out[4 * m + 2] = (float)ix; out[4 * m + 3] = (float)iy;
+				}
+			}
+		}
+	};
+
+	// SailorPt_ShadeHits: 28 floats per hit (include/sailor_pt.h)
+	struct ShadeHitsKernel
+	{
+		const V4* shade; const MaterialGpu* materials; TextureSet tex; const uint32_t* tri; const float* uv; const float* dir; float* out; uint32_t numTris, numSamples, numAmbient;
+		SPT_KERNEL_BODY void operator()(uint32_t i) const
+		{
+			float* o = out + (size_t)i * 28;
+			if (tri[i] >= numTris) { for (int k = 0; k < 28; k++) o[k] = 0.0f; return; }
+			HitShading h;
+			ShadeHit(shade, materials, tex, tri[i], uv[2 * i], uv[2 * i + 1], v3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]), h);
+			const V3 N = WorldNormal(h);
+			o[0] = h.s.baseColor.x; o[1] = h.s.baseColor.y; o[2] = h.s.baseColor.z; o[3] = h.s.baseColor.w;
+			o[4] = h.s.orm.x; o[5] = h.s.orm.y; o[6] = h.s.orm.z; o[7] = h.s.emissive.x; o[8] = h.s.emissive.y; o[9] = h.s.emissive.z;
+			o[10] = h.s.normal.x; o[11] = h.s.normal.y; o[12] = h.s.normal.z; o[13] = h.s.transmission; o[14] = h.s.ior; o[15] = h.s.thickness; o[16] = h.s.opaque ? 1.0f : 0.0f;
+			o[17] = N.x; o[18] = N.y; o[19] = N.z; o[20] = h.faceNormal.x; o[21] = h.faceNormal.y; o[22] = h.faceNormal.z; o[23] = h.uvT.x; o[24] = h.uvT.y;
+			o[25] = h.opposite ? 1.0f : 0.0f; o[26] = (float)AlphaScaledCount(h.s, numSamples); o[27] = (float)AlphaScaledCount(h.s, numAmbient);
+		}
+	};
+
 	struct ExpandKernel
 	{
 		IntegratorArgs a; uint32_t level;
@@ -429,34 +523,13 @@ namespace spt
 
 			// ---- :636-671 shading context
 			const uint32_t tri = n.tri;
-			const V4* S = a.shade + (size_t)tri * 9;
-			const V4 s0 = ld4(S), s1 = ld4(S + 1), s2 = ld4(S + 2), s3 = ld4(S + 3), s4 = ld4(S + 4), s5 = ld4(S + 5), s6 = ld4(S + 6), s7 = ld4(S + 7), s8 = ld4(S + 8);
-			const float bu = n.u, bv = n.v, bw = 1.0f - bu - bv;
-			V3 faceNormal = bw * v3(s0.x, s0.y, s0.z) + bu * v3(s1.x, s1.y, s1.z) + bv * v3(s2.x, s2.y, s2.z);
-			const V3 tangent = bw * v3(s3.x, s3.y, s3.z) + bu * v3(s4.x, s4.y, s4.z) + bv * v3(s5.x, s5.y, s5.z);
-			const V3 bitangent = bw * v3(s6.x, s6.y, s6.z) + bu * v3(s7.x, s7.y, s7.z) + bv * v3(s8.x, s8.y, s8.z);
-			const bool opposite = dot(faceNormal, n.rayD) < 0.0f;
-			if (!opposite) faceNormal = faceNormal * -1.0f;
-			const V2 uv = bw * v2(s0.w, s1.w) + bu * v2(s2.w, s3.w) + bv * v2(s4.w, s5.w);
-			const uint32_t matIdx = f2u(s6.w);
-			const MaterialGpu& m = a.materials[matIdx];
-			const float* T = m.uvTransform;
-			const float tu = T[0] * uv.x + T[4] * uv.y + T[8] * 1.0f, tv = T[1] * uv.x + T[5] * uv.y + T[9] * 1.0f;
-			// GetMaterialData (:881-927)
-			SampledData s;
-			s.baseColor = v4(m.baseColor[0], m.baseColor[1], m.baseColor[2], m.baseColor[3]);
-			V3 nrm = v3(0.0f, 0.0f, 1.0f);
-			s.orm = v3(0.0f, m.roughness, m.metallic);
-			s.emissive = v3(m.emissive[0], m.emissive[1], m.emissive[2]);
-			s.transmission = m.transmission;
-			if (m.texBase != kNoTexture) { const V4 t = SampleTexture(a.tex, m.texBase, tu, tv); s.baseColor = v4(s.baseColor.x * t.x, s.baseColor.y * t.y, s.baseColor.z * t.z, s.baseColor.w * t.w); }
-			if (m.texEmissive != kNoTexture) { const V4 t = SampleTexture(a.tex, m.texEmissive, tu, tv); s.emissive = s.emissive * v3(t.x, t.y, t.z); }
-			if (m.texMetallicRoughness != kNoTexture) { const V4 t = SampleTexture(a.tex, m.texMetallicRoughness, tu, tv); s.orm = v3(t.x, s.orm.y * t.y, s.orm.z * t.z); }
-			if (m.texNormal != kNoTexture) { const V4 t = SampleTexture(a.tex, m.texNormal, tu, tv); nrm = v3(t.x, t.y, t.z); }
-			if (m.texTransmission != kNoTexture) { const V4 t = SampleTexture(a.tex, m.texTransmission, tu, tv); s.transmission *= t.x; }
-			if (m.blendMode == kMask) s.baseColor.w = (s.baseColor.w > m.alphaCutoff) ? 1.0f : 0.0f;
-			s.opaque = m.blendMode == kOpaque;
-			s.normal = nrm; s.ior = m.ior; s.thickness = m.thickness;
+			HitShading hs;
+			ShadeHit(a.shade, a.materials, a.tex, tri, n.u, n.v, n.rayD, hs);
+			const MaterialGpu& m = a.materials[hs.matIdx];
+			const SampledData& s = hs.s;
+			const V3 faceNormal = hs.faceNormal, nrm = hs.s.normal;
+			const V3 tangent = hs.tangent, bitangent = hs.bitangent;
+			const bool opposite = hs.opposite;
 
 			const V3 V = -normalize(n.rayD);
 			// tbn * normal, glm mat3 * vec3 order (type_mat3x3.inl:468-474)

@@ -20,7 +20,9 @@ namespace spt
 {
 	inline double HostNow() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
-	struct DeviceTexture { uint32_t width, height, channels, clamping; uint64_t offset; };   // offset into the texel pool (float4 units)
+	// offset: into the texel pool (RGBA8 texels); mode: how CombinedSampler2D::Initialize turns a byte into a float (MaterialUtils.h:42-65)
+	enum TexelMode : uint32_t { kTexelLinear = 0, kTexelSrgb = 1, kTexelNormal = 2 };
+	struct DeviceTexture { uint32_t width, height, channels, clamping; uint64_t offset; uint32_t mode, pad; };
 
 	struct SceneDevice
 	{
@@ -34,7 +36,8 @@ namespace spt
 		DevBuf<V4> vtx, centroid, shade;
 		DevBuf<V2> uv2;
 		DevBuf<MaterialGpu> materials;
-		DevBuf<V4> texels;                    // all textures, float4 texels (vec3 textures leave w = 0)
+		DevBuf<uint32_t> texels;              // all textures as the file's RGBA8 texels (4 bytes each); converted to float at fetch time (textures.cuh)
+		DevBuf<float> srgbLut;                // 256 floats: Utils::SRGBToLinear(byte / 255) evaluated with the host's powf (bit-identical to the reference's)
 		DevBuf<DeviceTexture> textures;
 		std::vector<DeviceTexture> hostTextures;
 		DevBuf<V4> lights;                    // 2 float4 per light: direction, intensity

@@ -3,9 +3,11 @@
 // CombinedSampler2D::Initialize (reference MaterialUtils.h:42-65) turns every RGBA8 texel into float texels at load:
 //   normal maps  texel * (1/127.5) - 1          colour  SRGBToLinear(texel * (1/255))  (alpha: texel * (1/255))
 //   data maps    texel * (1/255)
-// An 8-bit input has 256 possible values per channel, so the conversion is a 256-entry table per mode; the tables
-// are evaluated on the host with the same libm powf the reference build uses (Core/Utils.cpp:59-63), which makes
-// the float texels bit-identical to the reference's, and the device kernel is a pure gather (RGBA8 in, float4 out).
+// The reference keeps those float texels (16 bytes each); here the pool keeps the file's RGBA8 texels (4 bytes each: C4's 224
+// 1024x1024 textures are 0.94 GB instead of 3.76 GB, and an import is one H2D copy per texture) and the conversion runs at fetch time.
+// It is the same single-precision arithmetic on a byte, so the fetched values are bit-identical to the reference's: the two linear
+// modes are one or two exact float operations, and the sRGB curve (which goes through libm's powf, Core/Utils.cpp:59-63) is a
+// 256-entry table evaluated on the host with the powf the reference build uses.
 //
 // CombinedSampler2D::Sample (MaterialUtils.h:75-124): wrap (Clamp: clamp(uv,0,1); Repeat: uv - floor(uv)), scale by
 // (w-1),(h-1) (texel-corner convention, NOT the half-texel convention of hardware filtering), clamped +1 neighbour
@@ -16,25 +18,14 @@
 
 namespace spt
 {
-	struct TexConvertKernel
+	// Utils::SRGBToLinear (Core/Utils.cpp:59-63) of byte / 255: mix(s/12.92, pow((s+0.055)/1.055, 2.4), step(0.04045, s)), arithmetic mix,
+	// evaluated on the host with the libm powf the reference build uses
+	inline void BuildSrgbLut(std::vector<float>& srgb)
 	{
-		const uint32_t* rgba; V4* out; const float* lutR; const float* lutA; uint32_t channels;
-		SPT_KERNEL_BODY void operator()(uint32_t i) const
-		{
-			const uint32_t p = rgba[i];
-			out[i] = v4(lutR[p & 255u], lutR[(p >> 8) & 255u], lutR[(p >> 16) & 255u], channels == 4 ? lutA[p >> 24] : 0.0f);
-		}
-	};
-
-	inline void BuildTexelLuts(std::vector<float>& srgb, std::vector<float>& linear, std::vector<float>& normal)
-	{
-		srgb.resize(256); linear.resize(256); normal.resize(256);
+		srgb.resize(256);
 		for (int i = 0; i < 256; i++)
 		{
 			const float s = (float)i * (1.0f / 255.0f);
-			linear[i] = s;
-			normal[i] = ((float)i * (1.0f / 127.5f)) - 1.0f;
-			// Utils::SRGBToLinear (Core/Utils.cpp:59-63): mix(s/12.92, pow((s+0.055)/1.055, 2.4), step(0.04045, s)), arithmetic mix
 			const float a = s < 0.04045f ? 0.0f : 1.0f;
 			const float lo = s / 12.92f;
 			const float hi = std::pow((s + 0.055f) / 1.055f, 2.4f);
@@ -49,35 +40,41 @@ namespace spt
 		for (const auto& t : Host().textures)
 		{
 			DeviceTexture d; d.width = (uint32_t)t.width; d.height = (uint32_t)t.height; d.channels = t.channels; d.clamping = t.clamping; d.offset = total;
+			d.mode = t.normalMap ? kTexelNormal : (t.srgb ? kTexelSrgb : kTexelLinear); d.pad = 0;
 			total += (uint64_t)t.width * t.height;
 			hostTextures.push_back(d);
 		}
 		if (hostTextures.empty()) return SAILOR_PT_OK;
-		std::vector<float> srgb, linear, normal;
-		BuildTexelLuts(srgb, linear, normal);
-		DevBuf<float> dSrgb, dLinear, dNormal; DevBuf<uint32_t> staging;
-		dSrgb.Upload(ctx, srgb); dLinear.Upload(ctx, linear); dNormal.Upload(ctx, normal);
+		std::vector<float> srgb;
+		BuildSrgbLut(srgb);
+		srgbLut.Upload(ctx, srgb);
 		texels.Alloc(ctx, total);
 		textures.Upload(ctx, hostTextures);
 		if (!ctx.ok) return SAILOR_PT_ERR_CUDA;
+		// the file's RGBA8 texels go to the pool as they are: one transfer per texture, no staging, no conversion pass
 		for (size_t i = 0; i < Host().textures.size(); i++)
 		{
 			const HostTexture& t = Host().textures[i];
-			const uint32_t n = (uint32_t)t.width * (uint32_t)t.height;
-			if (!n) continue;
-			staging.Ensure(ctx, n);
-			DevUpload(ctx, staging.p, t.rgba.data(), (size_t)n * 4);
-			TexConvertKernel k;
-			k.rgba = staging.p; k.out = texels.p + hostTextures[i].offset; k.channels = t.channels;
-			k.lutR = t.normalMap ? dNormal.p : (t.srgb ? dSrgb.p : dLinear.p);
-			k.lutA = dLinear.p;
-			launch_for(ctx, n, k);
-			ctx.Sync();   // staging is reused
+			const size_t n = (size_t)t.width * (size_t)t.height;
+			if (n) DevUpload(ctx, texels.p + hostTextures[i].offset, t.rgba.data(), n * 4);
 		}
 		return ctx.ok ? SAILOR_PT_OK : SAILOR_PT_ERR_CUDA;
 	}
 
-	struct TextureSet { const V4* texels; const DeviceTexture* textures; };
+	struct TextureSet { const uint32_t* texels; const DeviceTexture* textures; const float* srgbLut; };
+
+	// CombinedSampler2D::Initialize (MaterialUtils.h:42-65) for one texel: the same single-precision expressions on the byte (normal maps
+	// byte * (1/127.5) - 1, data maps and every alpha byte * (1/255)); sRGB colour through the 256-entry table.  vec3 textures carry w = 0.
+	SPT_HD V4 TexelToFloat(uint32_t p, uint32_t mode, bool hasAlpha, const float* srgbLut)
+	{
+		const uint32_t r = p & 255u, g = (p >> 8) & 255u, b = (p >> 16) & 255u, a = p >> 24;
+		V4 o;
+		if (mode == kTexelSrgb) { o.x = ldf(srgbLut + r); o.y = ldf(srgbLut + g); o.z = ldf(srgbLut + b); }
+		else if (mode == kTexelNormal) { o.x = ((float)r * (1.0f / 127.5f)) - 1.0f; o.y = ((float)g * (1.0f / 127.5f)) - 1.0f; o.z = ((float)b * (1.0f / 127.5f)) - 1.0f; }
+		else { o.x = (float)r * (1.0f / 255.0f); o.y = (float)g * (1.0f / 255.0f); o.z = (float)b * (1.0f / 255.0f); }
+		o.w = hasAlpha ? (float)a * (1.0f / 255.0f) : 0.0f;
+		return o;
+	}
 
 	// CombinedSampler2D::Sample<T> (MaterialUtils.h:75-124); vec3 textures carry w = 0
 	SPT_HD V4 SampleTexture(const TextureSet& ts, uint32_t index, float u, float v)
@@ -92,9 +89,11 @@ namespace spt
 		const int32_t x1 = (x0 + 1) < (W - 1) ? (x0 + 1) : (W - 1);    // std::min(tX0 + 1, m_width - 1)
 		const int32_t y1 = (y0 + 1) < (H - 1) ? (y0 + 1) : (H - 1);
 		const float fracX = fx - (float)x0, fracY = fy - (float)y0;
-		const V4* base = ts.texels + t.offset;
-		const V4 tl = ld4(base + x0 + (int64_t)y0 * W), tr = ld4(base + x1 + (int64_t)y0 * W);
-		const V4 bl = ld4(base + x0 + (int64_t)y1 * W), br = ld4(base + x1 + (int64_t)y1 * W);
+		const uint32_t* base = ts.texels + t.offset;
+		const bool alpha = t.channels == 4;
+		const uint32_t ptl = ldu(base + x0 + (int64_t)y0 * W), ptr = ldu(base + x1 + (int64_t)y0 * W), pbl = ldu(base + x0 + (int64_t)y1 * W), pbr = ldu(base + x1 + (int64_t)y1 * W);
+		const V4 tl = TexelToFloat(ptl, t.mode, alpha, ts.srgbLut), tr = TexelToFloat(ptr, t.mode, alpha, ts.srgbLut);
+		const V4 bl = TexelToFloat(pbl, t.mode, alpha, ts.srgbLut), br = TexelToFloat(pbr, t.mode, alpha, ts.srgbLut);
 		V4 r;
 		{
 			const float top = tl.x + fracX * (tr.x - tl.x), bot = bl.x + fracX * (br.x - bl.x); r.x = top + fracY * (bot - top);

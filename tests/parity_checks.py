@@ -8,10 +8,13 @@ texel fetch + bilinear blend, and the 8-bit output; relative
 converged images.
 """
 import hashlib
+import os
 
 import numpy as np
 
 from sailor_b200.capi import Params
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 
 NOHIT = 0xFFFFFFFF
 
@@ -269,3 +272,66 @@ def check_multi_device_frame(lib, path, devices=3, **base):
         a, _ = s.render(Params(**kw2)); b, _ = s.render(Params(device_count=devices, **kw2))
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
     return st["devicesUsed"]
+
+
+def check_shade_hits(lib, oracle, path, n=4000, seed=5, num_samples=7, num_ambient=5):
+    """Rows a13/a15: the shading context of a hit -- interpolated frame, flipped face normal, uvTransform, every field of
+    GetMaterialData (factors x bilinear texture samples, MASK cut-off), world normal, alpha-scaled sample counts -- is BIT-IDENTICAL to
+    the reference's own GetMaterialData / Raytrace head (PathTracer.cpp:636-661, 881-927) at random points of random triangles,
+    including triangle corners and edges."""
+    r = np.random.RandomState(seed)
+    with lib.load_scene(path) as a, oracle.load_scene(path) as b:
+        nt = a.counts()["triangles"]
+        tri = r.randint(0, nt, n).astype(np.uint32)
+        bary = r.dirichlet((1.0, 1.0, 1.0), n).astype(np.float32)[:, 1:]
+        bary[:16] = [[0, 0], [1, 0], [0, 1], [0.5, 0.5], [0.5, 0], [0, 0.5], [0.25, 0.25], [1.0 / 3, 1.0 / 3]] * 2
+        tri[n - 1] = nt + 7                                   # out of range: all zeros from both
+        d = r.normal(size=(n, 3)).astype(np.float32)
+        got = a.shade_hits(tri, bary, d, num_samples, num_ambient)
+        ref = b.shade_hits(tri, bary, d, num_samples, num_ambient)
+    bad = np.argwhere(bits(got) != bits(ref))
+    assert bad.size == 0, "shading context differs at %d of %d values, first (hit, field) %s: %r vs %r" % (len(bad), got.size, bad[0], got[tuple(bad[0])], ref[tuple(bad[0])])
+    return got
+
+
+def check_sample_generators(lib):
+    """Row a17: the counter-based generators have the distributions of the reference's (glm::linearRand on rand() % 255 bytes,
+    glm/gtc/random.inl:19-27,66-85,176-183; NextVec2_BlueNoise table walk, PathTracer.cpp:934-1077)."""
+    n = 1 << 18
+    u = lib.sample_generators(12345, 0, n)
+    by = u.view(np.uint8).reshape(n, 4)
+    assert by.max() == 254, "a byte is rand() % 255: never 255"
+    for k in range(4):
+        h = np.bincount(by[:, k], minlength=255)[:255]
+        assert h.min() > 0 and abs(h - n / 255.0).max() < 6.0 * np.sqrt(n / 255.0), "byte %d is not uniform over 0..254" % k
+    assert not np.array_equal(u[:1000], lib.sample_generators(12346, 0, 1000)), "streams of different keys differ"
+    assert np.array_equal(u[:1000], lib.sample_generators(12345, 0, 1000)), "a stream is a pure function of its key"
+    f = lib.sample_generators(99, 1, n)
+    raw = lib.sample_generators(99, 0, n)
+    # linearRand(0.f, 1.f) = float(u32) / float(UINT32_MAX) * (Max - Min) + Min (random.inl:176-183), bit for bit
+    expect = (raw.astype(np.float32) / np.float32(4294967296.0)) * np.float32(1.0) + np.float32(0.0)
+    assert np.array_equal(bits(f), bits(expect))
+    assert f.min() >= 0.0 and f.max() < 1.0 and abs(float(f.mean()) - 0.498) < 0.003      # top byte <= 254: mean = 127/255 + ...
+    # blue-noise walk: values are table[k] / 1024, indices advance by one up to 687 and restart at linearRand(0, 680)
+    table = blue_noise_table()
+    for key in (1, 2, 77):
+        w = lib.sample_generators(key, 2, 3000)
+        ix, iy = w[:, 2].astype(np.int64), w[:, 3].astype(np.int64)
+        assert np.array_equal(w[:, 0], table[ix].astype(np.float32) / np.float32(1024)) and np.array_equal(w[:, 1], table[iy].astype(np.float32) / np.float32(1024))
+        for idx in (ix, iy):
+            assert idx.min() >= 0 and idx.max() <= 687
+            step = np.diff(idx)
+            restart = step != 1
+            assert np.all(idx[:-1][restart] == 687) and np.all(idx[1:][restart] <= 680) and restart.sum() >= 3
+        assert ix[0] <= 680 and iy[0] <= 680
+
+
+def blue_noise_table():
+    """The integers of sailor_b200/csrc/blue_noise_table.h (value = k / 1024)."""
+    import re
+    src = open(os.path.join(ROOT, "sailor_b200", "csrc", "blue_noise_table.h")).read()
+    body = src[src.index("kBlueNoiseK[kBlueNoiseCount] = {") :]
+    body = body[body.index("{") + 1:body.index("};")]
+    t = np.array([int(x) for x in re.findall(r"\d+", body)], np.int64)
+    assert len(t) == 688
+    return t

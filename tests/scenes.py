@@ -186,6 +186,21 @@ def cube(path):
     return g.write(path)
 
 
+def zero_normal_cube(path):
+    """The cube with a NORMAL accessor of zeros on a floor quad: every shading normal on the cube is normalize(0) = NaN, so
+    LightingModel::Sample can never return a valid direction there and the reference's rejection loop (PathTracer.cpp:761-767) would
+    spin forever.  The product caps the loop at 4096 tries; tests check that such a frame finishes and stays finite."""
+    g = GlbBuilder()
+    pos, nrm, idx = _cube_arrays(0.3)
+    mat = g.material(pbrMetallicRoughness={"baseColorFactor": [0.8, 0.8, 0.8, 1.0], "metallicFactor": 0.0, "roughnessFactor": 0.5})
+    g.node(mesh=g.mesh(pos, idx, mat, nrm=np.zeros_like(nrm)), translation=[0.0, 0.3, 0.0])
+    floor = np.array([[-2, 0, -2], [2, 0, -2], [-2, 0, 2], [2, 0, 2]], np.float32)
+    g.node(mesh=g.mesh(floor, np.array([0, 2, 1, 1, 2, 3], np.uint16), mat, nrm=np.tile(np.array([[0, 1, 0]], np.float32), (4, 1))))
+    g.j["cameras"] = [{"type": "perspective", "perspective": {"yfov": 0.7, "aspectRatio": 1.5, "znear": 0.01, "zfar": 100.0}}]
+    g.node(camera=0, name="main", translation=[0.0, 1.0, 2.2], rotation=look_at_quat((0.0, -0.35, -1.0)))
+    return g.write(path)
+
+
 def default_material_scene(path, with_materials=False):
     """Three cubes that exercise the DEFAULT material and malformed attribute streams (the reference's Assimp front end appends
     a default material; a primitive without `material`, or with an index outside the array, uses it):
@@ -465,6 +480,9 @@ def ensure(directory, name, **kw):
         n, k = kw.get("n", 707), kw.get("instances", 10)
         p = os.path.join(directory, "instanced_%d_x%d.glb" % (n, k))
         return p if os.path.exists(p) else instanced_heightfield(p, n=n, instances=k)
+    if name == "zero_normals":
+        p = os.path.join(directory, "zero_normals.glb")
+        return p if os.path.exists(p) else zero_normal_cube(p)
     if name == "nomat":
         wm = bool(kw.get("with_materials", False))
         p = os.path.join(directory, "nomat_%d.glb" % int(wm))

@@ -230,3 +230,47 @@ def test_trim_memory_releases_the_working_set_and_rendering_goes_on(gpu, scene_d
         assert torch.cuda.mem_get_info()[0] >= free_before
         b, _ = s.render(p)                       # the scene is still valid; the arenas come back
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("name,kw", [("pbr", {}), ("gallery", {"tex_size": 64, "tiles": 4, "emitters": 8})])
+def test_shading_context_is_bit_identical_to_get_material_data(gpu, oracle, scene_dir, name, kw):
+    """a13 deterministically: SailorPt_ShadeHits (the function ExpandKernel calls) against the reference's own GetMaterialData."""
+    pc.check_shade_hits(gpu, oracle, _scene(scene_dir, name, kw), n=20000)
+
+
+def test_sample_generators_have_the_reference_distributions(gpu):
+    pc.check_sample_generators(gpu)
+
+
+@pytest.mark.parametrize("key,frames", [("c1_512", 512), ("c2_480x270", 64)])
+def test_converged_image_tolerance_at_baseline_config_sizes(gpu, scene_dir, key, frames):
+    """BASELINE configs[0] at FULL size (512x512, 16 spp, 4 bounces) and configs[1] at 480x270 (256 spp, 8 bounces): the mean of `frames`
+    GPU frames against the mean of as many reference frames (tests/golden/make_golden_converged.py).  Stated tolerance: mean relative
+    error < 1.5 % over all pixels and channels, and < 2 % for every channel on its own and for every quadrant of the image (a per-pixel
+    bias that averages out over the frame would show there)."""
+    import os
+    from golden import make_golden_converged as M
+    ref = np.load(os.path.join(os.path.dirname(M.__file__), "converged.npz"))[key].astype(np.float64)
+    kw = M.C1 if key == "c1_512" else M.C2
+    img = pc.render_mean(gpu, _scene(scene_dir, "cube", {}), Params(**kw), seeds=range(5000, 5000 + frames))
+    assert img.shape == ref.shape
+    err = pc.mean_rel_error(img, ref)
+    per_channel = [pc.mean_rel_error(img[..., c], ref[..., c]) for c in range(3) if ref[..., c].mean() > 1e-3]
+    h, w = ref.shape[:2]
+    quads = [pc.mean_rel_error(img[y:y + h // 2, x:x + w // 2], ref[y:y + h // 2, x:x + w // 2]) for y in (0, h // 2) for x in (0, w // 2)]
+    print("converged-image mean relative error %s: %.4f per channel %s per quadrant %s" % (key, err, ["%.4f" % e for e in per_channel], ["%.4f" % e for e in quads]))
+    assert err < 0.015 and max(per_channel) < 0.02 and max(quads) < 0.02
+    # the means themselves (bias, not noise): within 0.3 %
+    assert abs(img.mean() - ref.mean()) / ref.mean() < 0.003
+
+
+def test_rejection_loop_cap_keeps_the_frame_finite(gpu, scene_dir):
+    """A surface whose shading normal is NaN (zero NORMAL accessor) never yields a valid BSDF sample: the reference's rejection loop
+    (PathTracer.cpp:761-767) would spin forever, the product gives up after 4096 tries.  The frame finishes, is finite
+    and deterministic, and the rest of the scene (the floor) is lit as usual."""
+    p = Params(height=96, num_samples=4, num_ambient_samples=4, max_bounces=3, msaa=4, ambient=(1.0, 1.0, 1.0), seed=2)
+    with gpu.load_scene(_scene(scene_dir, "zero_normals", {})) as s:
+        a, _ = s.render(p)
+        b, _ = s.render(p)
+    assert np.isfinite(a).all() and np.array_equal(a, b)
+    assert 0.0 <= a.min() and a.max() <= 64.0 and a[-8:].mean() > 0.05          # bottom rows: the floor in front of the cube
