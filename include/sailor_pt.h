@@ -117,7 +117,8 @@ typedef struct SailorPtStats {
 	double secondsCall;       /* product, RenderResident: the whole call between two CUDA events on the launch stream (BVH build + render + output stage) */
 	uint64_t replayedRays;    /* product: rays of the last call that the fast secondary-ray walk handed to the exact (reference visit order) kernel */
 	uint32_t devicesUsed;     /* product, render calls: CUDA devices the frame was spread over (SailorPtParams::deviceCount, clamped to what the box has) */
-	uint32_t reserved0;
+	uint32_t secondaryTraversal; /* product, render calls: kernel that traced the secondary rays: 1 origin-local walk, 2 exact top-down kernel (picked once per scene by a
+	                                timed probe, same results either way), 0 the shared-memory kernel of small scenes / not applicable */
 } SailorPtStats;
 
 /* ---- the reference entry points (PathTracer.h:34-36) ---- */
@@ -245,6 +246,12 @@ SAILOR_PT_API int32_t SailorPt_SampleTexture(SailorPtScene* scene, uint32_t text
 /* LightingModel function table (LightingModel.cpp:28-386) on `count` inputs; see tests/test_lighting.py for the
  * record layout (in: 24 floats, out: 28 floats). */
 SAILOR_PT_API int32_t SailorPt_EvalLighting(uint32_t count, const float* in, float* out);
+
+/* The image decoder of the glTF front end on a file held in memory: RGBA8, row 0 = top, i.e. what the reference's texture loader gets from
+ * stbi_load_from_memory(..., STBI_rgb_alpha) (MaterialUtils.h:226-249).  PNG (all colour types and bit depths, interlaced too) and JPEG
+ * (baseline and progressive, any subsampling, grey / YCbCr / RGB / CMYK / YCCK) decode byte-identically to stb_image; other formats return
+ * SAILOR_PT_ERR_UNSUPPORTED.  rgba8 may be NULL to query the size; capacity is the size of rgba8 in bytes. */
+SAILOR_PT_API int32_t SailorPt_DecodeImage(const uint8_t* data, uint64_t size, uint32_t* width, uint32_t* height, uint8_t* rgba8, uint64_t capacity);
 
 /* The shading context the integrator builds at a hit, value for value (parity hook for rows a13/a15 of SURVEY.md 8):
  * PathTracer::Raytrace lines 636-661 (interpolated frame, face normal turned against the ray, uv through the material's

@@ -955,6 +955,20 @@ int32_t SailorPt_SampleTexture(SailorPtScene* s, uint32_t textureIndex, uint32_t
 	return SAILOR_PT_OK;
 }
 
+int32_t SailorPt_DecodeImage(const uint8_t* data, uint64_t size, uint32_t* width, uint32_t* height, uint8_t* rgba8, uint64_t capacity)
+{
+	// the reference's own decoder call (MaterialUtils.h:226-249): stbi_load_from_memory(..., STBI_rgb_alpha)
+	if (!data || !size || !width || !height) return SAILOR_PT_ERR_ARG;
+	int w = 0, h = 0, ch = 0;
+	unsigned char* px = stbi_load_from_memory(data, (int)size, &w, &h, &ch, 4);
+	if (!px) { t_lastError = "stbi_load_from_memory failed"; return SAILOR_PT_ERR_FORMAT; }
+	*width = (uint32_t)w; *height = (uint32_t)h;
+	int32_t rc = SAILOR_PT_OK;
+	if (rgba8) { if (capacity < (uint64_t)w * h * 4) rc = SAILOR_PT_ERR_ARG; else memcpy(rgba8, px, (size_t)w * h * 4); }
+	stbi_image_free(px);
+	return rc;
+}
+
 int32_t SailorPt_ShadeHits(SailorPtScene* s, uint32_t count, const uint32_t* triIds, const float* baryUV, const float* rayDirs, uint32_t numSamples, uint32_t numAmbient, float* out)
 {
 	// The head of PathTracer::Raytrace after a hit (PathTracer.cpp:636-661), statement for statement, around the reference's OWN

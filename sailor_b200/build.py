@@ -28,7 +28,7 @@ def _nvcc():
 
 
 def sources():
-    return [os.path.join(SRC, f) for f in ("capi.cu", "backend.cu", "gltf_loader.cpp", "png_codec.cpp", "image_io.cpp")]
+    return [os.path.join(SRC, f) for f in ("capi.cu", "backend.cu", "gltf_loader.cpp", "png_codec.cpp", "jpeg_codec.cpp", "image_io.cpp")]
 
 
 def needs_build():

@@ -43,7 +43,7 @@ class SailorPtStats(C.Structure):
         ("batches", C.c_uint32), ("h2dBytes", C.c_uint64), ("d2hBytes", C.c_uint64),
         ("secondsExpand", C.c_double), ("secondsFanOut", C.c_double), ("secondsClassify", C.c_double), ("secondsGather", C.c_double),
         ("fanOutSamples", C.c_uint64), ("secondsCall", C.c_double), ("replayedRays", C.c_uint64),
-        ("devicesUsed", C.c_uint32), ("reserved0", C.c_uint32),
+        ("devicesUsed", C.c_uint32), ("secondaryTraversal", C.c_uint32),
     ]
 
     def as_dict(self):
@@ -61,7 +61,7 @@ SYMBOLS = [
     "SailorPt_OutputStage", "SailorPt_SampleTexture", "SailorPt_EvalLighting", "SailorPt_GetStats",
     "SailorPt_LastError", "SailorPt_Backend", "SailorPt_RenderResident", "SailorPt_ReadResident", "SailorPt_CopyResidentToDevice", "SailorPt_SetDevice", "SailorPt_OutputStageResident",
     "SailorPt_PinHostBuffer", "SailorPt_UnpinHostBuffer", "SailorPt_WriteImage", "SailorPt_CompareImages", "SailorPt_RenderProgressive",
-    "SailorPt_TrimMemory", "SailorPt_IntersectRaysEx", "SailorPt_ShadeHits", "SailorPt_SampleGenerators",
+    "SailorPt_TrimMemory", "SailorPt_IntersectRaysEx", "SailorPt_ShadeHits", "SailorPt_SampleGenerators", "SailorPt_DecodeImage",
 ]
 
 
@@ -148,6 +148,7 @@ class Library:
         lib.SailorPt_OutputStage.argtypes = [C.c_uint32, C.c_uint32, P(C.c_float), P(C.c_uint8)]
         lib.SailorPt_SampleTexture.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, P(C.c_float), P(C.c_float)]
         lib.SailorPt_EvalLighting.argtypes = [C.c_uint32, P(C.c_float), P(C.c_float)]
+        lib.SailorPt_DecodeImage.argtypes = [C.c_char_p, C.c_uint64, P(C.c_uint32), P(C.c_uint32), P(C.c_uint8), C.c_uint64]
         lib.SailorPt_ShadeHits.argtypes = [C.c_void_p, C.c_uint32, P(C.c_uint32), P(C.c_float), P(C.c_float), C.c_uint32, C.c_uint32, P(C.c_float)]
         lib.SailorPt_SampleGenerators.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, P(C.c_float)]
         lib.SailorPt_GetStats.argtypes = [P(SailorPtStats)]
@@ -232,6 +233,14 @@ class Library:
         h, w, _ = linear.shape
         out = np.empty((h, w, 3), np.uint8)
         self.check(self.lib.SailorPt_OutputStage(w, h, _ptr(linear, C.c_float), _ptr(out, C.c_uint8)), "SailorPt_OutputStage")
+        return out
+
+    def decode_image(self, data: bytes):
+        """SailorPt_DecodeImage: an image file in memory -> uint8[h, w, 4] (stbi_load_from_memory(..., 4) convention)."""
+        w, h = C.c_uint32(0), C.c_uint32(0)
+        self.check(self.lib.SailorPt_DecodeImage(data, len(data), C.byref(w), C.byref(h), None, 0), "SailorPt_DecodeImage")
+        out = np.empty((h.value, w.value, 4), np.uint8)
+        self.check(self.lib.SailorPt_DecodeImage(data, len(data), C.byref(w), C.byref(h), _ptr(out, C.c_uint8), out.nbytes), "SailorPt_DecodeImage")
         return out
 
     def sample_generators(self, key, kind, count):

@@ -585,6 +585,7 @@ namespace
 		}
 		g_stats.secondsOutput = tOut;
 		g_stats.devicesUsed = (uint32_t)N;
+		g_stats.secondaryTraversal = (P.hasFast && !(p->flags & (SAILOR_PT_FLAG_EXACT_TRAVERSAL | SAILOR_PT_FLAG_WIDE_TRAVERSAL))) ? P.traceChoice : 0u;
 		g_stats.secondsCall = g_stats.secondsTotal = HostNow() - t0;      // several devices: no common CUDA clock, host clock around the whole call
 		DevSetCurrent(home);
 		return FromCtx(P, SAILOR_PT_OK);
@@ -636,6 +637,7 @@ int32_t SailorPt_RenderResident(SailorPtScene* s, const SailorPtParams* p, uint3
 	g_stats.secondsGather = rs.secondsStage[3]; g_stats.fanOutSamples = rs.fanOutSamples; g_stats.replayedRays = rs.replayedRays; g_stats.secondsOutput = tOut; g_stats.secondsBvhBuild = tBuild; g_stats.traverseLaunches = rs.traverseLaunches; g_stats.batches = rs.batches;
 	g_stats.kernelLaunches = D.ctx.kernelLaunches; g_stats.h2dBytes = D.ctx.h2dBytes; g_stats.d2hBytes = D.ctx.d2hBytes;
 	g_stats.devicesUsed = 1u;
+	g_stats.secondaryTraversal = (D.hasFast && !(p->flags & (SAILOR_PT_FLAG_EXACT_TRAVERSAL | SAILOR_PT_FLAG_WIDE_TRAVERSAL))) ? D.traceChoice : 0u;
 	g_stats.secondsTotal = HostNow() - t0;
 	return FromCtx(D, SAILOR_PT_OK);
 }
@@ -862,6 +864,21 @@ int32_t SailorPt_SampleTexture(SailorPtScene* s, uint32_t textureIndex, uint32_t
 	dOut.Download(D.ctx, host.data(), count);
 	for (uint32_t i = 0; i < count; i++) { out[4 * i] = host[i].x; out[4 * i + 1] = host[i].y; out[4 * i + 2] = host[i].z; out[4 * i + 3] = host[i].w; }
 	return FromCtx(D, SAILOR_PT_OK);
+}
+
+int32_t SailorPt_DecodeImage(const uint8_t* data, uint64_t size, uint32_t* width, uint32_t* height, uint8_t* rgba8, uint64_t capacity)
+{
+	if (!data || !size || !width || !height) return SAILOR_PT_ERR_ARG;
+	int32_t w = 0, h = 0; std::vector<uint8_t> rgba; std::string err;
+	const int rc = DecodeImageRgba8(data, (size_t)size, w, h, rgba, err);
+	if (rc != SAILOR_PT_OK) return SetError(rc, err);
+	*width = (uint32_t)w; *height = (uint32_t)h;
+	if (rgba8)
+	{
+		if (capacity < rgba.size()) return SetError(SAILOR_PT_ERR_ARG, "image buffer too small");
+		memcpy(rgba8, rgba.data(), rgba.size());
+	}
+	return SAILOR_PT_OK;
 }
 
 int32_t SailorPt_ShadeHits(SailorPtScene* s, uint32_t count, const uint32_t* triIds, const float* baryUV, const float* rayDirs, uint32_t numSamples, uint32_t numAmbient, float* out)

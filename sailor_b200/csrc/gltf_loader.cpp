@@ -592,7 +592,7 @@ namespace spt
 				else if (im.at("uri").type == Json::String) { if (!LoadUri(im.at("uri").str, g.baseDir, bytes)) return false; }
 				else return false;
 				std::string perr;
-				return DecodePngRgba8(bytes.data(), bytes.size(), t.width, t.height, t.rgba, perr) == SAILOR_PT_OK;
+				return DecodeImageRgba8(bytes.data(), bytes.size(), t.width, t.height, t.rgba, perr) == SAILOR_PT_OK;
 			};
 
 		// materials + textures (PathTracer.cpp:164-360)
@@ -714,7 +714,7 @@ namespace spt
 			for (auto& t : pool) t.join();
 			if (failed) badImage = true;
 		}
-		if (badImage) { err = "an image could not be decoded (only PNG is supported)"; return SAILOR_PT_ERR_FORMAT; }
+		if (badImage) { err = "an image could not be decoded (PNG and JPEG are supported)"; return SAILOR_PT_ERR_FORMAT; }
 
 		// directional lights (PathTracer.cpp:362-381)
 		for (size_t i = 0; i < numLights; i++)

@@ -67,6 +67,9 @@ namespace spt
 		std::vector<HostCamera> cameras;
 		std::vector<HostLight> lights;
 		uint64_t numTriangles = 0;
+		// which kernel traces this scene's secondary rays fastest (0 unknown; render.cuh decides it with a timed probe on the first frame): kept with the
+		// parsed file so that reloads served by the scene cache and the per-device replicas of a multi-device render do not probe again
+		mutable uint32_t traversalChoice = 0;
 	};
 
 	// returns SAILOR_PT_OK or a negative SAILOR_PT_ERR_*; err receives a message
@@ -75,6 +78,11 @@ namespace spt
 	// PNG codec (png_codec.cpp).  Decode follows stb_image's conventions (RGBA8, 16-bit -> high byte, low bit depths
 	// scaled, palette/tRNS expanded) because the reference decodes with stbi_load(..., STBI_rgb_alpha) (MaterialUtils.h:226-249).
 	int DecodePngRgba8(const uint8_t* data, size_t size, int32_t& w, int32_t& h, std::vector<uint8_t>& rgba, std::string& err);
+	// JPEG codec (jpeg_codec.cpp): baseline + progressive, byte-identical to stb_image's decoder
+	bool IsJpeg(const uint8_t* data, size_t size);
+	int DecodeJpegRgba8(const uint8_t* data, size_t size, int32_t& w, int32_t& h, std::vector<uint8_t>& rgba, std::string& err);
+	// any supported image file in memory -> RGBA8 (stbi_load_from_memory(..., STBI_rgb_alpha) convention)
+	int DecodeImageRgba8(const uint8_t* data, size_t size, int32_t& w, int32_t& h, std::vector<uint8_t>& rgba, std::string& err);
 	int EncodePngRgb8(const char* path, uint32_t w, uint32_t h, const uint8_t* rgb, std::string& err);
 
 	// linear image dumps, comparison, progressive-render checkpoints (image_io.cpp)

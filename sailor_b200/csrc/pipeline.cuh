@@ -52,6 +52,9 @@ namespace spt
 		uint32_t rootRef = 0;
 		// origin-local traversal layout (trace_fast.cuh): built with every BVH the shared-memory kernel does not take
 		bool hasFast = false;
+		// which kernel traces the secondary rays of this scene: 0 not decided yet, 1 origin-local walk, 2 exact (top-down) kernel.  Decided once per
+		// geometry by a timed probe on the first level of the first frame (render.cuh); the results are identical either way.
+		uint32_t traceChoice = 0, traceChoiceTris = 0; float probeMs[2] = { 0.0f, 0.0f };
 		DevBuf<FNode> fnodes; DevBuf<FTri> ftris; DevBuf<FStart> fstart; DevBuf<FHeader> fheader; DevBuf<uint32_t> nodeUp;
 		// wide layout (wide_bvh.cuh): an alternative traversal layout, built on demand (SAILOR_PT_FLAG_WIDE_TRAVERSAL / SAILOR_PT_RAYS_WIDE)
 		bool hasWide = false;

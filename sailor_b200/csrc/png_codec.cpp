@@ -78,29 +78,31 @@ namespace spt
 			off += 12 + (size_t)len;
 		}
 		if (!haveHdr || !width || !height || width > 65536 || height > 65536) { err = "bad PNG header"; return SAILOR_PT_ERR_FORMAT; }
-		if (interlace) { err = "interlaced PNG is not supported"; return SAILOR_PT_ERR_UNSUPPORTED; }
+		if (interlace > 1) { err = "bad PNG interlace method"; return SAILOR_PT_ERR_FORMAT; }
 		int channels;
 		switch (color) { case 0: channels = 1; break; case 2: channels = 3; break; case 3: channels = 1; break; case 4: channels = 2; break; case 6: channels = 4; break; default: err = "bad PNG colour type"; return SAILOR_PT_ERR_FORMAT; }
 		if (!(depth == 1 || depth == 2 || depth == 4 || depth == 8 || depth == 16)) { err = "bad PNG depth"; return SAILOR_PT_ERR_FORMAT; }
 		const uint32_t bitsPerPixel = (uint32_t)channels * depth;
-		const uint32_t rowBytes = (width * bitsPerPixel + 7) / 8;
 		const uint32_t bpp = bitsPerPixel >= 8 ? bitsPerPixel / 8 : 1;
 
-		std::vector<uint8_t> raw((size_t)(rowBytes + 1) * height);
+		// Adam7 (interlace method 1): seven reduced images, each filtered on its own; pass p holds the pixels (yOrig + j * ySpc, xOrig + i * xSpc)
+		static const uint32_t xOrig[7] = { 0, 4, 0, 2, 0, 1, 0 }, yOrig[7] = { 0, 0, 4, 0, 2, 0, 1 }, xSpc[7] = { 8, 8, 4, 4, 2, 2, 1 }, ySpc[7] = { 8, 8, 8, 4, 4, 2, 2 };
+		const int passes = interlace ? 7 : 1;
+		size_t rawSize = 0;
+		for (int ps = 0; ps < passes; ps++)
+		{
+			const uint32_t pw = interlace ? (width > xOrig[ps] ? (width - xOrig[ps] + xSpc[ps] - 1) / xSpc[ps] : 0u) : width, ph = interlace ? (height > yOrig[ps] ? (height - yOrig[ps] + ySpc[ps] - 1) / ySpc[ps] : 0u) : height;
+			if (pw && ph) rawSize += (size_t)((pw * bitsPerPixel + 7) / 8 + 1) * ph;
+		}
+		std::vector<uint8_t> raw(rawSize);
 		uLongf rawLen = (uLongf)raw.size();
 		const int zr = uncompress(raw.data(), &rawLen, idat.data(), (uLong)idat.size());
-		if (zr != Z_OK || rawLen != raw.size()) { err = "PNG inflate failed"; return SAILOR_PT_ERR_FORMAT; }
-		std::vector<uint8_t> img((size_t)rowBytes * height);
-		if (!Unfilter(raw, 0, rowBytes, height, bpp, img.data())) { err = "bad PNG filter"; return SAILOR_PT_ERR_FORMAT; }
+		if ((zr != Z_OK && zr != Z_BUF_ERROR) || rawLen != raw.size()) { err = "PNG inflate failed"; return SAILOR_PT_ERR_FORMAT; }
 
 		w = (int32_t)width; h = (int32_t)height;
 		rgba.resize((size_t)width * height * 4);
 		static const uint8_t depthScale[9] = { 0, 0xff, 0x55, 0, 0x11, 0, 0, 0, 0x01 };
-		for (uint32_t y = 0; y < height; y++)
-		{
-			const uint8_t* row = img.data() + (size_t)y * rowBytes;
-			uint8_t* o = rgba.data() + (size_t)y * width * 4;
-			for (uint32_t x = 0; x < width; x++, o += 4)
+		auto pixel = [&](const uint8_t* row, uint32_t x, uint8_t* o)
 			{
 				uint32_t s[4] = { 0, 0, 0, 0 };  // raw samples (full depth)
 				for (int c = 0; c < channels; c++)
@@ -135,6 +137,22 @@ namespace spt
 				case 4: o[0] = o[1] = o[2] = to8(s[0]); o[3] = to8(s[1]); break;
 				default: o[0] = to8(s[0]); o[1] = to8(s[1]); o[2] = to8(s[2]); o[3] = to8(s[3]); break;
 				}
+			};
+		std::vector<uint8_t> img;
+		size_t rawOff = 0;
+		for (int ps = 0; ps < passes; ps++)
+		{
+			const uint32_t x0 = interlace ? xOrig[ps] : 0, y0 = interlace ? yOrig[ps] : 0, dx = interlace ? xSpc[ps] : 1, dy = interlace ? ySpc[ps] : 1;
+			const uint32_t pw = width > x0 ? (width - x0 + dx - 1) / dx : 0u, ph = height > y0 ? (height - y0 + dy - 1) / dy : 0u;
+			if (!pw || !ph) continue;
+			const uint32_t passRowBytes = (pw * bitsPerPixel + 7) / 8;
+			img.assign((size_t)passRowBytes * ph, 0);
+			if (!Unfilter(raw, rawOff, passRowBytes, ph, bpp, img.data())) { err = "bad PNG filter"; return SAILOR_PT_ERR_FORMAT; }
+			rawOff += (size_t)(passRowBytes + 1) * ph;
+			for (uint32_t j = 0; j < ph; j++)
+			{
+				const uint8_t* row = img.data() + (size_t)j * passRowBytes;
+				for (uint32_t i = 0; i < pw; i++) pixel(row, i, rgba.data() + ((size_t)(y0 + j * dy) * width + (x0 + i * dx)) * 4);
 			}
 		}
 		return SAILOR_PT_OK;

@@ -270,7 +270,19 @@ namespace spt
 		const bool exactOnly = (p.flags & SAILOR_PT_FLAG_EXACT_TRAVERSAL) != 0u;
 		if (!exactOnly && (p.flags & SAILOR_PT_FLAG_WIDE_TRAVERSAL)) { const int rcw = D.EnsureWide(); if (rcw != SAILOR_PT_OK) return rcw; }
 		const bool useWide = !exactOnly && (p.flags & SAILOR_PT_FLAG_WIDE_TRAVERSAL) && D.hasWide;
-		const bool useFast = !exactOnly && !useWide && D.hasFast;
+		bool useFast = !exactOnly && !useWide && D.hasFast;
+		// The origin-local walk wins where occluders are near the ray origin (a 1M-triangle terrain: x1.1 over the top-down kernel) and loses
+		// where rays cross the scene (a gallery of boxes under far emitters: x0.7).  Which it is depends on the scene, not on its size, so the
+		// first frame of a scene times both kernels on the first rays of its first level and the scene keeps the winner (same bits either way).
+		// SAILOR_PT_TRAVERSAL=local|exact skips the probe.
+		bool probeTraversal = false;
+		if (useFast)
+		{
+			if (D.traceChoiceTris != D.numTris) { D.traceChoice = D.Host().traversalChoice; D.traceChoiceTris = D.numTris; }
+			if (const char* e = getenv("SAILOR_PT_TRAVERSAL")) D.traceChoice = e[0] == 'e' ? 2u : 1u;
+			probeTraversal = D.traceChoice == 0u;
+			if (D.traceChoice == 2u) useFast = false;
+		}
 		const WideView wide = D.Wide();
 		const FastView fast = D.Fast();
 		DevMemset(ctx, D.counter.p + 15, 0, sizeof(uint32_t));
@@ -351,6 +363,28 @@ namespace spt
 					launch_for_range<SPT_FAN_MIN_BLOCKS>(ctx, &counters->zero, &counters->fanThreads[0], a.fanCap * 32u, a.fanCap * 32u, FanOutKernel{ a, level, 0u });
 					launch_for_range<SPT_FAN_MIN_BLOCKS>(ctx, &counters->zero, &counters->fanThreads[1], a.fanCap * 32u, a.fanCap * 32u, FanOutKernel{ a, level, 1u });
 					st[1].End(ctx);
+					if (probeTraversal && level == 0u)
+					{
+						// hit-only launches (QueueSink) over the level's rays (at most 64 M: a short prefix is not representative, it holds the rays of
+						// the first image rows only): no status bytes, no slow list; the level launch below traces them again.  One round: tens of
+						// milliseconds, once per scene file.
+						probeTraversal = false;
+						const uint32_t probeN = plan.rayCap < (64u << 20) ? plan.rayCap : (64u << 20);
+						double best[2] = { 1e30, 1e30 };
+						for (int round = 0; round < 1 && ctx.ok; round++)
+						{
+							ctx.TimerStart(); LaunchTraceRaysFast(ctx, fast, view, wb, a.rays, a.hits, probeN, &L->rayCount); const double tf = ctx.TimerStop();
+							ctx.TimerStart(); LaunchTraceRays(ctx, view, a.rays, a.hits, probeN, D.counter.p, &L->rayCount); const double te = ctx.TimerStop();
+							if (tf < best[0]) best[0] = tf;
+							if (te < best[1]) best[1] = te;
+						}
+						DevMemset(ctx, D.counter.p + 15, 0, sizeof(uint32_t));          // the probe's replays are not the frame's
+						D.probeMs[0] = (float)(best[0] * 1e3); D.probeMs[1] = (float)(best[1] * 1e3);
+						D.traceChoice = best[1] < best[0] * 0.97 ? 2u : 1u;
+						D.Host().traversalChoice = D.traceChoice;
+						useFast = D.traceChoice == 1u;
+						if (hostTrace) fprintf(stderr, "[sailor_pt] traversal probe: origin-local %.3f ms, exact %.3f ms -> %s\n", best[0] * 1e3, best[1] * 1e3, useFast ? "origin-local" : "exact");
+					}
 					tt.Begin(ctx);
 					if (useFast) LaunchTraceLevelFast(ctx, fast, view, wb, a.rays, a.hits, plan.rayCap, &L->rayCount, WavefrontOut{ a.status, &L->auxBase, a.slowList, &counters->slowCount });
 					else if (useWide) LaunchTraceLevelWide(ctx, wide, view, wb, a.rays, a.hits, plan.rayCap, &L->rayCount, WavefrontOut{ a.status, &L->auxBase, a.slowList, &counters->slowCount });

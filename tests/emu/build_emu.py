@@ -19,7 +19,7 @@ OUT = os.path.join(HERE, "_build")
 def build():
     os.makedirs(OUT, exist_ok=True)
     lib = os.path.join(OUT, "libsailor_pt_emu.so")
-    srcs = [os.path.join(SRC, f) for f in ("capi.cu", "backend.cu", "gltf_loader.cpp", "png_codec.cpp", "image_io.cpp")]
+    srcs = [os.path.join(SRC, f) for f in ("capi.cu", "backend.cu", "gltf_loader.cpp", "png_codec.cpp", "jpeg_codec.cpp", "image_io.cpp")]
     newest = max(os.path.getmtime(os.path.join(SRC, f)) for f in os.listdir(SRC))
     newest = max(newest, os.path.getmtime(os.path.join(ROOT, "include", "sailor_pt.h")))
     if os.path.exists(lib) and os.path.getmtime(lib) > newest:

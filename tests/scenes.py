@@ -86,7 +86,8 @@ class GlbBuilder:
         return len(self.j["materials"]) - 1
 
     def texture(self, png: bytes, wrap=10497):
-        self.j.setdefault("images", []).append({"bufferView": self._view(png), "mimeType": "image/png"})
+        mime = "image/jpeg" if png[:3] == b"\xff\xd8\xff" else "image/png"
+        self.j.setdefault("images", []).append({"bufferView": self._view(png), "mimeType": mime})
         self.j.setdefault("samplers", []).append({"magFilter": 9729, "minFilter": 9729, "wrapS": wrap, "wrapT": wrap})
         self.j.setdefault("textures", []).append({"sampler": len(self.j["samplers"]) - 1, "source": len(self.j["images"]) - 1})
         return len(self.j["textures"]) - 1
@@ -310,8 +311,37 @@ def _quad(center, ux, uy, uv_scale=1.0):
     return pos, nrm, uv, idx
 
 
-def pbr_scene(path, tex_size=64):
+def jpeg_bytes(img: np.ndarray, **kw) -> bytes:
+    """RGB8 -> JPEG file (Pillow; baseline 4:2:0 unless told otherwise)."""
+    import io
+    from PIL import Image
+    b = io.BytesIO()
+    Image.fromarray(np.ascontiguousarray(img[..., :3])).save(b, "JPEG", **({"quality": 88} | kw))
+    return b.getvalue()
+
+
+def pbr_scene(path, tex_size=64, jpeg=False):
+    """jpeg=True: the base-colour, ORM and emissive textures are JPEG files (baseline 4:2:0, progressive 4:4:4, baseline 4:2:2): the most
+    common glTF texture format, decoded by csrc/jpeg_codec.cpp; the normal map stays PNG."""
     g = GlbBuilder()
+    if jpeg:
+        enc = {1: dict(), 3: dict(progressive=True, subsampling=0), 4: dict(subsampling=1)}
+        global png_bytes
+        _png = png_bytes
+        counter = [0]
+
+        def as_file(img, level=6):
+            counter[0] += 1
+            return jpeg_bytes(img, **enc[counter[0]]) if counter[0] in enc else _png(img, level)
+        png_bytes = as_file
+        try:
+            return _pbr_scene_body(g, path, tex_size)
+        finally:
+            png_bytes = _png
+    return _pbr_scene_body(g, path, tex_size)
+
+
+def _pbr_scene_body(g, path, tex_size):
     g.j["extensionsUsed"] = ["KHR_lights_punctual", "KHR_materials_transmission", "KHR_materials_volume", "KHR_materials_ior",
                              "KHR_materials_emissive_strength", "KHR_texture_transform"]
     tb = g.texture(png_bytes(_checker(tex_size, 1, "base")))
@@ -468,6 +498,9 @@ def ensure(directory, name, **kw):
     if name == "pbr":
         p = os.path.join(directory, "pbr.glb")
         return p if os.path.exists(p) else pbr_scene(p)
+    if name == "pbr_jpeg":
+        p = os.path.join(directory, "pbr_jpeg.glb")
+        return p if os.path.exists(p) else pbr_scene(p, jpeg=True)
     if name == "heightfield":
         n = kw.get("n", 64)
         p = os.path.join(directory, "heightfield_%d.glb" % n)
