@@ -38,6 +38,8 @@ using namespace Sailor::Raytracing;
 
 extern "C" unsigned char* stbi_load_from_memory(unsigned char const* buffer, int len, int* x, int* y, int* comp, int req_comp);
 extern "C" void stbi_image_free(void* p);
+extern "C" int stbi_is_hdr_from_memory(unsigned char const* buffer, int len);
+extern "C" float* stbi_loadf_from_memory(unsigned char const* buffer, int len, int* x, int* y, int* comp, int req_comp);
 
 // ---------------------------------------------------------------------------------------------------------
 // rand(): glm::linearRand draws bytes with std::rand() % 255 (glm/gtc/random.inl:19-27).  glibc's rand() takes a
@@ -343,6 +345,14 @@ namespace
 		ptr->m_channels = sizeof(T) == sizeof(vec4) ? 4 : 3;
 		if (imageIndex < 0 || imageIndex >= (int)imageBytes.size() || imageBytes[imageIndex].empty()) return false;
 		int ch = 0;
+		if (stbi_is_hdr_from_memory(imageBytes[imageIndex].data(), (int)imageBytes[imageIndex].size()))          // MaterialUtils.h:224-229, 250-253
+		{
+			float* pf = stbi_loadf_from_memory(imageBytes[imageIndex].data(), (int)imageBytes[imageIndex].size(), &ptr->m_width, &ptr->m_height, &ch, 4);
+			if (!pf) return false;
+			ptr->template Initialize<T, vec4>((vec4*)pf, bConvertToLinear, bNormalMap);
+			stbi_image_free(pf);
+			return true;
+		}
 		unsigned char* px = stbi_load_from_memory(imageBytes[imageIndex].data(), (int)imageBytes[imageIndex].size(), &ptr->m_width, &ptr->m_height, &ch, 4);
 		if (!px) return false;
 		ptr->template Initialize<T, u8vec4>((u8vec4*)px, bConvertToLinear, bNormalMap);

@@ -858,7 +858,7 @@ int32_t SailorPt_SampleTexture(SailorPtScene* s, uint32_t textureIndex, uint32_t
 	DevBuf<V2> dUv; DevBuf<V4> dOut;
 	dUv.Upload(D.ctx, reinterpret_cast<const V2*>(uv), count); dOut.Alloc(D.ctx, count);
 	if (!D.ctx.ok) return FromCtx(D, SAILOR_PT_ERR_CUDA);
-	SampleTextureKernel k; k.ts.texels = D.texels.p; k.ts.textures = D.textures.p; k.ts.srgbLut = D.srgbLut.p; k.index = textureIndex; k.uv = dUv.p; k.out = dOut.p;
+	SampleTextureKernel k; k.ts.texels = D.texels.p; k.ts.textures = D.textures.p; k.ts.srgbLut = D.srgbLut.p; k.ts.texelsF = D.texelsF.p; k.index = textureIndex; k.uv = dUv.p; k.out = dOut.p;
 	launch_for(D.ctx, count, k);
 	std::vector<V4> host(count);
 	dOut.Download(D.ctx, host.data(), count);
@@ -890,7 +890,7 @@ int32_t SailorPt_ShadeHits(SailorPtScene* s, uint32_t count, const uint32_t* tri
 	dTri.Upload(D.ctx, triIds, count); dUv.Upload(D.ctx, baryUV, (size_t)count * 2); dDir.Upload(D.ctx, rayDirs, (size_t)count * 3); dOut.Alloc(D.ctx, (size_t)count * SAILOR_PT_SHADE_FLOATS);
 	if (!D.ctx.ok) return FromCtx(D, SAILOR_PT_ERR_CUDA);
 	ShadeHitsKernel k;
-	k.shade = D.shade.p; k.materials = D.materials.p; k.tex.texels = D.texels.p; k.tex.textures = D.textures.p; k.tex.srgbLut = D.srgbLut.p;
+	k.shade = D.shade.p; k.materials = D.materials.p; k.tex.texels = D.texels.p; k.tex.textures = D.textures.p; k.tex.srgbLut = D.srgbLut.p; k.tex.texelsF = D.texelsF.p;
 	k.tri = dTri.p; k.uv = dUv.p; k.dir = dDir.p; k.out = dOut.p; k.numTris = D.numTris; k.numSamples = numSamples; k.numAmbient = numAmbient;
 	launch_for(D.ctx, count, k);
 	dOut.Download(D.ctx, out, (size_t)count * SAILOR_PT_SHADE_FLOATS);

@@ -592,6 +592,7 @@ namespace spt
 				else if (im.at("uri").type == Json::String) { if (!LoadUri(im.at("uri").str, g.baseDir, bytes)) return false; }
 				else return false;
 				std::string perr;
+				if (IsHdr(bytes.data(), bytes.size())) return DecodeHdrRgba32F(bytes.data(), bytes.size(), t.width, t.height, t.rgbaF, perr) == SAILOR_PT_OK;   // stbi_is_hdr_from_memory branch (MaterialUtils.h:224-229)
 				return DecodeImageRgba8(bytes.data(), bytes.size(), t.width, t.height, t.rgba, perr) == SAILOR_PT_OK;
 			};
 

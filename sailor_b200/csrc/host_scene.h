@@ -47,6 +47,7 @@ namespace spt
 		bool srgb = false;          // bConvertToLinear
 		bool normalMap = false;     // bNormalMap
 		std::vector<uint8_t> rgba;  // width*height*4, stbi RGBA8 convention (row 0 = top)
+		std::vector<float> rgbaF;   // Radiance .hdr images only: width*height*4 floats as stbi_loadf(..., STBI_rgb_alpha) returns them (rgba stays empty)
 	};
 
 	struct HostCamera
@@ -81,6 +82,9 @@ namespace spt
 	// JPEG codec (jpeg_codec.cpp): baseline + progressive, byte-identical to stb_image's decoder
 	bool IsJpeg(const uint8_t* data, size_t size);
 	int DecodeJpegRgba8(const uint8_t* data, size_t size, int32_t& w, int32_t& h, std::vector<uint8_t>& rgba, std::string& err);
+	// Radiance RGBE (.hdr) -> RGBA32F exactly as stbi_loadf_from_memory(..., STBI_rgb_alpha) (MaterialUtils.h:226-229)
+	bool IsHdr(const uint8_t* data, size_t size);
+	int DecodeHdrRgba32F(const uint8_t* data, size_t size, int32_t& w, int32_t& h, std::vector<float>& rgba, std::string& err);
 	// any supported image file in memory -> RGBA8 (stbi_load_from_memory(..., STBI_rgb_alpha) convention)
 	int DecodeImageRgba8(const uint8_t* data, size_t size, int32_t& w, int32_t& h, std::vector<uint8_t>& rgba, std::string& err);
 	int EncodePngRgb8(const char* path, uint32_t w, uint32_t h, const uint8_t* rgb, std::string& err);

@@ -15,7 +15,9 @@
 #include "host_scene.h"
 #include "../../include/sailor_pt.h"
 
+#include <math.h>
 #include <memory>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -699,6 +701,93 @@ namespace spt
 		if (IsJpeg(data, size)) return DecodeJpegRgba8(data, size, w, h, rgba, err);
 		err = "unsupported image format (PNG and JPEG are decoded)";
 		return SAILOR_PT_ERR_UNSUPPORTED;
+	}
+
+	// ---- Radiance RGBE ------------------------------------------------------------------------------------------------------------
+	// stb_image's stbi__hdr_load restated: "#?RADIANCE" / "#?RGBE" header, FORMAT=32-bit_rle_rgbe, "-Y h +X w", new-style RLE scanlines (flat
+	// data for widths < 8 or >= 32768), value = mantissa * 2^(e - 136) (one float multiply per channel), alpha 1.
+	bool IsHdr(const uint8_t* data, size_t size)
+	{
+		return (size >= 11 && !memcmp(data, "#?RADIANCE\n", 11)) || (size >= 7 && !memcmp(data, "#?RGBE\n", 7));
+	}
+	int DecodeHdrRgba32F(const uint8_t* data, size_t size, int32_t& w, int32_t& h, std::vector<float>& out, std::string& err)
+	{
+		const uint8_t* p = data; const uint8_t* end = data + size;
+		auto get8 = [&]() -> int { return p < end ? *p++ : 0; };
+		auto token = [&]() -> std::string { std::string t; while (p < end) { const char c = (char)*p++; if (c == '\n') break; if (t.size() < 1023) t.push_back(c); } return t; };
+		const std::string magic = token();
+		if (magic != "#?RADIANCE" && magic != "#?RGBE") { err = "not HDR"; return SAILOR_PT_ERR_FORMAT; }
+		bool valid = false;
+		for (;;) { const std::string t = token(); if (t.empty()) break; if (t == "FORMAT=32-bit_rle_rgbe") valid = true; if (p >= end) break; }
+		if (!valid) { err = "unsupported HDR format"; return SAILOR_PT_ERR_FORMAT; }
+		const std::string dims = token();
+		if (dims.compare(0, 3, "-Y ") != 0) { err = "unsupported HDR data layout"; return SAILOR_PT_ERR_FORMAT; }
+		char* rest = nullptr;
+		const long height = strtol(dims.c_str() + 3, &rest, 10);
+		while (*rest == ' ') ++rest;
+		if (strncmp(rest, "+X ", 3)) { err = "unsupported HDR data layout"; return SAILOR_PT_ERR_FORMAT; }
+		const long width = strtol(rest + 3, nullptr, 10);
+		if (width <= 0 || height <= 0 || width > (1 << 24) || height > (1 << 24) || (uint64_t)width * (uint64_t)height > (1ull << 28)) { err = "HDR image too large"; return SAILOR_PT_ERR_FORMAT; }
+		out.assign((size_t)width * height * 4, 0.0f);
+		auto convert = [](float* o, const uint8_t* in)
+			{
+				if (in[3] != 0)
+				{
+					const float f1 = (float)ldexp(1.0f, (int)in[3] - (int)(128 + 8));
+					o[0] = in[0] * f1; o[1] = in[1] * f1; o[2] = in[2] * f1; o[3] = 1.0f;
+				}
+				else { o[0] = o[1] = o[2] = 0.0f; o[3] = 1.0f; }
+			};
+		auto flat = [&](long j0, long i0)
+			{
+				for (long j = j0; j < height; j++) for (long i = (j == j0 ? i0 : 0); i < width; i++)
+				{
+					uint8_t rgbe[4]; for (int k = 0; k < 4; k++) rgbe[k] = (uint8_t)get8();
+					convert(out.data() + ((size_t)j * width + i) * 4, rgbe);
+				}
+			};
+		if (width < 8 || width >= 32768) flat(0, 0);
+		else
+		{
+			std::vector<uint8_t> scan((size_t)width * 4);
+			for (long j = 0; j < height; j++)
+			{
+				const int c1 = get8(), c2 = get8(); int len = get8();
+				if (c1 != 2 || c2 != 2 || (len & 0x80))
+				{
+					// not run-length encoded: these four bytes are the first pixel of a flat file
+					uint8_t rgbe[4] = { (uint8_t)c1, (uint8_t)c2, (uint8_t)len, (uint8_t)get8() };
+					convert(out.data(), rgbe);
+					flat(0, 1);
+					break;
+				}
+				len = (len << 8) | get8();
+				if (len != width) { err = "corrupt HDR: bad scanline length"; return SAILOR_PT_ERR_FORMAT; }
+				for (int k = 0; k < 4; k++)
+				{
+					long i = 0, nleft;
+					while ((nleft = width - i) > 0)
+					{
+						int count = get8();
+						if (count > 128)
+						{
+							const uint8_t value = (uint8_t)get8();
+							count -= 128;
+							if (count > nleft) { err = "corrupt HDR: bad RLE data"; return SAILOR_PT_ERR_FORMAT; }
+							for (int z = 0; z < count; z++) scan[(size_t)(i++) * 4 + k] = value;
+						}
+						else
+						{
+							if (count > nleft || count == 0) { err = "corrupt HDR: bad RLE data"; return SAILOR_PT_ERR_FORMAT; }
+							for (int z = 0; z < count; z++) scan[(size_t)(i++) * 4 + k] = (uint8_t)get8();
+						}
+					}
+				}
+				for (long i = 0; i < width; i++) convert(out.data() + ((size_t)j * width + i) * 4, scan.data() + (size_t)i * 4);
+			}
+		}
+		w = (int32_t)width; h = (int32_t)height;
+		return SAILOR_PT_OK;
 	}
 
 	bool IsJpeg(const uint8_t* data, size_t size) { return size >= 3 && data[0] == 0xFF && data[1] == 0xD8 && data[2] == 0xFF; }

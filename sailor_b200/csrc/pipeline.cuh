@@ -21,7 +21,7 @@ namespace spt
 	inline double HostNow() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 	// offset: into the texel pool (RGBA8 texels); mode: how CombinedSampler2D::Initialize turns a byte into a float (MaterialUtils.h:42-65)
-	enum TexelMode : uint32_t { kTexelLinear = 0, kTexelSrgb = 1, kTexelNormal = 2 };
+	enum TexelMode : uint32_t { kTexelLinear = 0, kTexelSrgb = 1, kTexelNormal = 2, kTexelFloat = 3 };      // kTexelFloat: offset is into the float4 pool of .hdr images
 	struct DeviceTexture { uint32_t width, height, channels, clamping; uint64_t offset; uint32_t mode, pad; };
 
 	struct SceneDevice
@@ -37,6 +37,7 @@ namespace spt
 		DevBuf<V2> uv2;
 		DevBuf<MaterialGpu> materials;
 		DevBuf<uint32_t> texels;              // all textures as the file's RGBA8 texels (4 bytes each); converted to float at fetch time (textures.cuh)
+		DevBuf<V4> texelsF;                   // .hdr images only: float4 texels, converted on the host with the reference's expressions (Initialize<T, vec4>)
 		DevBuf<float> srgbLut;                // 256 floats: Utils::SRGBToLinear(byte / 255) evaluated with the host's powf (bit-identical to the reference's)
 		DevBuf<DeviceTexture> textures;
 		std::vector<DeviceTexture> hostTextures;

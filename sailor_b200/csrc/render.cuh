@@ -320,7 +320,7 @@ namespace spt
 			{
 				const BatchPlan plan = PlanBatch(budget, hitCount - done, numLights, p.numAmbientSamples, p.numSamples, p.maxBounces, ambientOn, shrink);
 				IntegratorArgs a;
-				a.shade = D.shade.p; a.centroid = D.centroid.p; a.materials = D.materials.p; a.tex.texels = D.texels.p; a.tex.textures = D.textures.p; a.tex.srgbLut = D.srgbLut.p;
+				a.shade = D.shade.p; a.centroid = D.centroid.p; a.materials = D.materials.p; a.tex.texels = D.texels.p; a.tex.textures = D.textures.p; a.tex.srgbLut = D.srgbLut.p; a.tex.texelsF = D.texelsF.p;
 				a.lights = D.lights.p; a.numLights = numLights; a.blueNoise = blue;
 				a.cam = cam; a.rowBegin = rowBegin; a.rowEnd = rowEnd; a.msBegin = msBegin; a.msEnd = msEnd; a.msaa = p.msaa;
 				a.maxBounces = p.maxBounces; a.numSamples = p.numSamples; a.numAmbientSamples = p.numAmbientSamples;

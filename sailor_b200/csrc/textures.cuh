@@ -36,19 +36,21 @@ namespace spt
 	inline int SceneDevice::UploadTextures()
 	{
 		hostTextures.clear();
-		uint64_t total = 0;
+		uint64_t total = 0, totalF = 0;
 		for (const auto& t : Host().textures)
 		{
-			DeviceTexture d; d.width = (uint32_t)t.width; d.height = (uint32_t)t.height; d.channels = t.channels; d.clamping = t.clamping; d.offset = total;
-			d.mode = t.normalMap ? kTexelNormal : (t.srgb ? kTexelSrgb : kTexelLinear); d.pad = 0;
-			total += (uint64_t)t.width * t.height;
+			const bool isFloat = !t.rgbaF.empty();
+			DeviceTexture d; d.width = (uint32_t)t.width; d.height = (uint32_t)t.height; d.channels = t.channels; d.clamping = t.clamping; d.offset = isFloat ? totalF : total;
+			d.mode = isFloat ? kTexelFloat : (t.normalMap ? kTexelNormal : (t.srgb ? kTexelSrgb : kTexelLinear)); d.pad = 0;
+			(isFloat ? totalF : total) += (uint64_t)t.width * t.height;
 			hostTextures.push_back(d);
 		}
 		if (hostTextures.empty()) return SAILOR_PT_OK;
 		std::vector<float> srgb;
 		BuildSrgbLut(srgb);
 		srgbLut.Upload(ctx, srgb);
-		texels.Alloc(ctx, total);
+		texels.Alloc(ctx, total ? total : 1);
+		if (totalF) texelsF.Alloc(ctx, totalF);
 		textures.Upload(ctx, hostTextures);
 		if (!ctx.ok) return SAILOR_PT_ERR_CUDA;
 		// the file's RGBA8 texels go to the pool as they are: one transfer per texture, no staging, no conversion pass
@@ -56,12 +58,36 @@ namespace spt
 		{
 			const HostTexture& t = Host().textures[i];
 			const size_t n = (size_t)t.width * (size_t)t.height;
-			if (n) DevUpload(ctx, texels.p + hostTextures[i].offset, t.rgba.data(), n * 4);
+			if (!n) continue;
+			if (!t.rgbaF.empty())
+			{
+				// CombinedSampler2D::Initialize<T, vec4> (MaterialUtils.h:42-65) on the float pixels of a .hdr image, with the host's powf
+				std::vector<V4> conv(n);
+				for (size_t k = 0; k < n; k++)
+				{
+					const float* src = t.rgbaF.data() + k * 4; float o[4];
+					for (int c = 0; c < 4; c++)
+					{
+						if (t.normalMap) o[c] = (src[c] * (1.0f / 127.5f)) - 1.0f;
+						else
+						{
+							const float s = src[c] * (1.0f / 255.0f);
+							if (t.srgb && c < 3) { const float a = s < 0.04045f ? 0.0f : 1.0f; o[c] = (s / 12.92f) * (1.0f - a) + std::pow((s + 0.055f) / 1.055f, 2.4f) * a; }
+							else o[c] = s;
+						}
+					}
+					conv[k] = v4(o[0], o[1], o[2], t.channels == 4 ? o[3] : 0.0f);
+				}
+				DevUpload(ctx, texelsF.p + hostTextures[i].offset, conv.data(), n * sizeof(V4));
+				ctx.Sync();          // `conv` dies here
+				continue;
+			}
+			DevUpload(ctx, texels.p + hostTextures[i].offset, t.rgba.data(), n * 4);
 		}
 		return ctx.ok ? SAILOR_PT_OK : SAILOR_PT_ERR_CUDA;
 	}
 
-	struct TextureSet { const uint32_t* texels; const DeviceTexture* textures; const float* srgbLut; };
+	struct TextureSet { const uint32_t* texels; const DeviceTexture* textures; const float* srgbLut; const V4* texelsF; };
 
 	// CombinedSampler2D::Initialize (MaterialUtils.h:42-65) for one texel: the same single-precision expressions on the byte (normal maps
 	// byte * (1/127.5) - 1, data maps and every alpha byte * (1/255)); sRGB colour through the 256-entry table.  vec3 textures carry w = 0.
@@ -89,11 +115,20 @@ namespace spt
 		const int32_t x1 = (x0 + 1) < (W - 1) ? (x0 + 1) : (W - 1);    // std::min(tX0 + 1, m_width - 1)
 		const int32_t y1 = (y0 + 1) < (H - 1) ? (y0 + 1) : (H - 1);
 		const float fracX = fx - (float)x0, fracY = fy - (float)y0;
-		const uint32_t* base = ts.texels + t.offset;
-		const bool alpha = t.channels == 4;
-		const uint32_t ptl = ldu(base + x0 + (int64_t)y0 * W), ptr = ldu(base + x1 + (int64_t)y0 * W), pbl = ldu(base + x0 + (int64_t)y1 * W), pbr = ldu(base + x1 + (int64_t)y1 * W);
-		const V4 tl = TexelToFloat(ptl, t.mode, alpha, ts.srgbLut), tr = TexelToFloat(ptr, t.mode, alpha, ts.srgbLut);
-		const V4 bl = TexelToFloat(pbl, t.mode, alpha, ts.srgbLut), br = TexelToFloat(pbr, t.mode, alpha, ts.srgbLut);
+		V4 tl, tr, bl, br;
+		if (t.mode == kTexelFloat)
+		{
+			const V4* base = ts.texelsF + t.offset;
+			tl = ld4(base + x0 + (int64_t)y0 * W); tr = ld4(base + x1 + (int64_t)y0 * W); bl = ld4(base + x0 + (int64_t)y1 * W); br = ld4(base + x1 + (int64_t)y1 * W);
+		}
+		else
+		{
+			const uint32_t* base = ts.texels + t.offset;
+			const bool alpha = t.channels == 4;
+			const uint32_t ptl = ldu(base + x0 + (int64_t)y0 * W), ptr = ldu(base + x1 + (int64_t)y0 * W), pbl = ldu(base + x0 + (int64_t)y1 * W), pbr = ldu(base + x1 + (int64_t)y1 * W);
+			tl = TexelToFloat(ptl, t.mode, alpha, ts.srgbLut); tr = TexelToFloat(ptr, t.mode, alpha, ts.srgbLut);
+			bl = TexelToFloat(pbl, t.mode, alpha, ts.srgbLut); br = TexelToFloat(pbr, t.mode, alpha, ts.srgbLut);
+		}
 		V4 r;
 		{
 			const float top = tl.x + fracX * (tr.x - tl.x), bot = bl.x + fracX * (br.x - bl.x); r.x = top + fracY * (bot - top);

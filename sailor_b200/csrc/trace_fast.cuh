@@ -309,7 +309,7 @@ namespace spt
 #define SPT_FAST_BLOCK 128
 #endif
 #ifndef SPT_FAST_MIN_BLOCKS
-#define SPT_FAST_MIN_BLOCKS 7
+#define SPT_FAST_MIN_BLOCKS 8      // 64 registers: 8 CTAs of 128 threads per SM (65 registers / 7 CTAs measured 6 % slower, profiles/r02_fast_variants.txt)
 #endif
 #ifndef SPT_FAST_NODE_STACK
 #define SPT_FAST_NODE_STACK 12     // node entries per lane in shared memory; a deeper walk is replayed
@@ -327,7 +327,7 @@ namespace spt
 #define SPT_FAST_NODE_REPS 4
 #endif
 #ifndef SPT_FAST_TRI_REPS
-#define SPT_FAST_TRI_REPS 3
+#define SPT_FAST_TRI_REPS 4
 #endif
 #ifndef SPT_FAST_NODE_BIAS
 #define SPT_FAST_NODE_BIAS 1       // SPT_FAST_IMMEDIATE: a node step runs when (lanes with a node) * bias >= lanes with a triangle

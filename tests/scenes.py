@@ -86,7 +86,7 @@ class GlbBuilder:
         return len(self.j["materials"]) - 1
 
     def texture(self, png: bytes, wrap=10497):
-        mime = "image/jpeg" if png[:3] == b"\xff\xd8\xff" else "image/png"
+        mime = "image/jpeg" if png[:3] == b"\xff\xd8\xff" else ("image/vnd.radiance" if png[:2] == b"#?" else "image/png")
         self.j.setdefault("images", []).append({"bufferView": self._view(png), "mimeType": mime})
         self.j.setdefault("samplers", []).append({"magFilter": 9729, "minFilter": 9729, "wrapS": wrap, "wrapT": wrap})
         self.j.setdefault("textures", []).append({"sampler": len(self.j["samplers"]) - 1, "source": len(self.j["images"]) - 1})
@@ -320,19 +320,31 @@ def jpeg_bytes(img: np.ndarray, **kw) -> bytes:
     return b.getvalue()
 
 
-def pbr_scene(path, tex_size=64, jpeg=False):
+def hdr_bytes(img: np.ndarray) -> bytes:
+    """RGB8 -> Radiance .hdr file (new-style RLE scanlines, written by OpenCV) holding the values img / 64 (so some exceed 1)."""
+    import cv2
+    ok, enc = cv2.imencode(".hdr", (img[..., 2::-1].astype(np.float32) / np.float32(64.0)))
+    assert ok
+    return enc.tobytes()
+
+
+def pbr_scene(path, tex_size=64, jpeg=False, hdr=False):
     """jpeg=True: the base-colour, ORM and emissive textures are JPEG files (baseline 4:2:0, progressive 4:4:4, baseline 4:2:2): the most
-    common glTF texture format, decoded by csrc/jpeg_codec.cpp; the normal map stays PNG."""
+    common glTF texture format, decoded by csrc/jpeg_codec.cpp; the normal map stays PNG.
+    hdr=True: the base-colour and the emissive textures are Radiance .hdr files (the reference keeps those as float texels,
+    MaterialUtils.h:224-229, 250-253)."""
     g = GlbBuilder()
-    if jpeg:
-        enc = {1: dict(), 3: dict(progressive=True, subsampling=0), 4: dict(subsampling=1)}
+    if jpeg or hdr:
+        enc = {1: dict(), 3: dict(progressive=True, subsampling=0), 4: dict(subsampling=1)} if jpeg else {1: None, 4: None}
         global png_bytes
         _png = png_bytes
         counter = [0]
 
         def as_file(img, level=6):
             counter[0] += 1
-            return jpeg_bytes(img, **enc[counter[0]]) if counter[0] in enc else _png(img, level)
+            if counter[0] in enc:
+                return hdr_bytes(img) if hdr else jpeg_bytes(img, **enc[counter[0]])
+            return _png(img, level)
         png_bytes = as_file
         try:
             return _pbr_scene_body(g, path, tex_size)
@@ -501,6 +513,9 @@ def ensure(directory, name, **kw):
     if name == "pbr_jpeg":
         p = os.path.join(directory, "pbr_jpeg.glb")
         return p if os.path.exists(p) else pbr_scene(p, jpeg=True)
+    if name == "pbr_hdr":
+        p = os.path.join(directory, "pbr_hdr.glb")
+        return p if os.path.exists(p) else pbr_scene(p, hdr=True)
     if name == "heightfield":
         n = kw.get("n", 64)
         p = os.path.join(directory, "heightfield_%d.glb" % n)

@@ -232,7 +232,7 @@ def test_trim_memory_releases_the_working_set_and_rendering_goes_on(gpu, scene_d
         assert np.array_equal(a, b)
 
 
-@pytest.mark.parametrize("name,kw", [("pbr", {}), ("pbr_jpeg", {}), ("gallery", {"tex_size": 64, "tiles": 4, "emitters": 8})])
+@pytest.mark.parametrize("name,kw", [("pbr", {}), ("pbr_jpeg", {}), ("pbr_hdr", {}), ("gallery", {"tex_size": 64, "tiles": 4, "emitters": 8})])
 def test_shading_context_is_bit_identical_to_get_material_data(gpu, oracle, scene_dir, name, kw):
     """a13 deterministically: SailorPt_ShadeHits (the function ExpandKernel calls) against the reference's own GetMaterialData."""
     pc.check_shade_hits(gpu, oracle, _scene(scene_dir, name, kw), n=20000)
@@ -276,10 +276,11 @@ def test_rejection_loop_cap_keeps_the_frame_finite(gpu, scene_dir):
     assert 0.0 <= a.min() and a.max() <= 64.0 and a[-8:].mean() > 0.05          # bottom rows: the floor in front of the cube
 
 
-def test_jpeg_textured_scene_fetches_the_reference_texels(gpu, oracle, scene_dir):
+@pytest.mark.parametrize("name", ["pbr_jpeg", "pbr_hdr"])
+def test_jpeg_and_hdr_textured_scenes_fetch_the_reference_texels(gpu, oracle, scene_dir, name):
     """ADVICE r1 / VERDICT r1 item 7: a glTF whose textures are JPEG files (baseline 4:2:0, progressive 4:4:4, baseline 4:2:2) imports, and every
     texture samples bit-identically to the reference's stb_image + CombinedSampler2D path."""
-    path = _scene(scene_dir, "pbr_jpeg", {})
+    path = _scene(scene_dir, name, {})          # pbr_hdr: two Radiance .hdr images, kept as float texels like the reference (MaterialUtils.h:224-229)
     uv = np.random.RandomState(7).uniform(-1.0, 2.0, (20000, 2)).astype(np.float32)
     with gpu.load_scene(path) as a, oracle.load_scene(path) as b:
         assert a.counts() == b.counts() and a.counts()["textures"] == 4

@@ -186,7 +186,7 @@ int main() {
     assert n > 8_000_000 and bad == 0, "%d of %d powf results differ from the C library" % (bad, n)
 
 
-@pytest.mark.parametrize("name,kw", [("pbr", {}), ("pbr_jpeg", {}), ("gallery", {"tex_size": 32, "tiles": 3, "emitters": 4}), ("nomat", {"with_materials": True})])
+@pytest.mark.parametrize("name,kw", [("pbr", {}), ("pbr_jpeg", {}), ("pbr_hdr", {}), ("gallery", {"tex_size": 32, "tiles": 3, "emitters": 4}), ("nomat", {"with_materials": True})])
 def test_shading_context_is_bit_identical_to_get_material_data_cpu(emu, oracle, scene_dir, name, kw):
     pc.check_shade_hits(emu, oracle, _scene(scene_dir, name, kw))
 
