@@ -377,7 +377,12 @@ namespace spt
 		return (pos | neg) & (t < kFltMax) & (t > -0.0000001f) & ((pt.x != inf) | (pt.y != inf) | (pt.z != inf));
 	}
 
-	template<class Source, class Sink>
+	// kMode 0: the queue's rays as they come.  kMode 1: hit-or-miss rays only, with everything a closest-hit walk needs compiled out (no
+	// candidate record, no shrinking ray length, no reach distances).
+#ifndef SPT_FAST_EXP_MODE
+#define SPT_FAST_EXP_MODE 0
+#endif
+	template<int kMode, class Source, class Sink>
 	__device__ __forceinline__ void TraceFastLoop(const FastView& w, uint32_t n, uint32_t* __restrict__ counter, uint32_t* stackMem, const ReplayOut& replay, Source& src, Sink& sink)
 	{
 		// [entry][thread], 4-byte entries: the 32 lanes of a warp always hit 32 different banks
@@ -389,7 +394,9 @@ namespace spt
 		FastRay r; r.rD = v3(0.0f); r.nc = v3(0.0f);
 		WideBest best; best.Reset();
 		uint32_t ignore = kNoHit, index = 0;
-		bool anyHit = false, bad = false, active = false;
+		bool anyHitVar = false, bad = false, active = false;
+		constexpr bool kAnyOnly = kMode == 1;
+#define anyHit (kAnyOnly ? true : anyHitVar)
 		uint32_t cur = kFastNone, up = kUpDone, tcur = kFastNone;
 		int sp = 0;
 		uint32_t level = 0; float reach4 = 0.0f, reach7 = 0.0f, reach11 = 0.0f;          // climb levels done; scaled reach distances (FStart)
@@ -467,7 +474,14 @@ namespace spt
 				{
 					const uint32_t i = base + (uint32_t)__popc(freeMask & ((1u << lane) - 1u));
 					float maxLen;
-					if (i < n && src.Load(i, o, d, ignore, maxLen, anyHit))
+					if (i < n && src.Load(i, o, d, ignore, maxLen, anyHitVar)
+#if defined(SPT_FAST_EXP_SKIP_CLOSEST)
+						&& anyHitVar
+#endif
+#if defined(SPT_FAST_EXP_SKIP_ANY)
+						&& !anyHitVar
+#endif
+						)
 					{
 						r.rD = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);          // Ray::SetDirection (Bounds.h:44-48)
 						if (!FastSafe(o, r.rD, originLimit)) { toReplay = true; replayIndex = i; }
@@ -530,8 +544,9 @@ namespace spt
 						if (!climbing) ld256(base + 32, B);
 						else { B[0] = B[1] = B[2] = B[3] = B[4] = B[5] = 0u; B[6] = 0u; B[7] = 0u; }
 						float tA, tB;
-						const bool hitA = FastSlab(r, __uint_as_float(A[0]), __uint_as_float(A[1]), __uint_as_float(A[2]), __uint_as_float(A[3]), __uint_as_float(A[4]), __uint_as_float(A[5]), best.limit, tA);
-						const bool hitB = FastSlab(r, __uint_as_float(B[0]), __uint_as_float(B[1]), __uint_as_float(B[2]), __uint_as_float(B[3]), __uint_as_float(B[4]), __uint_as_float(B[5]), best.limit, tB) && !climbing;
+						const float limit = kAnyOnly ? kFltMax : best.limit;
+						const bool hitA = FastSlab(r, __uint_as_float(A[0]), __uint_as_float(A[1]), __uint_as_float(A[2]), __uint_as_float(A[3]), __uint_as_float(A[4]), __uint_as_float(A[5]), limit, tA);
+						const bool hitB = FastSlab(r, __uint_as_float(B[0]), __uint_as_float(B[1]), __uint_as_float(B[2]), __uint_as_float(B[3]), __uint_as_float(B[4]), __uint_as_float(B[5]), limit, tB) && !climbing;
 						up = climbing ? A[7] : up;
 						level += climbing ? 1u : 0u;
 						const uint32_t refA = A[6], refB = B[6];
@@ -553,7 +568,7 @@ namespace spt
 							if (pop) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(popped) : "r"(sa) : "memory");
 							sp += both ? 1 : (pop ? -1 : 0);
 							// nothing below: one level up, unless the root has been passed or nothing above is within the ray's length
-							const bool climbOn = up != kUpDone && !FastReachStop(level, best.limit, reach4, reach7, reach11);
+							const bool climbOn = up != kUpDone && (kAnyOnly || !FastReachStop(level, best.limit, reach4, reach7, reach11));
 							cur = (inA || inB) ? (aFirst ? refA : refB) : (pop ? popped : (climbOn ? kFastClimb : kFastNone));
 						}
 					}
@@ -577,6 +592,8 @@ namespace spt
 						const bool ok = FastTriTest(o, d, v3(__uint_as_float(P[0]), __uint_as_float(P[1]), __uint_as_float(P[2])), v3(__uint_as_float(P[3]), __uint_as_float(P[4]), __uint_as_float(P[5])),
 							v3(__uint_as_float(P[6]), __uint_as_float(P[7]), __uint_as_float(q.x)), t, u, v) && triId != ignore;      // BVH.cpp:136-139
 						// WideBest::Offer, as selects
+						if (kAnyOnly) { best.tri = ok ? triId : best.tri; best.rec = ok ? tcur : best.rec; }
+						else
 						{
 							const bool none = best.tri == kNoHit;
 							const bool better = ok && (none || t < best.t);
@@ -602,6 +619,7 @@ namespace spt
 		if (lane == 0) for (int k = 0; k < 16; k++) atomicAdd(&g_fastLoopStats[k], fl_[k]);
 #endif
 #undef SPT_FAST_CAN_NODE
+#undef anyHit
 	}
 
 	// exact replay: the rays on the replay list through the reference-visit-order warp loop
@@ -624,7 +642,7 @@ namespace spt
 		__shared__ uint32_t stackMem[kFastSmemWords];
 		if (nPtr) { const uint32_t m = *nPtr; if (m < n) n = m; }
 		QueueSource src{ rays }; QueueSink sink{ hits };
-		TraceFastLoop(w, n, counter, stackMem, replay, src, sink);
+		TraceFastLoop<0>(w, n, counter, stackMem, replay, src, sink);
 	}
 	__global__ void __launch_bounds__(kFastBlock, SPT_FAST_MIN_BLOCKS) k_trace_fast_level(FastView w, const RayRec* __restrict__ rays, Hit* __restrict__ hits,
 		uint32_t n, const uint32_t* __restrict__ nPtr, uint32_t* __restrict__ counter, WavefrontOut out, ReplayOut replay)
@@ -632,7 +650,7 @@ namespace spt
 		__shared__ uint32_t stackMem[kFastSmemWords];
 		{ const uint32_t m = *nPtr; if (m < n) n = m; }
 		QueueSource src{ rays }; WavefrontSink sink{ hits, out.status + *out.auxBase, out.slowList, out.slowCount };
-		TraceFastLoop(w, n, counter, stackMem, replay, src, sink);
+		TraceFastLoop<SPT_FAST_EXP_MODE>(w, n, counter, stackMem, replay, src, sink);
 	}
 	// The replay list is short (a few thousand rays of a 70 M ray level): a grid of one warp-sized CTA per 32 rays instead of the
 	// machine-wide persistent grid keeps an (almost) empty replay at launch latency.

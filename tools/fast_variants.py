@@ -18,7 +18,7 @@ VARIANTS = {
     "q4": ["SPT_FAST_LEAF_QUEUE=4"], "mb8": ["SPT_FAST_MIN_BLOCKS=8"], "mb6": ["SPT_FAST_MIN_BLOCKS=6"],
     "b256": ["SPT_FAST_BLOCK=256", "SPT_FAST_MIN_BLOCKS=4"], "b64": ["SPT_FAST_BLOCK=64", "SPT_FAST_MIN_BLOCKS=16"],
     "imm": ["SPT_FAST_IMMEDIATE"],
-    "xskip": ["SPT_FAST_EXP_SKIP_CLOSEST"], "xskipany": ["SPT_FAST_EXP_SKIP_CLOSEST", "SPT_FAST_EXP_MODE=1"], "xskipany10": ["SPT_FAST_EXP_SKIP_CLOSEST", "SPT_FAST_EXP_MODE=1", "SPT_FAST_MIN_BLOCKS=10"], "xskipany9": ["SPT_FAST_EXP_SKIP_CLOSEST", "SPT_FAST_EXP_MODE=1", "SPT_FAST_MIN_BLOCKS=9"],
+    "xskip": ["SPT_FAST_EXP_SKIP_CLOSEST"], "xonlyclosest": ["SPT_FAST_EXP_SKIP_ANY"], "xonlyclosest_stats": ["SPT_FAST_EXP_SKIP_ANY", "SPT_FAST_LOOP_STATS"], "xskip_stats": ["SPT_FAST_EXP_SKIP_CLOSEST", "SPT_FAST_LOOP_STATS"], "xskipany": ["SPT_FAST_EXP_SKIP_CLOSEST", "SPT_FAST_EXP_MODE=1"], "xskipany10": ["SPT_FAST_EXP_SKIP_CLOSEST", "SPT_FAST_EXP_MODE=1", "SPT_FAST_MIN_BLOCKS=10"], "xskipany9": ["SPT_FAST_EXP_SKIP_CLOSEST", "SPT_FAST_EXP_MODE=1", "SPT_FAST_MIN_BLOCKS=9"],
     "mb9": ["SPT_FAST_MIN_BLOCKS=9"], "mb10": ["SPT_FAST_MIN_BLOCKS=10"], "mb12": ["SPT_FAST_MIN_BLOCKS=12"],
     "mb8q4": ["SPT_FAST_MIN_BLOCKS=8", "SPT_FAST_LEAF_QUEUE=4"], "mb10q4": ["SPT_FAST_MIN_BLOCKS=10", "SPT_FAST_LEAF_QUEUE=4", "SPT_FAST_NODE_STACK=10"],
     "mb8r44": ["SPT_FAST_MIN_BLOCKS=8", "SPT_FAST_NODE_REPS=4", "SPT_FAST_TRI_REPS=4"], "b256mb4": ["SPT_FAST_BLOCK=256", "SPT_FAST_MIN_BLOCKS=4"], "b64mb16": ["SPT_FAST_BLOCK=64", "SPT_FAST_MIN_BLOCKS=16"],
