@@ -927,6 +927,18 @@ namespace spt
 			c->fanEntries = 0; c->fanThreads[0] = c->fanThreads[1] = 0; c->slowCount = 0;
 		}
 	};
+	// An arena overflowed while this level was expanded: some activations left their reserved queue entries unwritten, so nothing of the
+	// level may be traced or classified (stale entries would send ClassifyKernel after record indices of another batch).  The batch is
+	// redone smaller by the host (render.cuh); until it notices, the remaining launches of the batch find empty ranges.
+	struct OverflowGuardKernel
+	{
+		BatchCounters* c; uint32_t level;
+		SPT_KERNEL_BODY void operator()(uint32_t) const
+		{
+			if (!c->overflow) return;
+			c->level[level].rayCount = 0; c->slowCount = 0; c->skyCount[0] = c->skyCount[1] = 0;
+		}
+	};
 	struct SkySwapKernel         // after a sky iteration: queue q is consumed
 	{
 		BatchCounters* c; uint32_t q;

@@ -318,7 +318,9 @@ namespace spt
 			if (hostTrace) fprintf(stderr, "[sailor_pt] t=%.3f ms primary pass done: %u first hits\n", (HostNow() - tFrame0) * 1e3, hitCount);
 			while (done < hitCount && ctx.ok)
 			{
-				const BatchPlan plan = PlanBatch(budget, hitCount - done, numLights, p.numAmbientSamples, p.numSamples, p.maxBounces, ambientOn, shrink);
+				BatchPlan plan = PlanBatch(budget, hitCount - done, numLights, p.numAmbientSamples, p.numSamples, p.maxBounces, ambientOn, shrink);
+				// test hook (tests/test_*: the overflow-and-retry path): the first attempt of every batch gets arenas an eighth of the plan, overflows, and is redone
+				if (shrink == 0u && plan.firstHits > 1024u && getenv("SAILOR_PT_TEST_OVERFLOW")) { plan.auxCap = plan.auxCap / 8u + 64u; plan.recCap = plan.recCap / 8u + 64u; }
 				IntegratorArgs a;
 				a.shade = D.shade.p; a.centroid = D.centroid.p; a.materials = D.materials.p; a.tex.texels = D.texels.p; a.tex.textures = D.textures.p; a.tex.srgbLut = D.srgbLut.p; a.tex.texelsF = D.texelsF.p;
 				a.lights = D.lights.p; a.numLights = numLights; a.blueNoise = blue;
@@ -363,6 +365,7 @@ namespace spt
 					launch_for_range<SPT_FAN_MIN_BLOCKS>(ctx, &counters->zero, &counters->fanThreads[0], a.fanCap * 32u, a.fanCap * 32u, FanOutKernel{ a, level, 0u });
 					launch_for_range<SPT_FAN_MIN_BLOCKS>(ctx, &counters->zero, &counters->fanThreads[1], a.fanCap * 32u, a.fanCap * 32u, FanOutKernel{ a, level, 1u });
 					st[1].End(ctx);
+					launch_for(ctx, 1, OverflowGuardKernel{ counters, level });
 					if (probeTraversal && level == 0u)
 					{
 						// hit-only launches (QueueSink) over the level's rays (at most 64 M: a short prefix is not representative, it holds the rays of

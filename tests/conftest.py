@@ -54,7 +54,8 @@ def emu():
     from sailor_b200.capi import Library
     sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
     import build_emu
-    return Library(build_emu.build())
+    # SAILOR_EMU_LIB: another build of the same sources, e.g. one compiled with -fsanitize=address (tools/asan_emu.sh)
+    return Library(os.environ.get("SAILOR_EMU_LIB") or build_emu.build())
 
 
 @pytest.fixture(scope="session")

@@ -335,3 +335,21 @@ def blue_noise_table():
     t = np.array([int(x) for x in re.findall(r"\d+", body)], np.int64)
     assert len(t) == 688
     return t
+
+
+def check_batching_and_overflow_retry(lib, path, monkeypatch, **base):
+    """The wavefront works on batches of first hits sized by a memory budget, and redoes a batch smaller when an arena overflows
+    (render.cuh).  Results are keyed per activation, so the frame must not depend on either: a 1 MiB budget (many batches) and a forced
+    overflow of every first attempt (SAILOR_PT_TEST_OVERFLOW) give the bits of the default frame."""
+    kw = dict(height=72, num_samples=3, num_ambient_samples=3, max_bounces=3, msaa=3, ambient=(1, 1, 1), seed=4)
+    kw.update(base)
+    with lib.load_scene(path) as s:
+        ref, _ = s.render(Params(**kw)); b0 = lib.stats()["batches"]
+        monkeypatch.setenv("SAILOR_PT_BATCH_MB", "1")
+        many, _ = s.render(Params(**kw)); b1 = lib.stats()["batches"]
+        monkeypatch.delenv("SAILOR_PT_BATCH_MB")
+        monkeypatch.setenv("SAILOR_PT_TEST_OVERFLOW", "1")
+        redo, _ = s.render(Params(**kw)); b2 = lib.stats()["batches"]
+        monkeypatch.delenv("SAILOR_PT_TEST_OVERFLOW")
+    assert b1 > b0, (b0, b1, b2)          # (a forced overflow redoes the batch; whether it also splits it depends on the budget)
+    assert np.array_equal(bits(ref), bits(many)) and np.array_equal(bits(ref), bits(redo))

@@ -248,3 +248,7 @@ def test_rejection_loop_cap_keeps_the_frame_finite_cpu(emu, scene_dir):
         a, _ = s.render(p)
         b, _ = s.render(p)
     assert np.isfinite(a).all() and np.array_equal(a, b) and a.max() <= 64.0
+
+
+def test_frame_does_not_depend_on_batching_or_on_an_overflow_retry_cpu(emu, scene_dir, monkeypatch):
+    pc.check_batching_and_overflow_retry(emu, _scene(scene_dir, "pbr", {}), monkeypatch, camera="main_cam", height=40)
