@@ -533,7 +533,7 @@ namespace spt
 
 		// Structural checks the reference's importer makes on the whole document, whether or not a scene node reaches the object
 		// (tinygltf's parse rejects these files outright; External/tinygltf/models/BoundsChecking/*.gltf are its regression inputs):
-		// a bufferView's byteLength is a positive integer, an accessor's bufferView, a primitive's accessors and an image's bufferView
+		// a bufferView's byteLength is a positive integer; a primitive's index accessor, that accessor's bufferView and an image's bufferView
 		// (and that view's buffer) exist.
 		{
 			const Json& views = g.root.at("bufferViews"); const Json& accs = g.root.at("accessors"); const Json& imgs = g.root.at("images");
@@ -543,11 +543,6 @@ namespace spt
 				if (!len || len->type != Json::Number || !(len->num >= 1.0) || !(len->num <= 9007199254740992.0) || len->num != (double)(uint64_t)len->num)
 				{ err = "bufferView[" + std::to_string(i) + "]: 'byteLength' is not a positive integer"; return SAILOR_PT_ERR_FORMAT; }
 			}
-			for (size_t i = 0; i < accs.size(); i++)
-			{
-				const Json* bv = accs.at(i).find("bufferView");
-				if (bv && (bv->type != Json::Number || bv->num < 0.0 || bv->num >= (double)views.size())) { err = "accessor[" + std::to_string(i) + "]: invalid bufferView"; return SAILOR_PT_ERR_FORMAT; }
-			}
 			const Json& meshes = g.root.at("meshes");
 			for (size_t m = 0; m < meshes.size(); m++)
 			{
@@ -556,10 +551,13 @@ namespace spt
 				{
 					const Json* idx = prims.at(k).find("indices");
 					if (idx && (idx->type != Json::Number || idx->num < 0.0 || idx->num >= (double)accs.size())) { err = "mesh[" + std::to_string(m) + "]: primitive indices accessor out of bounds"; return SAILOR_PT_ERR_FORMAT; }
-					const Json* attrs = prims.at(k).find("attributes");
-					if (attrs && attrs->type == Json::Object)
-						for (const auto& kv : attrs->obj)
-							if (kv.second.type != Json::Number || kv.second.num < 0.0 || kv.second.num >= (double)accs.size()) { err = "mesh[" + std::to_string(m) + "]: attribute accessor out of bounds"; return SAILOR_PT_ERR_FORMAT; }
+					// ... and that accessor's bufferView must exist (attribute accessors are NOT checked by the reference's importer: a primitive
+					// whose POSITION cannot be read is dropped by the flattener instead)
+					if (idx)
+					{
+						const Json* bv = accs.at((size_t)idx->num).find("bufferView");
+						if (bv && bv->type == Json::Number && bv->num >= (double)views.size()) { err = "accessor[" + std::to_string((size_t)idx->num) + "]: invalid bufferView"; return SAILOR_PT_ERR_FORMAT; }
+					}
 				}
 			}
 			for (size_t i = 0; i < imgs.size(); i++)

@@ -90,13 +90,14 @@ def _broken_documents(glb, out_dir):
     js, bn = _split_glb(glb)
     open(os.path.join(out_dir, "b.bin"), "wb").write(bn)
     out = {}
-    for name in ("byteLength 1e300", "accessor -> missing bufferView", "indices -> missing accessor", "image -> missing buffer"):
+    for name in ("byteLength 1e300", "accessor -> missing bufferView",   # (the INDEX accessor: attribute accessors are not checked at parse time)
+                  "indices -> missing accessor", "image -> missing buffer"):
         d = json.loads(json.dumps(js))
         d["buffers"][0]["uri"] = "b.bin"
         if name == "byteLength 1e300":
             d["bufferViews"][0]["byteLength"] = 1e300
         elif name == "accessor -> missing bufferView":
-            d["accessors"][0]["bufferView"] = len(d["bufferViews"]) + 3
+            d["accessors"][d["meshes"][0]["primitives"][0]["indices"]]["bufferView"] = len(d["bufferViews"]) + 3
         elif name == "indices -> missing accessor":
             d["meshes"][0]["primitives"][0]["indices"] = len(d["accessors"]) + 1
         else:
