@@ -577,18 +577,13 @@ namespace spt
 						if (!ParseScan()) return false;
 						if (marker == 0xFF)
 						{
-							// junk after the entropy-coded data: look for the next marker
-							while (p < end)
-							{
-								int x = Get8();
-								while (x == 0xFF) { if (p >= end) break; x = Get8(); if (x != 0x00 && x != 0xFF) { marker = x; break; } }
-								if (marker != 0xFF) break;
-							}
+							// bytes after the entropy-coded data that are no marker (stb_image v2.27: "handle 0s at the end of image data"): the byte
+							// after the next 0xFF is taken as the marker, whatever it is
+							while (p < end) { const int x = Get8(); if (x == 255) { marker = Get8(); break; } }
 						}
 					}
 					else if (m == 0xDC) { const int Ld = Get16(); const int NL = Get16(); if (Ld != 4) return Fail("bad DNL len"); if (NL != height) return Fail("bad DNL height"); }
 					else if (!ProcessMarker(m)) return false;
-					if (p >= end && marker == 0xFF) break;           // ran out of data: what was decoded so far is the image
 					m = NextMarker();
 				}
 				if (progressive) FinishProgressive();

@@ -61,20 +61,27 @@ namespace spt
 		uint32_t width = 0, height = 0; int depth = 0, color = 0, interlace = 0;
 		std::vector<uint8_t> idat, palette, trns;
 		size_t off = 8; bool haveHdr = false, done = false;
-		while (!done && off + 12 <= size)
+		// chunk walk with stb_image's tolerance: CRCs are never checked (the last one may even be missing), the file must reach an IEND
+		// chunk header, a chunk's body must be complete, and an unknown CRITICAL chunk (upper-case first letter) is an error
+		while (!done)
 		{
+			if (off + 8 > size) { err = "PNG ends before IEND"; return SAILOR_PT_ERR_FORMAT; }
 			const uint32_t len = be32(data + off);
 			const uint8_t* type = data + off + 4;
 			const uint8_t* body = data + off + 8;
-			if (off + 12 + (size_t)len > size) { err = "truncated PNG"; return SAILOR_PT_ERR_FORMAT; }
-			if (!memcmp(type, "IHDR", 4) && len >= 13)
+			if (!memcmp(type, "IEND", 4)) { done = true; break; }
+			if (off + 8 + (size_t)len > size) { err = "truncated PNG"; return SAILOR_PT_ERR_FORMAT; }
+			if (!memcmp(type, "IHDR", 4))
 			{
+				if (len != 13 || haveHdr) { err = "bad PNG header"; return SAILOR_PT_ERR_FORMAT; }
 				width = be32(body); height = be32(body + 4); depth = body[8]; color = body[9]; interlace = body[12]; haveHdr = true;
+				if (body[10] || body[11]) { err = "bad PNG compression / filter method"; return SAILOR_PT_ERR_FORMAT; }
 			}
-			else if (!memcmp(type, "PLTE", 4)) palette.assign(body, body + len);
+			else if (!haveHdr) { err = "PNG: first chunk is not IHDR"; return SAILOR_PT_ERR_FORMAT; }
+			else if (!memcmp(type, "PLTE", 4)) { if (len > 256 * 3 || len % 3) { err = "bad PNG palette"; return SAILOR_PT_ERR_FORMAT; } palette.assign(body, body + len); }
 			else if (!memcmp(type, "tRNS", 4)) trns.assign(body, body + len);
 			else if (!memcmp(type, "IDAT", 4)) idat.insert(idat.end(), body, body + len);
-			else if (!memcmp(type, "IEND", 4)) done = true;
+			else if (!(type[0] & 32)) { err = "unknown critical PNG chunk"; return SAILOR_PT_ERR_FORMAT; }
 			off += 12 + (size_t)len;
 		}
 		if (!haveHdr || !width || !height || width > 65536 || height > 65536) { err = "bad PNG header"; return SAILOR_PT_ERR_FORMAT; }
@@ -96,8 +103,20 @@ namespace spt
 		}
 		std::vector<uint8_t> raw(rawSize);
 		uLongf rawLen = (uLongf)raw.size();
-		const int zr = uncompress(raw.data(), &rawLen, idat.data(), (uLong)idat.size());
-		if ((zr != Z_OK && zr != Z_BUF_ERROR) || rawLen != raw.size()) { err = "PNG inflate failed"; return SAILOR_PT_ERR_FORMAT; }
+		// zlib stream: the 2-byte header is checked the way stb_image does (method 8, FCHECK, no preset dictionary), the deflate data is
+		// inflated raw and the Adler-32 trailer is NOT verified (stb_image never looks at it: a file with a damaged checksum still loads)
+		if (idat.size() < 2 || (idat[0] & 15) != 8 || ((idat[0] << 8) | idat[1]) % 31 != 0 || (idat[1] & 32)) { err = "bad zlib header"; return SAILOR_PT_ERR_FORMAT; }
+		{
+			z_stream zs; memset(&zs, 0, sizeof(zs));
+			if (inflateInit2(&zs, -15) != Z_OK) { err = "PNG inflate failed"; return SAILOR_PT_ERR_FORMAT; }
+			zs.next_in = idat.data() + 2; zs.avail_in = (uInt)(idat.size() - 2);
+			zs.next_out = raw.data(); zs.avail_out = (uInt)raw.size();
+			const int zr = inflate(&zs, Z_FINISH);
+			rawLen = (uLongf)zs.total_out;
+			inflateEnd(&zs);
+			// stb_image accepts more decoded bytes than the image needs and rejects fewer ("not enough pixels")
+			if ((zr != Z_STREAM_END && zr != Z_BUF_ERROR && zr != Z_OK) || rawLen != raw.size()) { err = "PNG inflate failed"; return SAILOR_PT_ERR_FORMAT; }
+		}
 
 		w = (int32_t)width; h = (int32_t)height;
 		rgba.resize((size_t)width * height * 4);

@@ -186,3 +186,47 @@ def test_a_gltf_with_jpeg_textures_loads_and_matches_the_oracle(product, oracle,
     bad = b"\x00\x01\x02not an image at all"
     with pytest.raises(Exception):
         product.decode_image(bad)
+
+
+def test_damaged_files_fail_or_decode_like_stb_image(product, oracle):
+    """Truncated files and files with damaged entropy-coded / compressed data: the decoders reject what stb_image v2.27 (the version the reference's
+    path tracer includes) rejects and otherwise produce the same pixels.  Exceptions are allowed for at most 2 % of the damaged JPEGs: stb's SSE2
+    inverse DCT wraps around in 16 bits on coefficients no valid stream contains, where this decoder's integer IDCT (= stb's scalar one) does not."""
+    r = np.random.RandomState(1)
+    img = _picture(40, 28, 1)
+    seeds = {"baseline": _jpeg(img, quality=80, subsampling=2), "progressive": _jpeg(img, quality=80, subsampling=0, progressive=True),
+             "restart": _jpeg(img, quality=60, subsampling=1, restart_marker_blocks=2), "png": _png_bytes(PIL.fromarray(img), False), "png adam7": _png_bytes(PIL.fromarray(img), True)}
+
+    def data_start(d):
+        if d[:2] != b"\xff\xd8":
+            return d.index(b"IDAT") + 4
+        i = 2
+        while True:
+            m, n = d[i + 1], (d[i + 2] << 8) | d[i + 3]
+            if m == 0xDA:
+                return i + 2 + n
+            i += 2 + n
+
+    def outcome(lib, d):
+        try:
+            return lib.decode_image(d)
+        except Exception:
+            return None
+    mismatches, total, truncated_mismatches = 0, 0, 0
+    for name, seed in seeds.items():
+        s0 = data_start(seed)
+        for it in range(400):
+            d = bytearray(seed)
+            truncated = it % 4 == 0
+            if truncated:
+                d = d[:r.randint(s0, len(d))]
+            else:
+                for _ in range(r.randint(1, 4)):
+                    d[r.randint(s0, len(d) - (12 if name.startswith("png") else 0))] = r.randint(0, 256)
+            a, b = outcome(product, bytes(d)), outcome(oracle, bytes(d))
+            same = (a is None and b is None) or (a is not None and b is not None and a.shape == b.shape and np.array_equal(a, b))
+            total += 1
+            mismatches += 0 if same else 1
+            truncated_mismatches += 0 if (same or not truncated) else 1
+    assert truncated_mismatches == 0, "a truncated file decoded differently"
+    assert mismatches <= 0.02 * total, (mismatches, total)
