@@ -493,7 +493,9 @@ namespace
 		P.ctx.Sync();                                                            // the frame exists before any peer writes into it
 		if (!P.ctx.ok) { DevSetCurrent(home); return FromCtx(P, SAILOR_PT_ERR_CUDA); }
 
-		const uint32_t nBands = rows < (uint32_t)N * kBandsPerDevice ? rows : (uint32_t)N * kBandsPerDevice;
+		uint32_t perDevice = kBandsPerDevice;
+		if (const char* e = getenv("SAILOR_PT_BANDS")) { const int v = atoi(e); if (v >= 1 && v <= 64) perDevice = (uint32_t)v; }      // tuning aid
+		const uint32_t nBands = rows < (uint32_t)N * perDevice ? rows : (uint32_t)N * perDevice;
 		const CameraGpu cam = ToGpuCamera(c);
 		std::atomic<uint32_t> next{ 0u };
 		const bool wantWide = (p->flags & SAILOR_PT_FLAG_WIDE_TRAVERSAL) != 0u && !(p->flags & SAILOR_PT_FLAG_EXACT_TRAVERSAL);
