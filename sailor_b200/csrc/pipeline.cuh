@@ -56,7 +56,7 @@ namespace spt
 		// which kernel traces the secondary rays of this scene: 0 not decided yet, 1 origin-local walk, 2 exact (top-down) kernel.  Decided once per
 		// geometry by a timed probe on the first level of the first frame (render.cuh); the results are identical either way.
 		uint32_t traceChoice = 0, traceChoiceTris = 0; float probeMs[2] = { 0.0f, 0.0f };
-		DevBuf<FNode> fnodes; DevBuf<FTri> ftris; DevBuf<FStart> fstart; DevBuf<FHeader> fheader; DevBuf<uint32_t> nodeUp;
+		DevBuf<FNode> fnodes; DevBuf<FNode> fclimb; DevBuf<FTri> ftris; DevBuf<FStart> fstart; DevBuf<FHeader> fheader; DevBuf<uint32_t> nodeUp;
 		// wide layout (wide_bvh.cuh): an alternative traversal layout, built on demand (SAILOR_PT_FLAG_WIDE_TRAVERSAL / SAILOR_PT_RAYS_WIDE)
 		bool hasWide = false;
 		bool wantWide = false;                // the caller renders through the wide layout: BuildBvh builds it (inside its timed region)
@@ -77,7 +77,7 @@ namespace spt
 
 		BvhView View() const { BvhView v; v.nodes = tnodes.p; v.tris = ttris.p; v.rootRef = rootRef; v.numNodes = numInternal; v.numTris = numTris; return v; }
 		WideView Wide() const { WideView w; w.nodes = wnodes.p; w.tris = wtris.p; w.leafBox = wleafBox.p; w.numNodes = numWideNodes; return w; }
-		FastView Fast() const { FastView w; w.nodes = fnodes.p; w.tris = ftris.p; w.start = fstart.p; w.header = fheader.p; w.numNodes = numInternal; w.numTris = numTris; return w; }
+		FastView Fast() const { FastView w; w.nodes = fnodes.p; w.tris = ftris.p; w.start = fstart.p; w.header = fheader.p; w.climb = fclimb.p; w.numNodes = numInternal; w.numTris = numTris; return w; }
 		// [12] wide work counter, [13] replay count, [14] replay work counter, [15] rays replayed since the last reset
 		ReplayBuffers Replay(uint32_t* list, uint32_t cap) { ReplayBuffers b; b.counters = counter.p + 12; b.replayList = list; b.replayCap = cap; return b; }
 
@@ -94,11 +94,12 @@ namespace spt
 		{
 			hasFast = false;
 			if (TakesSmallKernel() || !numInternal || getenv("SAILOR_PT_NO_FAST")) return SAILOR_PT_OK;
-			fnodes.Ensure(ctx, numInternal); ftris.Ensure(ctx, numTris); fstart.Ensure(ctx, numTris); fheader.Ensure(ctx, 1); nodeUp.Ensure(ctx, numInternal);
+			fnodes.Ensure(ctx, numInternal); fclimb.Ensure(ctx, (size_t)numInternal * 2); ftris.Ensure(ctx, numTris); fstart.Ensure(ctx, numTris); fheader.Ensure(ctx, 1); nodeUp.Ensure(ctx, numInternal);
 			if (!ctx.ok) return CudaStatus();
 			launch_for(ctx, 1, FastHeaderKernel{ aabb, fheader.p });
 			launch_for(ctx, nodesUsed, FastLinkKernel{ left, rank, nodeUp.p });
 			launch_for(ctx, nodesUsed, FastPackKernel{ left, count, rank, refIdx, leafOffsetByRef, mapping.p, aabb, vtx.p, nodeUp.p, fheader.p, fnodes.p, ftris.p, fstart.p });
+			launch_for(ctx, numInternal, FastClimbKernel{ fnodes.p, nodeUp.p, fclimb.p });
 			launch_for(ctx, numTris, FastReachKernel{ fnodes.p, ftris.p, fstart.p, fheader.p, numTris });
 			hasFast = ctx.ok;
 			return CudaStatus();

@@ -59,14 +59,16 @@ namespace spt
 	struct FHeader { float originLimit; float pad; uint32_t r0, r1; };
 	static_assert(sizeof(FNode) == 64 && sizeof(FTri) == 64 && sizeof(FStart) == 32, "fast traversal layout");
 
-	struct FastView { const FNode* nodes; const FTri* tris; const FStart* start; const FHeader* header; uint32_t numNodes, numTris; };
+	struct FastView { const FNode* nodes; const FTri* tris; const FStart* start; const FHeader* header; const FNode* climb; uint32_t numNodes, numTris; };
 
 	constexpr float kFastPad = 1.0f / 262144.0f;       // box padding, relative to the scene's largest |coordinate| (2^-18)
 	constexpr float kFastOriginScale = 8.0f;           // rays that start farther out than this many scene extents are replayed
-#ifndef SPT_FAST_REACH_LEVELS
-#define SPT_FAST_REACH_LEVELS 4u, 7u, 11u
+#ifndef SPT_FAST_REACH_L0
+#define SPT_FAST_REACH_L0 4u       // even: a climb step takes two levels
+#define SPT_FAST_REACH_L1 8u
+#define SPT_FAST_REACH_L2 12u
 #endif
-	constexpr uint32_t kFastReachTab[3] = { SPT_FAST_REACH_LEVELS };
+	constexpr uint32_t kFastReachTab[3] = { SPT_FAST_REACH_L0, SPT_FAST_REACH_L1, SPT_FAST_REACH_L2 };
 	constexpr uint32_t kFastReach0 = kFastReachTab[0], kFastReach1 = kFastReachTab[1], kFastReach2 = kFastReachTab[2];     // climb levels at which FStart::reach is sampled
 	constexpr uint32_t kFastMaxRd = 0x6F800000u;       // |1/d| must stay below 2^96 (finite, and b * 1/d cannot overflow)
 
@@ -133,6 +135,31 @@ namespace spt
 					}
 				}
 				nodes[me].h[side] = h;
+			}
+		}
+	};
+
+	// Climb nodes: TWO levels of the way up per step.  For the child X = (P, side) of inner node P, climb[(P << 1) | side] is an ordinary
+	// FNode whose two "children" are the subtrees a walk that has finished X must look at next: X's sibling (the other half of P) and P's
+	// own sibling (the other half of P's parent G); its link is G's link, i.e. where the walk stands once both are done.  A climb step is
+	// therefore a DOWN step on that record (both boxes tested, the nearer one first, the other one pushed) and the chain of ancestors is
+	// walked in half as many steps.
+	struct FastClimbKernel     // one thread per inner node (traversal numbering), after FastPackKernel
+	{
+		const FNode* nodes; const uint32_t* nodeUp; FNode* climb;
+		SPT_KERNEL_BODY void operator()(uint32_t me) const
+		{
+			const uint32_t upMe = nodeUp[me];
+			// no second level under the root: a point box in a far corner.  (An inverted box would not do: the slab test orders every interval
+			// itself.  A ray aimed exactly at that corner "hits" it and walks the tree once more from the root: more work, same result.)
+			FHalf uncle; uncle.lox = uncle.hix = kFltMax; uncle.loy = uncle.hiy = -kFltMax; uncle.loz = uncle.hiz = kFltMax; uncle.ref = 0u; uncle.up = kUpDone;
+			uint32_t next = kUpDone;
+			if (upMe != kUpDone) { uncle = nodes[upMe >> 1].h[(upMe & 1u) ^ 1u]; next = nodeUp[upMe >> 1]; }
+			for (uint32_t side = 0; side < 2u; side++)
+			{
+				FNode c; c.h[0] = nodes[me].h[side ^ 1u]; c.h[1] = uncle;
+				c.h[0].up = next; c.h[1].up = next;
+				climb[(me << 1) | side] = c;
 			}
 		}
 	};
@@ -282,15 +309,23 @@ namespace spt
 			}
 			if (sp > 0) { cur = stack[--sp]; continue; }
 			bool found = false;
-			while (up != kUpDone)            // the subtree is exhausted: climb until a sibling box is hit
+			while (up != kUpDone)            // the subtree is exhausted: climb (two levels per step, FastClimbKernel) until a box is hit
 			{
 				if (FastReachStop(level, best.limit, reach[0], reach[1], reach[2])) break;        // nothing above is within the ray's length
-				level++;
-				const FHalf* h = &w.nodes[up >> 1].h[(up & 1u) ^ 1u];
-				up = h->up;
+				level += 2u;
+				const FNode* n = w.climb + up;
+				up = n->h[0].up;
 				SPT_FSTAT(0);
-				float ts;
-				if (FastSlab(r, h->lox, h->loy, h->loz, h->hix, h->hiy, h->hiz, best.limit, ts)) { cur = h->ref; found = true; break; }
+				float t0, t1;
+				const bool h0 = FastSlab(r, n->h[0].lox, n->h[0].loy, n->h[0].loz, n->h[0].hix, n->h[0].hiy, n->h[0].hiz, best.limit, t0);
+				const bool h1 = FastSlab(r, n->h[1].lox, n->h[1].loy, n->h[1].loz, n->h[1].hix, n->h[1].hiy, n->h[1].hiz, best.limit, t1);
+				if (h0 || h1)
+				{
+					const bool first0 = h0 && (!h1 || t0 <= t1);
+					cur = first0 ? n->h[0].ref : n->h[1].ref;
+					if (h0 && h1) stack[sp++] = first0 ? n->h[1].ref : n->h[0].ref;          // the stack is empty here
+					found = true; break;
+				}
 			}
 			if (!found) break;
 		}
@@ -535,20 +570,19 @@ namespace spt
 					SPT_FL(2, 1); SPT_FL_LANES(3, take); SPT_FL_LANES(10, take && cur == kFastClimb); SPT_FL_LANES(11, take && anyHit); SPT_FL_MINE(myNode, take);
 					if (take)
 					{
-						// DOWN: both halves of node `cur`.  UP: the sibling's half of the parent; the finished side never hits.
+						// DOWN: both halves of node `cur`.  UP: both halves of the climb node of the subtree just finished (its sibling and its
+						// parent's sibling, FastClimbKernel) - the same step on another record, and the way up takes half as many of them.
 						const bool climbing = cur == kFastClimb;
-						const uint32_t p = climbing ? (up >> 1) : cur;
-						const unsigned char* base = reinterpret_cast<const unsigned char*>(w.nodes) + (size_t)p * 64u;
+						const unsigned char* base = reinterpret_cast<const unsigned char*>(climbing ? w.climb : w.nodes) + (size_t)(climbing ? up : cur) * 64u;
 						uint32_t A[8], B[8];
-						ld256(base + (climbing ? ((~up & 1u) << 5) : 0u), A);
-						if (!climbing) ld256(base + 32, B);
-						else { B[0] = B[1] = B[2] = B[3] = B[4] = B[5] = 0u; B[6] = 0u; B[7] = 0u; }
+						ld256(base, A);
+						ld256(base + 32, B);
 						float tA, tB;
 						const float limit = kAnyOnly ? kFltMax : best.limit;
 						const bool hitA = FastSlab(r, __uint_as_float(A[0]), __uint_as_float(A[1]), __uint_as_float(A[2]), __uint_as_float(A[3]), __uint_as_float(A[4]), __uint_as_float(A[5]), limit, tA);
-						const bool hitB = FastSlab(r, __uint_as_float(B[0]), __uint_as_float(B[1]), __uint_as_float(B[2]), __uint_as_float(B[3]), __uint_as_float(B[4]), __uint_as_float(B[5]), limit, tB) && !climbing;
+						const bool hitB = FastSlab(r, __uint_as_float(B[0]), __uint_as_float(B[1]), __uint_as_float(B[2]), __uint_as_float(B[3]), __uint_as_float(B[4]), __uint_as_float(B[5]), limit, tB);
 						up = climbing ? A[7] : up;
-						level += climbing ? 1u : 0u;
+						level += climbing ? 2u : 0u;
 						const uint32_t refA = A[6], refB = B[6];
 						const bool inA = hitA && !(refA & kLeafBit), inB = hitB && !(refB & kLeafBit);
 						// leaves: the nearer one first

@@ -19,6 +19,10 @@ VARIANTS = {
     "b256": ["SPT_FAST_BLOCK=256", "SPT_FAST_MIN_BLOCKS=4"], "b64": ["SPT_FAST_BLOCK=64", "SPT_FAST_MIN_BLOCKS=16"],
     "imm": ["SPT_FAST_IMMEDIATE"],
     "xskip": ["SPT_FAST_EXP_SKIP_CLOSEST"], "xonlyclosest": ["SPT_FAST_EXP_SKIP_ANY"], "xonlyclosest_stats": ["SPT_FAST_EXP_SKIP_ANY", "SPT_FAST_LOOP_STATS"], "xskip_stats": ["SPT_FAST_EXP_SKIP_CLOSEST", "SPT_FAST_LOOP_STATS"], "xskipany": ["SPT_FAST_EXP_SKIP_CLOSEST", "SPT_FAST_EXP_MODE=1"], "xskipany10": ["SPT_FAST_EXP_SKIP_CLOSEST", "SPT_FAST_EXP_MODE=1", "SPT_FAST_MIN_BLOCKS=10"], "xskipany9": ["SPT_FAST_EXP_SKIP_CLOSEST", "SPT_FAST_EXP_MODE=1", "SPT_FAST_MIN_BLOCKS=9"],
+    "rl4610": ["SPT_FAST_REACH_L0=4u", "SPT_FAST_REACH_L1=6u", "SPT_FAST_REACH_L2=10u"], "rl61014": ["SPT_FAST_REACH_L0=6u", "SPT_FAST_REACH_L1=10u", "SPT_FAST_REACH_L2=14u"], "rl2612": ["SPT_FAST_REACH_L0=2u", "SPT_FAST_REACH_L1=6u", "SPT_FAST_REACH_L2=12u"],
+    "tv22": ["SPT_FAST_TRI_VOTE=22"], "tv24": ["SPT_FAST_TRI_VOTE=24"], "tv24q16": ["SPT_FAST_TRI_VOTE=24", "SPT_FAST_LEAF_QUEUE=16"],
+    "r42": ["SPT_FAST_NODE_REPS=4", "SPT_FAST_TRI_REPS=2"], "r43": ["SPT_FAST_NODE_REPS=4", "SPT_FAST_TRI_REPS=3"], "r22": ["SPT_FAST_NODE_REPS=2", "SPT_FAST_TRI_REPS=2"], "r23": ["SPT_FAST_NODE_REPS=2", "SPT_FAST_TRI_REPS=3"],
+    "r24": ["SPT_FAST_NODE_REPS=2", "SPT_FAST_TRI_REPS=4"], "r33": ["SPT_FAST_NODE_REPS=3", "SPT_FAST_TRI_REPS=3"], "r34": ["SPT_FAST_NODE_REPS=3", "SPT_FAST_TRI_REPS=4"], "r46": ["SPT_FAST_NODE_REPS=4", "SPT_FAST_TRI_REPS=6"],
     "mb9": ["SPT_FAST_MIN_BLOCKS=9"], "mb10": ["SPT_FAST_MIN_BLOCKS=10"], "mb12": ["SPT_FAST_MIN_BLOCKS=12"],
     "mb8q4": ["SPT_FAST_MIN_BLOCKS=8", "SPT_FAST_LEAF_QUEUE=4"], "mb10q4": ["SPT_FAST_MIN_BLOCKS=10", "SPT_FAST_LEAF_QUEUE=4", "SPT_FAST_NODE_STACK=10"],
     "mb8r44": ["SPT_FAST_MIN_BLOCKS=8", "SPT_FAST_NODE_REPS=4", "SPT_FAST_TRI_REPS=4"], "b256mb4": ["SPT_FAST_BLOCK=256", "SPT_FAST_MIN_BLOCKS=4"], "b64mb16": ["SPT_FAST_BLOCK=64", "SPT_FAST_MIN_BLOCKS=16"],
