@@ -657,17 +657,26 @@ namespace spt
 	}
 
 	// exact replay: the rays on the replay list through the reference-visit-order warp loop
+	// A short replay list is SPREAD: only every 2^shift-th work index carries a ray, so a warp that fetches 32 indices traces 32 >> shift
+	// rays.  The rays on the list are the awkward ones (grazing ties, deep walks) and their walks have nothing in common: 32 of them in one
+	// warp run one after the other, and a list of a few hundred rays kept a dozen warps busy for 0.3 ms while the machine idled.
+	constexpr uint32_t kReplaySpreadShift = 3u, kReplaySpreadMax = 1u << 20;
+	__device__ __forceinline__ uint32_t ReplaySpread(uint32_t& n) { const uint32_t shift = n <= kReplaySpreadMax ? kReplaySpreadShift : 0u; n <<= shift; return shift; }
 	template<class Inner>
 	struct ReplaySource
 	{
-		const uint32_t* list; Inner inner;
-		__device__ __forceinline__ bool Load(uint32_t i, V3& o, V3& d, uint32_t& ignore, float& maxLen, bool& anyHit) const { return inner.Load(list[i], o, d, ignore, maxLen, anyHit); }
+		const uint32_t* list; Inner inner; uint32_t shift;
+		__device__ __forceinline__ bool Load(uint32_t i, V3& o, V3& d, uint32_t& ignore, float& maxLen, bool& anyHit) const
+		{
+			if (i & ((1u << shift) - 1u)) return false;
+			return inner.Load(list[i >> shift], o, d, ignore, maxLen, anyHit);
+		}
 	};
 	template<class Inner>
 	struct ReplaySink
 	{
-		const uint32_t* list; Inner inner;
-		__device__ __forceinline__ void Retire(bool finished, uint32_t i, const Hit& h, bool anyHit) const { inner.Retire(finished, finished ? list[i] : 0u, h, anyHit); }
+		const uint32_t* list; Inner inner; uint32_t shift;
+		__device__ __forceinline__ void Retire(bool finished, uint32_t i, const Hit& h, bool anyHit) const { inner.Retire(finished, finished ? list[i >> shift] : 0u, h, anyHit); }
 	};
 
 	__global__ void __launch_bounds__(kFastBlock, SPT_FAST_MIN_BLOCKS) k_trace_fast_rays(FastView w, const RayRec* __restrict__ rays, Hit* __restrict__ hits,
@@ -694,7 +703,8 @@ namespace spt
 		__shared__ uint32_t stackMem[kSmemStack * kTraceBlock];
 		uint32_t n = *nPtr; if (n > cap) n = cap;
 		if (!n) return;
-		ReplaySource<QueueSource> src{ list, QueueSource{ rays } }; ReplaySink<QueueSink> sink{ list, QueueSink{ hits } };
+		const uint32_t shift = ReplaySpread(n);
+		ReplaySource<QueueSource> src{ list, QueueSource{ rays }, shift }; ReplaySink<QueueSink> sink{ list, QueueSink{ hits }, shift };
 		TraceWarpLoop(bvh, n, counter, stackMem, src, sink);
 	}
 	__global__ void __launch_bounds__(kTraceBlock) k_replay_level(BvhView bvh, const RayRec* __restrict__ rays, Hit* __restrict__ hits,
@@ -703,8 +713,9 @@ namespace spt
 		__shared__ uint32_t stackMem[kSmemStack * kTraceBlock];
 		uint32_t n = *nPtr; if (n > cap) n = cap;
 		if (!n) return;
-		ReplaySource<QueueSource> src{ list, QueueSource{ rays } };
-		ReplaySink<WavefrontSink> sink{ list, WavefrontSink{ hits, out.status + *out.auxBase, out.slowList, out.slowCount } };
+		const uint32_t shift = ReplaySpread(n);
+		ReplaySource<QueueSource> src{ list, QueueSource{ rays }, shift };
+		ReplaySink<WavefrontSink> sink{ list, WavefrontSink{ hits, out.status + *out.auxBase, out.slowList, out.slowCount }, shift };
 		TraceWarpLoop(bvh, n, counter, stackMem, src, sink);
 	}
 
