@@ -21,6 +21,12 @@
 #ifndef SPT_FAN_MIN_BLOCKS
 #define SPT_FAN_MIN_BLOCKS 4
 #endif
+#ifndef SPT_CLASSIFY_MIN_BLOCKS
+#define SPT_CLASSIFY_MIN_BLOCKS 1
+#endif
+#ifndef SPT_GATHER_MIN_BLOCKS
+#define SPT_GATHER_MIN_BLOCKS 1
+#endif
 
 namespace spt
 {
@@ -394,7 +400,7 @@ namespace spt
 					else LaunchTraceLevel(ctx, view, a.rays, a.hits, plan.rayCap, D.counter.p, &L->rayCount, WavefrontOut{ a.status, &L->auxBase, a.slowList, &counters->slowCount });
 					tt.End(ctx);
 					st[2].Begin(ctx);
-					launch_for_range(ctx, &counters->zero, &counters->slowCount, plan.rayCap, plan.rayCap, ClassifyKernel{ a, level });
+					launch_for_range<SPT_CLASSIFY_MIN_BLOCKS>(ctx, &counters->zero, &counters->slowCount, plan.rayCap, plan.rayCap, ClassifyKernel{ a, level });
 					st[2].End(ctx);
 					if (hasSky)
 					{
@@ -435,7 +441,7 @@ namespace spt
 				for (uint32_t level = usedLevels; level-- > 0;)
 				{
 					const LevelInfo* L = &counters->level[level];
-					launch_for_range(ctx, &L->recBegin, &L->recEnd, plan.recCap, level == 0 ? plan.firstHits : plan.recCap, GatherKernel{ a });
+					launch_for_range<SPT_GATHER_MIN_BLOCKS>(ctx, &L->recBegin, &L->recEnd, plan.recCap, level == 0 ? plan.firstHits : plan.recCap, GatherKernel{ a });
 				}
 				st[3].End(ctx);
 				// The batch's counters (overflow flag, ray count) are read back with a host round trip.  For the LAST batch of the frame

@@ -660,7 +660,7 @@ namespace spt
 	// A short replay list is SPREAD: only every 2^shift-th work index carries a ray, so a warp that fetches 32 indices traces 32 >> shift
 	// rays.  The rays on the list are the awkward ones (grazing ties, deep walks) and their walks have nothing in common: 32 of them in one
 	// warp run one after the other, and a list of a few hundred rays kept a dozen warps busy for 0.3 ms while the machine idled.
-	constexpr uint32_t kReplaySpreadShift = 3u, kReplaySpreadMax = 1u << 20;
+	constexpr uint32_t kReplaySpreadShift = 3u, kReplaySpreadMax = 1u << 13;      // longer lists fill the replay grid (296 CTAs) as they are
 	__device__ __forceinline__ uint32_t ReplaySpread(uint32_t& n) { const uint32_t shift = n <= kReplaySpreadMax ? kReplaySpreadShift : 0u; n <<= shift; return shift; }
 	template<class Inner>
 	struct ReplaySource

@@ -23,6 +23,9 @@ VARIANTS = {
     "tv22": ["SPT_FAST_TRI_VOTE=22"], "tv24": ["SPT_FAST_TRI_VOTE=24"], "tv24q16": ["SPT_FAST_TRI_VOTE=24", "SPT_FAST_LEAF_QUEUE=16"],
     "r42": ["SPT_FAST_NODE_REPS=4", "SPT_FAST_TRI_REPS=2"], "r43": ["SPT_FAST_NODE_REPS=4", "SPT_FAST_TRI_REPS=3"], "r22": ["SPT_FAST_NODE_REPS=2", "SPT_FAST_TRI_REPS=2"], "r23": ["SPT_FAST_NODE_REPS=2", "SPT_FAST_TRI_REPS=3"],
     "r24": ["SPT_FAST_NODE_REPS=2", "SPT_FAST_TRI_REPS=4"], "r33": ["SPT_FAST_NODE_REPS=3", "SPT_FAST_TRI_REPS=3"], "r34": ["SPT_FAST_NODE_REPS=3", "SPT_FAST_TRI_REPS=4"], "r46": ["SPT_FAST_NODE_REPS=4", "SPT_FAST_TRI_REPS=6"],
+    "cl4": ["SPT_CLASSIFY_MIN_BLOCKS=4"], "cl5": ["SPT_CLASSIFY_MIN_BLOCKS=5"], "cl6": ["SPT_CLASSIFY_MIN_BLOCKS=6"], "g3": ["SPT_GATHER_MIN_BLOCKS=3"], "g4": ["SPT_GATHER_MIN_BLOCKS=4"], "g6": ["SPT_GATHER_MIN_BLOCKS=6"], "g8": ["SPT_GATHER_MIN_BLOCKS=8"],
+    "e3": ["SPT_EXPAND_MIN_BLOCKS=3"], "e1": ["SPT_EXPAND_MIN_BLOCKS=1"], "f5": ["SPT_FAN_MIN_BLOCKS=5"], "f3": ["SPT_FAN_MIN_BLOCKS=3"],
+    "lazy0": ["SPT_FAST_LAZY_ANY=0"], "lazy1": ["SPT_FAST_LAZY_ANY=1"], "lazy2": ["SPT_FAST_LAZY_ANY=2"], "lazy3": ["SPT_FAST_LAZY_ANY=3"], "lazy1tv12": ["SPT_FAST_LAZY_ANY=1", "SPT_FAST_TRI_VOTE=12"], "lazy2tv14": ["SPT_FAST_LAZY_ANY=2", "SPT_FAST_TRI_VOTE=14"], "lazy1r24": ["SPT_FAST_LAZY_ANY=1", "SPT_FAST_NODE_REPS=2", "SPT_FAST_TRI_REPS=4"],
     "mb9": ["SPT_FAST_MIN_BLOCKS=9"], "mb10": ["SPT_FAST_MIN_BLOCKS=10"], "mb12": ["SPT_FAST_MIN_BLOCKS=12"],
     "mb8q4": ["SPT_FAST_MIN_BLOCKS=8", "SPT_FAST_LEAF_QUEUE=4"], "mb10q4": ["SPT_FAST_MIN_BLOCKS=10", "SPT_FAST_LEAF_QUEUE=4", "SPT_FAST_NODE_STACK=10"],
     "mb8r44": ["SPT_FAST_MIN_BLOCKS=8", "SPT_FAST_NODE_REPS=4", "SPT_FAST_TRI_REPS=4"], "b256mb4": ["SPT_FAST_BLOCK=256", "SPT_FAST_MIN_BLOCKS=4"], "b64mb16": ["SPT_FAST_BLOCK=64", "SPT_FAST_MIN_BLOCKS=16"],
@@ -50,9 +53,9 @@ else:
             p = bench.make_params(w, seed=1)
             tr = []
             for _ in range(3):
-                s.render_resident(p, rebuild_bvh=False, output_stage=False); st = L.stats(); tr.append((st["secondsTraverse"], st["secondsCall"], st["rays"], st["replayedRays"]))
+                s.render_resident(p, rebuild_bvh=False, output_stage=False); st = L.stats(); tr.append((st["secondsTraverse"], st["secondsCall"], st["rays"], st["replayedRays"], st["secondsExpand"], st["secondsFanOut"], st["secondsClassify"], st["secondsGather"]))
             best = min(tr)
-            row = dict(trace_ms=round(best[0] * 1e3, 2), step_ms=round(best[1] * 1e3, 2), trace_Grays=round(best[2] / best[0] / 1e9, 3), replayed=best[3])
+            row = dict(trace_ms=round(best[0] * 1e3, 2), step_ms=round(best[1] * 1e3, 2), trace_Grays=round(best[2] / best[0] / 1e9, 3), replayed=best[3], expand=round(best[4] * 1e3, 2), fan=round(best[5] * 1e3, 2), classify=round(best[6] * 1e3, 2), gather=round(best[7] * 1e3, 2))
             if hasattr(L.lib, "SailorPt_DebugFastStats"):
                 buf = (ctypes.c_ulonglong * 64)()
                 L.lib.SailorPt_DebugFastStats(buf)          # clear
