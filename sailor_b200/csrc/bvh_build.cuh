@@ -123,17 +123,22 @@ namespace spt
 					bs[3 + a] = (bmin == bmax) ? 0.0f : (float)kBins / (bmax - bmin);   // :36-43 (0 = axis skipped)
 				}
 				const uint32_t slot = atomic_add_u32(s.binCounter, 1u);                 // slot order is irrelevant: bins are per node
-				s.binSlot[node] = slot;
-				uint32_t* bins = s.bins + (size_t)slot * kNodeBinWords;
-				const uint32_t kmin = float_key(10e30f), kmax = float_key(-10e30f);     // AABB defaults, Bounds.h:112-113
-				for (uint32_t w = 0; w < 3 * kBins; w++)
-				{
-					uint32_t* b = bins + w * kBinWords;
-					b[0] = 0; b[1] = b[2] = b[3] = kmin; b[4] = b[5] = b[6] = kmax;
-				}
+				s.binSlot[node] = slot;                                                 // the slot's words are reset by BinInitKernel
 			}
 			s.state[node] = st;
 			s.left[node] = 0;
+		}
+	};
+
+	struct BinInitKernel     // one thread per word of the bin slots handed out by PrepareKernel (a node's 168 words were 130 us of serial stores per level)
+	{
+		BuildState s; uint64_t base;      // base: first word of this launch (scenes beyond 2^32 bin words take several)
+		SPT_KERNEL_BODY void operator()(uint32_t i) const
+		{
+			const uint64_t w = base + i;
+			if (w / kNodeBinWords >= *s.binCounter) return;
+			const uint32_t r = (uint32_t)(w % kNodeBinWords) % kBinWords;
+			s.bins[w] = r == 0 ? 0u : (r < 4 ? float_key(10e30f) : float_key(-10e30f));     // AABB defaults, Bounds.h:112-113
 		}
 	};
 
@@ -202,7 +207,13 @@ namespace spt
 		}
 		if (!uniform)
 		{
-			if (active)
+			// the CTA straddles nodes: lanes of one node (contiguous slots, so usually most of the warp) reduce among themselves first and
+			// one of them touches memory - 12 atomics per (warp, node) instead of 12 per triangle.  Around level 12 of a 1 M-triangle build
+			// (nodes of ~250 slots: every CTA straddles two) the per-triangle form spent 0.19 ms per level on the same few addresses.
+			const uint32_t peers = __match_any_sync(0xffffffffu, active ? node : 0xFFFFFFFFu);
+#pragma unroll
+			for (int d = 0; d < 12; d++) k[d] = ((d % 6) < 3) ? __reduce_min_sync(peers, k[d]) : __reduce_max_sync(peers, k[d]);
+			if (active && (threadIdx.x & 31u) == (uint32_t)(__ffs(peers) - 1))
 			{
 				uint32_t* g = s.keys + (size_t)node * 12;
 #pragma unroll
@@ -244,27 +255,42 @@ namespace spt
 			__syncthreads();
 		}
 		const bool active = inRange && node >= levelStart && (s.state[node] & kStBinning);
+		float mnA[3] = { 0.0f, 0.0f, 0.0f }, mxA[3] = { 0.0f, 0.0f, 0.0f }, ccA[3] = { 0.0f, 0.0f, 0.0f };
 		if (active)
 		{
 			const uint32_t tri = s.idxA[p];
 			const V4 a = s.vtx[tri * 3], b = s.vtx[tri * 3 + 1], c = s.vtx[tri * 3 + 2], ce = s.centroid[tri];
-			const float mn[3] = { glm_min(glm_min(a.x, b.x), c.x), glm_min(glm_min(a.y, b.y), c.y), glm_min(glm_min(a.z, b.z), c.z) };
-			const float mx[3] = { glm_max(glm_max(a.x, b.x), c.x), glm_max(glm_max(a.y, b.y), c.y), glm_max(glm_max(a.z, b.z), c.z) };
-			const float cc[3] = { ce.x, ce.y, ce.z };
-			const float* bs = s.binScale + (size_t)node * 6;
-			uint32_t* bins = uniform ? sBins : (s.bins + (size_t)s.binSlot[node] * kNodeBinWords);
+			mnA[0] = glm_min(glm_min(a.x, b.x), c.x); mnA[1] = glm_min(glm_min(a.y, b.y), c.y); mnA[2] = glm_min(glm_min(a.z, b.z), c.z);
+			mxA[0] = glm_max(glm_max(a.x, b.x), c.x); mxA[1] = glm_max(glm_max(a.y, b.y), c.y); mxA[2] = glm_max(glm_max(a.z, b.z), c.z);
+			ccA[0] = ce.x; ccA[1] = ce.y; ccA[2] = ce.z;
+		}
+		// every lane takes part in the votes below (inactive lanes and skipped axes form their own group and write nothing)
+		{
+			const float* bs = active ? s.binScale + (size_t)node * 6 : nullptr;
+			uint32_t* bins = active ? (uniform ? sBins : (s.bins + (size_t)s.binSlot[node] * kNodeBinWords)) : nullptr;
+			uint32_t km[6];
+#pragma unroll
+			for (int d = 0; d < 3; d++) { km[d] = active ? float_key(mnA[d]) : 0xFFFFFFFFu; km[3 + d] = active ? float_key(mxA[d]) : 0u; }
 #pragma unroll
 			for (int ax = 0; ax < 3; ax++)
 			{
-				const float scale = bs[3 + ax];
-				if (scale == 0.0f) continue;
-				int32_t bi = (int32_t)((cc[ax] - bs[ax]) * scale);                      // BVH.cpp:49-50
+				const float scale = active ? bs[3 + ax] : 0.0f;
+				const bool on = active && scale != 0.0f;
+				int32_t bi = on ? (int32_t)((ccA[ax] - bs[ax]) * scale) : 0;            // BVH.cpp:49-50
 				bi = bi < (int32_t)kBins - 1 ? bi : (int32_t)kBins - 1;
 				if (bi < 0) bi = 0;
-				uint32_t* bn = bins + ((uint32_t)ax * kBins + (uint32_t)bi) * kBinWords;
-				atomicAdd(bn, 1u);
+				// lanes of the same (node, bin) reduce among themselves: one lane per group does the 7 atomics (count, 3 min keys, 3 max keys)
+				const uint32_t peers = __match_any_sync(0xffffffffu, on ? ((node << 3) | (uint32_t)bi) : 0xFFFFFFFFu);
+				uint32_t r[6];
 #pragma unroll
-				for (int d = 0; d < 3; d++) { atomicMin(bn + 1 + d, float_key(mn[d])); atomicMax(bn + 4 + d, float_key(mx[d])); }
+				for (int d = 0; d < 3; d++) { r[d] = __reduce_min_sync(peers, km[d]); r[3 + d] = __reduce_max_sync(peers, km[3 + d]); }
+				if (on && (threadIdx.x & 31u) == (uint32_t)(__ffs(peers) - 1))
+				{
+					uint32_t* bn = bins + ((uint32_t)ax * kBins + (uint32_t)bi) * kBinWords;
+					atomicAdd(bn, (uint32_t)__popc(peers));
+#pragma unroll
+					for (int d = 0; d < 3; d++) { atomicMin(bn + 1 + d, r[d]); atomicMax(bn + 4 + d, r[3 + d]); }
+				}
 			}
 		}
 		if (uniform)

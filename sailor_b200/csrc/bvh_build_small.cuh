@@ -83,6 +83,7 @@ namespace spt
 			BlockFor(cnt, InitNodesKernel{ s, start });
 			BlockFor(N, BoundsKernel{ s, start });
 			BlockFor(cnt, PrepareKernel{ s, start });
+			BlockFor(*s.binCounter * kNodeBinWords, BinInitKernel{ s, 0ull });
 			BlockFor(N, BinKernel{ s, start });
 			BlockFor(cnt, SplitKernel{ s, start });
 			BlockFor(N, FlagKernel{ s, start });

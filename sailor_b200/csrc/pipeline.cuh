@@ -332,6 +332,10 @@ namespace spt
 				launch_for(ctx, cnt, InitNodesKernel{ s, start });
 				LaunchBuildBounds(ctx, s, start);
 				launch_for(ctx, cnt, PrepareKernel{ s, start });
+				{
+					const uint64_t words = (uint64_t)(cnt < maxBinned ? cnt : maxBinned) * kNodeBinWords;
+					for (uint64_t base = 0; base < words; base += 1ull << 30) launch_for(ctx, (uint32_t)(words - base < (1ull << 30) ? words - base : (1ull << 30)), BinInitKernel{ s, base });
+				}
 				LaunchBuildBin(ctx, s, start);
 				launch_for(ctx, cnt, SplitKernel{ s, start });
 				launch_for(ctx, N, FlagKernel{ s, start });
