@@ -85,9 +85,12 @@ namespace spt
 	__device__ __forceinline__ V4 ld4(const V4* p) { const float4 f = __ldg(reinterpret_cast<const float4*>(p)); V4 r; r.x = f.x; r.y = f.y; r.z = f.z; r.w = f.w; return r; }
 	__device__ __forceinline__ uint4 ld4u(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 	__device__ __forceinline__ float ldf(const float* p) { return __ldg(p); }
+	// start fetching a line whose address is known long before the (conditional, sequential) code that reads it gets there
+	__device__ __forceinline__ void prefetch(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 	__device__ __forceinline__ uint32_t ldu(const uint32_t* p) { return __ldg(p); }
 #else
 	inline V4 ld4(const V4* p) { return *p; }
+	inline void prefetch(const void*) {}
 	inline float ldf(const float* p) { return *p; }
 	inline uint32_t ldu(const uint32_t* p) { return *p; }
 	struct U4 { uint32_t x, y, z, w; };

@@ -63,18 +63,21 @@ namespace spt
 		kNfLevel0 = 128u,       // parent = pixel, parentAux = primary-sample index
 	};
 
-	// One Raytrace() activation (:622).  Rows 1-6 are written when the record is created, rows 7-8 by expand/gather.
+	// One Raytrace() activation (:622), four 32-byte sectors: [0] the ray and its closest hit (expand; classify only for thick volumes),
+	// [1] what classify reads of an OWNER when one of its importance rays hit (rows 4-5), [2]-[3] everything gather reads and everything
+	// expand / gather write (rows 5-8) - a classify pass and a gather pass each move half a record.
 	struct alignas(16) NodeRec
 	{
-		V3 rayO; uint32_t parent;            // parent record (or pixel for level 0)
-		V3 rayD; uint32_t parentAux;         // global RayAux index of the importance sample this activation hangs on; kNone for alpha/tail children
+		V3 rayO; float envIor;
+		V3 rayD; uint32_t pad0;
 		float t, u, v; uint32_t tri;         // closest hit of (rayO, rayD)
-		float inAcc, envIor; uint32_t bounces; uint32_t flags;   // bounces = bounceLimit | params.m_maxBounces << 16
-		uint64_t rngKey; uint32_t auxBase; uint32_t child;       // auxBase: first RayAux of this record; child: alpha / tail child record
-		uint32_t pNumSamples, pNumAmbient, nA, nS;               // params.m_numSamples / m_numAmbientSamples; loop counts of :716-717
-		V3 emissive; float alpha;            // sample.m_emissive, sample.m_baseColor.a
-		V3 result; uint32_t nLights;
+		float inAcc; uint32_t pNum; uint64_t rngKey;             // pNum: params.m_numSamples | params.m_numAmbientSamples << 16 of this activation
+		uint32_t bounces, flags, auxBase; float alpha;           // bounces = bounceLimit | params.m_maxBounces << 16; auxBase: first RayAux of this record; alpha: sample.m_baseColor.a
+		uint32_t parent, parentAux, nA, nS;                      // parent record (or pixel for level 0); global RayAux index of the importance sample this activation hangs on (kNone for alpha / tail children); loop counts of :716-717
+		V3 emissive; uint32_t child;         // sample.m_emissive; alpha / tail child record
+		V3 result; uint32_t pad1;
 	};
+	SPT_HD uint32_t PackNum(uint32_t samples, uint32_t ambient) { return (samples & 0xFFFFu) | (ambient << 16); }      // both <= 65535 (checked by RenderFrame)
 	static_assert(sizeof(NodeRec) == 128, "NodeRec layout");
 
 	// ray kinds (RayAux::tag low 3 bits) and state bits.  Whether a ray hit anything is NOT in the tag: the trace kernel writes
@@ -138,8 +141,8 @@ namespace spt
 		const PrimaryHitRec* hitQueue; uint32_t queueBegin, queueCount;     // first hits [queueBegin, queueBegin+queueCount) are level 0
 		NodeRec* recs; uint32_t recCap;
 		RayAux* aux; uint32_t auxCap; uint32_t hasSky;                       // hasSky: the scene has thick transmissive materials (TraceSky can continue)
-		RayRec* rays; Hit* hits; uint32_t rayCap;                             // ray queue of the current level (hits: only rays on the slow list)
-		uint8_t* status; uint32_t* slowList;                                  // per RayAux: 1 = the ray hit something (written by the trace kernel); level-local indices of rays for ClassifyKernel
+		RayRec* rays; Hit* hits; uint32_t rayCap;                             // ray queue of the current level (hits: scratch of the traversal probe)
+		uint8_t* status; SlowRec* slow;                                       // per RayAux: 1 = the ray hit something (written by the trace kernel); closest-hit queries that hit, for ClassifyKernel
 		SkyState* sky[2]; RayRec* skyRays; Hit* skyHits; uint32_t skyCap;
 		ShadeCtx* fan; uint32_t fanCap; uint32_t* fanSlots[2];                // activations whose samples are produced by FanOutKernel; 8-lane slot tables (4 x fanCap each)
 		BatchCounters* c;
@@ -368,11 +371,12 @@ namespace spt
 		WriteAux(a, g, term.x, term.y, term.z, pdf, newIor, kRkSample | (transRay ? kRsTransRay : 0u), c.rec);
 	}
 
-	// ---- level 0: first hits of the primary pass become records --------------------------------------------------
+	// ---- level 0: first hits of the primary pass become records (inside ExpandKernel: a separate pass wrote 128 bytes per first hit that
+	// expand read back at once) ------------------------------------------------------------------------------------
 	struct SeedKernel
 	{
 		IntegratorArgs a;
-		SPT_KERNEL_BODY void operator()(uint32_t i) const
+		SPT_KERNEL_BODY NodeRec Make(uint32_t i) const
 		{
 			const PrimaryHitRec rec = a.hitQueue[a.queueBegin + i];
 			const uint32_t x = rec.pixel % a.cam.width, y = rec.pixel / a.cam.width;
@@ -385,9 +389,9 @@ namespace spt
 			n.t = rec.t; n.u = rec.u; n.v = rec.v; n.tri = rec.tri;
 			n.inAcc = 1.0f; n.envIor = 1.0f; n.bounces = a.maxBounces | (a.maxBounces << 16); n.flags = kNfLevel0;
 			n.rngKey = ChildRngKey(rng.key, 0x7FFFFFFFu); n.auxBase = 0; n.child = kNone;
-			n.pNumSamples = a.numSamples; n.pNumAmbient = a.numAmbientSamples; n.nA = 0; n.nS = 0;
-			n.emissive = v3(0.0f); n.alpha = 1.0f; n.result = v3(0.0f); n.nLights = 0;
-			a.recs[i] = n;
+			n.pNum = PackNum(a.numSamples, a.numAmbientSamples); n.pad0 = 0; n.nA = 0; n.nS = 0;
+			n.emissive = v3(0.0f); n.alpha = 1.0f; n.result = v3(0.0f); n.pad1 = 0;
+			return n;
 		}
 	};
 
@@ -506,18 +510,21 @@ namespace spt
 			c.t = 0.0f; c.u = 0.0f; c.v = 0.0f; c.tri = kNoHit;
 			c.inAcc = inAcc; c.envIor = envIor; c.bounces = bounceLimit | (pMaxBounces << 16); c.flags = kNfDone;   // a miss is final (:873-876); a hit clears kNfDone (ClassifyKernel)
 			c.rngKey = ChildRngKey(n.rngKey, slot); c.auxBase = 0; c.child = kNone;
-			c.pNumSamples = pNumSamples; c.pNumAmbient = pNumAmbient; c.nA = 0; c.nS = 0;
-			c.emissive = v3(0.0f); c.alpha = 1.0f; c.result = a.ambient; c.nLights = 0;
+			c.pNum = PackNum(pNumSamples, pNumAmbient); c.pad0 = 0; c.nA = 0; c.nS = 0;
+			c.emissive = v3(0.0f); c.alpha = 1.0f; c.result = a.ambient; c.pad1 = 0;
 			a.recs[ci] = c;
 			return ci;
 		}
 
 		SPT_KERNEL_BODY void operator()(uint32_t ri) const
 		{
-			NodeRec n = a.recs[ri];
+			NodeRec n;
+			if (level == 0u) { n = SeedKernel{ a }.Make(ri); a.recs[ri] = n; }          // level 0 = the batch's first hits, records [0, queueCount)
+			else n = a.recs[ri];
 			if (n.flags & kNfDone) return;
 			LevelInfo* L = &a.c->level[level];
 			const uint32_t bounceLimit = n.bounces & 0xFFFFu, pMaxBounces = n.bounces >> 16;
+			const uint32_t pNumSamples = n.pNum & 0xFFFFu, pNumAmbient = n.pNum >> 16;
 			Ctx2 cx; cx.rng.key = n.rngKey; cx.rng.counter = 0;
 			cx.seedX = cx.rng.Seed681(); cx.seedY = cx.rng.Seed681();                   // :626-627
 
@@ -537,9 +544,9 @@ namespace spt
 				tangent.y * nrm.x + bitangent.y * nrm.y + faceNormal.y * nrm.z,
 				tangent.z * nrm.x + bitangent.z * nrm.y + faceNormal.z * nrm.z));
 			const bool alphaBlend = !s.opaque && s.baseColor.w < 1.0f;
-			const uint32_t sRound = (uint32_t)roundf(s.baseColor.w * (float)n.pNumSamples), aRound = (uint32_t)roundf(s.baseColor.w * (float)n.pNumAmbient);
-			const uint32_t numSamples = alphaBlend ? (sRound > 1u ? sRound : 1u) : n.pNumSamples;
-			const uint32_t numAmbient = alphaBlend ? (aRound > 1u ? aRound : 1u) : n.pNumAmbient;
+			const uint32_t sRound = (uint32_t)roundf(s.baseColor.w * (float)pNumSamples), aRound = (uint32_t)roundf(s.baseColor.w * (float)pNumAmbient);
+			const uint32_t numSamples = alphaBlend ? (sRound > 1u ? sRound : 1u) : pNumSamples;
+			const uint32_t numAmbient = alphaBlend ? (aRound > 1u ? aRound : 1u) : pNumAmbient;
 			const V3 offset = 0.000001f * faceNormal;
 			const bool fullMetal = s.orm.z == 1.0f;
 			const bool hasTrans = !fullMetal && s.transmission > 0.0f;
@@ -554,11 +561,11 @@ namespace spt
 				const uint32_t base = atomic_inc_u32_agg(&L->rayCount);
 				if (base >= a.rayCap || L->auxBase + base >= a.auxCap) { a.c->overflow = 1u; out->result = v3(0.0f); out->flags = n.flags | kNfDone; return; }
 				const V3 d = nd - offset;
-				const uint32_t ci = SpawnOwn(n, ri, hitPoint, d, bounceLimit - 1u, pMaxBounces, n.pNumSamples, n.pNumAmbient, n.inAcc, 1.0f, 0x40000000u);
+				const uint32_t ci = SpawnOwn(n, ri, hitPoint, d, bounceLimit - 1u, pMaxBounces, pNumSamples, pNumAmbient, n.inAcc, 1.0f, 0x40000000u);
 				WriteRay(a.rays, base, hitPoint, d, tri, ci != kNone);
 				WriteAux(a, L->auxBase + base, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, ci != kNone ? kRkOwn : kRkInactive, ci);
 				out->auxBase = L->auxBase + base; out->child = ci; out->flags = n.flags | kNfTail;
-				out->nLights = 0; out->nA = 0; out->nS = 0;
+				out->nA = 0; out->nS = 0;
 				return;
 			}
 
@@ -632,17 +639,17 @@ namespace spt
 			uint32_t child = kNone;
 			if (alphaChild)
 			{
-				const uint32_t mb = pMaxBounces - 1u, nsm = n.pNumSamples - numSamples, nam = n.pNumAmbient - numAmbient;   // std::max(0u, x) is x
+				const uint32_t mb = pMaxBounces - 1u, nsm = pNumSamples - numSamples, nam = pNumAmbient - numAmbient;   // std::max(0u, x) is x
 				const V3 o = hitPoint + n.rayD * 0.0001f;
-				child = SpawnOwn(n, ri, o, n.rayD, bounceLimit - 1u, mb, (n.pNumSamples > numSamples && nsm > 1u) ? nsm : 1u,
-					(n.pNumAmbient > numAmbient && nam > 1u) ? nam : 1u, n.inAcc * (1.0f - s.baseColor.w), n.envIor, 0x40000001u);
+				child = SpawnOwn(n, ri, o, n.rayD, bounceLimit - 1u, mb, (pNumSamples > numSamples && nsm > 1u) ? nsm : 1u,
+					(pNumAmbient > numAmbient && nam > 1u) ? nam : 1u, n.inAcc * (1.0f - s.baseColor.w), n.envIor, 0x40000001u);
 				WriteRay(a.rays, r, o, n.rayD, tri, child != kNone);
 				WriteAux(a, L->auxBase + r, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, child != kNone ? kRkOwn : kRkInactive, child);
 				r++;
 			}
 			out->auxBase = g0; out->child = child;
 			out->flags = n.flags | (opposite ? kNfOpposite : 0u) | (thick ? kNfThick : 0u) | (alphaBlend ? kNfAlpha : 0u) | (first ? kNfFirst : 0u) | (ambientOn ? kNfAmbientOn : 0u);
-			out->nA = nA; out->nS = nS; out->nLights = a.numLights;
+			out->nA = nA; out->nS = nS;
 			out->emissive = s.emissive; out->alpha = s.baseColor.w;
 		}
 	};
@@ -691,11 +698,12 @@ namespace spt
 		IntegratorArgs a; uint32_t level;
 		SPT_KERNEL_BODY void operator()(uint32_t k) const
 		{
-			const uint32_t i = a.slowList[k];
+			const SlowRec sr = a.slow[k];
+			const uint32_t i = sr.index;
 			const uint32_t g = a.c->level[level].auxBase + i;
 			RayAux x = a.aux[g];
 			const uint32_t kind = x.tag & kRkMask;
-			const Hit h = a.hits[i];
+			Hit h; h.t = sr.t; h.u = sr.u; h.v = sr.v; h.tri = sr.tri;
 			if (kind == kRkInactive || kind == kRkLight || h.tri == kNoHit) return;      // cannot be on the list
 			const uint32_t owner = f2u(x.b1);
 			if (kind == kRkOwn)
@@ -704,12 +712,11 @@ namespace spt
 				c->t = h.t; c->u = h.u; c->v = h.v; c->tri = h.tri; c->flags &= ~kNfDone;
 				return;
 			}
-			const RayRec ray = a.rays[i];
-			const V3 ro = v3(ray.ox, ray.oy, ray.oz), rd = v3(ray.dx, ray.dy, ray.dz);
+			const V3 ro = v3(sr.ox, sr.oy, sr.oz), rd = v3(sr.dx, sr.dy, sr.dz);
 			if (kind == kRkHemi)
 			{
 				const NodeRec* o = a.recs + owner;
-				SkyState s; s.att = v3(1.0f); s.targetAux = g; s.prev = ro; s.ignore = ray.ignoreTri; s.start = ro; s.ior = o->envIor; s.dir = rd;
+				SkyState s; s.att = v3(1.0f); s.targetAux = g; s.prev = ro; s.ignore = a.rays[i].ignoreTri; s.start = ro; s.ior = o->envIor; s.dir = rd;
 				s.jAndMax = 0u | ((o->bounces >> 16) << 16);
 				V3 att;
 				if (SkyAdvance(a, s, h, att)) SkyPush(a, 0, s);
@@ -746,8 +753,8 @@ namespace spt
 					c.t = h.t; c.u = h.u; c.v = h.v; c.tri = h.tri;
 					c.inAcc = newAcc; c.envIor = x.b0; c.bounces = (bounceLimit - 1u) | (pMaxBounces << 16); c.flags = 0;
 					c.rngKey = ChildRngKey(o->rngKey, g - o->auxBase); c.auxBase = 0; c.child = kNone;
-					c.pNumSamples = o->pNumSamples; c.pNumAmbient = o->pNumAmbient; c.nA = 0; c.nS = 0;
-					c.emissive = v3(0.0f); c.alpha = 1.0f; c.result = v3(0.0f); c.nLights = 0;
+					c.pNum = o->pNum; c.pad0 = 0; c.nA = 0; c.nS = 0;
+					c.emissive = v3(0.0f); c.alpha = 1.0f; c.result = v3(0.0f); c.pad1 = 0;
 					a.recs[ci] = c;
 					spawned = true;
 				}
@@ -806,7 +813,17 @@ namespace spt
 			{
 				res = v3(0.0f);
 				uint32_t g = rec->auxBase;
-				const uint32_t nLights = rec->nLights, nA = rec->nA, nS = rec->nS;
+				const uint32_t nLights = a.numLights, nA = rec->nA, nS = rec->nS;
+				// The loops below read the record's entries one dependent load after the other (a light's weight only if its status byte
+				// says unblocked, ...): six DRAM round trips for the three rays of a deep activation.  Everything they will touch is known
+				// now, so it is requested now: the first entries, their status bytes and the parent's entry this result goes to.
+				{
+					const uint32_t total = nLights + ((flags & kNfThick) ? 0u : nA) + nS;
+					prefetch(a.status + g);
+					for (uint32_t j = 0; j < total && j < 8u; j += 4u) prefetch(a.aux + g + j);          // 4 entries per 128-byte line
+					if (total) prefetch(a.aux + g + (total < 8u ? total : 8u) - 1u);
+					if (!(flags & kNfLevel0) && rec->parentAux != kNone) prefetch(a.aux + rec->parentAux);
+				}      // an expanded activation has one shadow ray per light (:691-705)
 				bool blocked = false;                                                     // stale hitLight (:694)
 				for (uint32_t j = 0; j < nLights; j++, g++)
 				{

@@ -88,7 +88,7 @@ namespace spt
 	struct PrimaryPassSink
 	{
 		PrimaryArgs a;
-		__device__ __forceinline__ void Retire(bool finished, uint32_t g, const Hit& h, bool) const
+		__device__ __forceinline__ void Retire(bool finished, uint32_t g, const Hit& h, bool, V3, V3) const
 		{
 			const bool hit = finished && h.tri != kNoHit;
 			uint32_t x = 0, y = 0, sample = 0;
@@ -191,7 +191,7 @@ namespace spt
 		const uint64_t raysPer = lvl0 > lvl1 ? lvl0 : lvl1;
 		const uint64_t auxPer = lvl0 + kDepthFactor * lvl1;
 		const uint64_t recPer = 2u + kDepthFactor * S;
-		const uint64_t bytesPer = raysPer * (sizeof(RayRec) + sizeof(Hit) + 4u) + auxPer * (sizeof(RayAux) + 1u) + recPer * sizeof(NodeRec);
+		const uint64_t bytesPer = raysPer * (sizeof(RayRec) + sizeof(SlowRec)) + auxPer * (sizeof(RayAux) + 1u) + recPer * sizeof(NodeRec);
 		uint64_t B = budget / bytesPer;
 		B >>= shrink;
 		if (B < 1024u) B = 1024u;
@@ -251,6 +251,7 @@ namespace spt
 		const uint32_t msBegin = p.msaaEnd ? p.msaaBegin : 0u, msEnd = p.msaaEnd ? (p.msaaEnd < p.msaa ? p.msaaEnd : p.msaa) : p.msaa;
 		if (rowBegin >= rowEnd || msBegin >= msEnd) { ctx.error = "empty shard"; return SAILOR_PT_ERR_ARG; }
 		if (p.maxBounces > 64u) { ctx.error = "maxBounces > 64 is not supported"; return SAILOR_PT_ERR_LIMIT; }
+		if (p.numSamples > 65535u || p.numAmbientSamples > 65535u) { ctx.error = "more than 65535 samples per first hit are not supported"; return SAILOR_PT_ERR_LIMIT; }
 		const uint32_t rows = rowEnd - rowBegin, ns = msEnd - msBegin;
 		const uint64_t tiles = (uint64_t)((cam.width + 7u) / 8u) * ((rows + 3u) / 4u);
 		const uint64_t total = tiles * ns * 32ull;
@@ -336,11 +337,12 @@ namespace spt
 				a.hitQueue = queue; a.queueBegin = done; a.queueCount = plan.firstHits;
 				a.recs = EnsureBytes<NodeRec>(ctx, renderMem[0], plan.recCap); a.recCap = plan.recCap;
 				a.aux = EnsureBytes<RayAux>(ctx, renderMem[1], plan.auxCap); a.auxCap = plan.auxCap; a.hasSky = hasSky ? 1u : 0u;
-				a.rays = EnsureBytes<RayRec>(ctx, renderMem[2], plan.rayCap); a.hits = EnsureBytes<Hit>(ctx, renderMem[3], plan.rayCap); a.rayCap = plan.rayCap;
+				a.rays = EnsureBytes<RayRec>(ctx, renderMem[2], plan.rayCap); a.slow = EnsureBytes<SlowRec>(ctx, renderMem[13], plan.rayCap); a.rayCap = plan.rayCap;
+				a.hits = reinterpret_cast<Hit*>(a.slow);          // plain hit records: only the traversal probe below writes them, before the level's own trace
 				a.skyCap = hasSky ? plan.skyCap : 16u;
 				a.sky[0] = EnsureBytes<SkyState>(ctx, renderMem[9], (size_t)a.skyCap * 2); a.sky[1] = a.sky[0] + a.skyCap;
 				a.skyRays = EnsureBytes<RayRec>(ctx, renderMem[10], (size_t)a.skyCap * 2); a.skyHits = EnsureBytes<Hit>(ctx, renderMem[11], a.skyCap);
-				a.status = EnsureBytes<uint8_t>(ctx, renderMem[12], plan.auxCap); a.slowList = EnsureBytes<uint32_t>(ctx, renderMem[13], plan.rayCap);
+				a.status = EnsureBytes<uint8_t>(ctx, renderMem[12], plan.auxCap);
 				// the fan-out slot words keep the ShadeCtx index in 24 bits (integrator.cuh): activations beyond 2^24 per batch take the inline path
 				a.fanCap = plan.firstHits + 1024u < (1u << 24) ? plan.firstHits + 1024u : (1u << 24);
 				a.fan = EnsureBytes<ShadeCtx>(ctx, renderMem[8], a.fanCap);
@@ -354,7 +356,6 @@ namespace spt
 					(HostNow() - tFrame0) * 1e3, plan.firstHits, hitCount, done, (double)budget / (1 << 30), plan.rayCap, plan.auxCap, plan.recCap, shrink);
 
 				launch_for(ctx, 1, BeginBatchKernel{ counters, plan.firstHits });
-				launch_for(ctx, plan.firstHits, SeedKernel{ a });
 				uint32_t usedLevels = levels;
 				uint32_t* pin = ctx.Pinned();
 				constexpr int kMarkLevel = 10;                                  // markers 10 / 11: level read-backs (alternating)
@@ -395,9 +396,9 @@ namespace spt
 						if (hostTrace) fprintf(stderr, "[sailor_pt] traversal probe: origin-local %.3f ms, exact %.3f ms -> %s\n", best[0] * 1e3, best[1] * 1e3, useFast ? "origin-local" : "exact");
 					}
 					tt.Begin(ctx);
-					if (useFast) LaunchTraceLevelFast(ctx, fast, view, wb, a.rays, a.hits, plan.rayCap, &L->rayCount, WavefrontOut{ a.status, &L->auxBase, a.slowList, &counters->slowCount });
-					else if (useWide) LaunchTraceLevelWide(ctx, wide, view, wb, a.rays, a.hits, plan.rayCap, &L->rayCount, WavefrontOut{ a.status, &L->auxBase, a.slowList, &counters->slowCount });
-					else LaunchTraceLevel(ctx, view, a.rays, a.hits, plan.rayCap, D.counter.p, &L->rayCount, WavefrontOut{ a.status, &L->auxBase, a.slowList, &counters->slowCount });
+					if (useFast) LaunchTraceLevelFast(ctx, fast, view, wb, a.rays, a.hits, plan.rayCap, &L->rayCount, WavefrontOut{ a.status, &L->auxBase, a.slow, &counters->slowCount });
+					else if (useWide) LaunchTraceLevelWide(ctx, wide, view, wb, a.rays, a.hits, plan.rayCap, &L->rayCount, WavefrontOut{ a.status, &L->auxBase, a.slow, &counters->slowCount });
+					else LaunchTraceLevel(ctx, view, a.rays, a.hits, plan.rayCap, D.counter.p, &L->rayCount, WavefrontOut{ a.status, &L->auxBase, a.slow, &counters->slowCount });
 					tt.End(ctx);
 					st[2].Begin(ctx);
 					launch_for_range<SPT_CLASSIFY_MIN_BLOCKS>(ctx, &counters->zero, &counters->slowCount, plan.rayCap, plan.rayCap, ClassifyKernel{ a, level });

@@ -6,8 +6,9 @@
 // (profiles/r01g_SUMMARY.md).  Every query whose result does not depend on the visit order can start at the other end:
 //
 //   start     in the leaf that holds the ray's own triangle (triStart): its triangles are queued first, nearest geometry first;
-//   UP        one level up (the `up` link kept in every node record): test only the SIBLING box against the current ray length;
-//   DOWN      the ordinary stack walk of a sibling subtree that was hit, then UP again until the root has been passed.
+//   UP        TWO levels up per step: the climb node of the subtree just finished (FastClimbKernel) holds its sibling's box, its parent's
+//             sibling's box and the grandparent's link, laid out like any other node, so an UP step is a DOWN step on that record;
+//   DOWN      the ordinary stack walk of the subtrees that were hit, then UP again until the root has been passed.
 // Every subtree is visited at most once and none is skipped unless its box fails a slab test that is CONSERVATIVE with respect
 // to the reference's own (see FastSlab), so the triangles tested are a superset of those the reference can reach (its slab
 // distances are monotone under box nesting: a leaf whose box passes is reached whatever its ancestors were).  What changes is
@@ -25,8 +26,10 @@
 // records pays the L1TEX pipe per (instruction, 128-byte line): 92 SM cycles for a 64-byte node as 4 x LDG.128, 71 as
 // 2 x LDG.256, 40 for ONE 32-byte LDG.256 — and an SM issues 4 warp instructions per cycle, so every variant of the round-1
 // kernel that read 64-byte nodes with 128-bit loads ran at 80 % L1TEX utilisation however its steps were scheduled.  Hence:
-//   FNode   64 B = two 32-byte halves {child box (fp32, padded outwards), child reference, parent link}.  A DOWN step reads
-//           both halves (2 x LDG.256); an UP step reads only the sibling's half (1 x LDG.256), and the link comes with it.
+//   FNode   64 B = two 32-byte halves {child box (fp32, padded outwards), child reference, parent link}, read as 2 x LDG.256.  The climb
+//           nodes are a second array of the same records (two per inner node).  Round 2 first climbed one level per step (one half of
+//           the parent, 1 x LDG.256); two levels per step cost the same 64 bytes per two levels and half the steps: C3 traversal
+//           81.8 -> 74.5 ms (profiles/r03b_two_level_climb_ab.txt).
 //   FTri    64 B = {v0, e1, e2} in the first 32 + 8 bytes (LDG.256 + LDG.64 per test), the exact box of its leaf behind them
 //           (read once, for the winner).
 //   slab    6 FFMA (b * 1/d - o/d) + 3 FMNMX + 3 FMNMX + 2 FMNMX3-pairs per box instead of the reference's exact
@@ -494,7 +497,7 @@ namespace spt
 					}
 #endif
 					Hit h; h.t = best.t; h.u = best.u; h.v = best.v; h.tri = best.tri;
-					sink.Retire(done && !toReplay, index, h, anyHit);
+					sink.Retire(done && !toReplay, index, h, anyHit, o, d);
 					if (done) active = false;
 				}
 				if (exhausted) { if (freeMask == 0xffffffffu) break; continue; }       // queue exhausted and every lane retired
@@ -676,7 +679,7 @@ namespace spt
 	struct ReplaySink
 	{
 		const uint32_t* list; Inner inner; uint32_t shift;
-		__device__ __forceinline__ void Retire(bool finished, uint32_t i, const Hit& h, bool anyHit) const { inner.Retire(finished, finished ? list[i >> shift] : 0u, h, anyHit); }
+		__device__ __forceinline__ void Retire(bool finished, uint32_t i, const Hit& h, bool anyHit, V3 o, V3 d) const { inner.Retire(finished, finished ? list[i >> shift] : 0u, h, anyHit, o, d); }
 	};
 
 	__global__ void __launch_bounds__(kFastBlock, SPT_FAST_MIN_BLOCKS) k_trace_fast_rays(FastView w, const RayRec* __restrict__ rays, Hit* __restrict__ hits,
@@ -692,7 +695,7 @@ namespace spt
 	{
 		__shared__ uint32_t stackMem[kFastSmemWords];
 		{ const uint32_t m = *nPtr; if (m < n) n = m; }
-		QueueSource src{ rays }; WavefrontSink sink{ hits, out.status + *out.auxBase, out.slowList, out.slowCount };
+		QueueSource src{ rays }; WavefrontSink sink{ out.status + *out.auxBase, out.slow, out.slowCount };
 		TraceFastLoop<SPT_FAST_EXP_MODE>(w, n, counter, stackMem, replay, src, sink);
 	}
 	// The replay list is short (a few thousand rays of a 70 M ray level): a grid of one warp-sized CTA per 32 rays instead of the
@@ -715,7 +718,7 @@ namespace spt
 		if (!n) return;
 		const uint32_t shift = ReplaySpread(n);
 		ReplaySource<QueueSource> src{ list, QueueSource{ rays }, shift };
-		ReplaySink<WavefrontSink> sink{ list, WavefrontSink{ hits, out.status + *out.auxBase, out.slowList, out.slowCount }, shift };
+		ReplaySink<WavefrontSink> sink{ list, WavefrontSink{ out.status + *out.auxBase, out.slow, out.slowCount }, shift };
 		TraceWarpLoop(bvh, n, counter, stackMem, src, sink);
 	}
 
@@ -789,7 +792,7 @@ namespace spt
 				b.counters[3]++;
 			}
 			out.status[*out.auxBase + i] = h.tri != kNoHit ? 1 : 0;
-			if (h.tri != kNoHit && !(rays[i].tmax < 0.0f)) { hits[i] = h; out.slowList[(*out.slowCount)++] = i; }
+			if (h.tri != kNoHit && !(rays[i].tmax < 0.0f)) PushSlow(out, h, rays[i], i);
 		}
 		ctx.kernelLaunches += 3;
 	}

@@ -73,7 +73,7 @@ namespace spt
 	__device__ __forceinline__ bool FiniteF(float f) { return (__float_as_uint(f) & 0x7F800000u) != 0x7F800000u; }
 
 	// The warp loop.  Source: bool Load(uint32_t index, V3& o, V3& d, uint32_t& ignore, float& maxLen, bool& anyHit) (false = nothing to
-	// trace at this index).  Sink: void Retire(bool finished, uint32_t index, const Hit&, bool anyHit) called by ALL lanes each iteration.
+	// trace at this index).  Sink: void Retire(bool finished, uint32_t index, const Hit&, bool anyHit, V3 o, V3 d) called by ALL lanes each iteration.
 	// Lane state is one word: kLaneIdle, an inner node index, or kLeafBit | triangle slot (the next triangle to test).
 #ifndef SPT_VOTE_INNER_BIAS
 #define SPT_VOTE_INNER_BIAS 1      // inner step when nInner * bias >= nLeaf
@@ -242,7 +242,7 @@ namespace spt
 #endif
 				}
 			}
-			sink.Retire(finished, index, hit, anyHit);
+			sink.Retire(finished, index, hit, anyHit, o, d);
 		}
 	}
 
@@ -263,18 +263,18 @@ namespace spt
 	struct QueueSink
 	{
 		Hit* hits;
-		__device__ __forceinline__ void Retire(bool finished, uint32_t i, const Hit& h, bool) const
+		__device__ __forceinline__ void Retire(bool finished, uint32_t i, const Hit& h, bool, V3, V3) const
 		{
 			if (finished) *reinterpret_cast<float4*>(hits + i) = make_float4(h.t, h.u, h.v, __uint_as_float(h.tri));
 		}
 	};
 	// Wavefront levels: every ray leaves ONE status byte (hit or miss).  Only closest-hit queries that hit something (a child
-	// activation or a TraceSky walk may start there) also leave their hit record and a slow-list entry for ClassifyKernel.
-	struct WavefrontOut { uint8_t* status; const uint32_t* auxBase; uint32_t* slowList; uint32_t* slowCount; };
+	// activation or a TraceSky walk may start there) also leave a SlowRec (hit + ray + index) for ClassifyKernel.
+	struct WavefrontOut { uint8_t* status; const uint32_t* auxBase; SlowRec* slow; uint32_t* slowCount; };
 	struct WavefrontSink
 	{
-		Hit* hits; uint8_t* status; uint32_t* slowList; uint32_t* slowCount;     // status already offset by the level's auxBase
-		__device__ __forceinline__ void Retire(bool finished, uint32_t i, const Hit& h, bool anyHit) const
+		uint8_t* status; SlowRec* slowRecs; uint32_t* slowCount;     // status already offset by the level's auxBase
+		__device__ __forceinline__ void Retire(bool finished, uint32_t i, const Hit& h, bool anyHit, V3 o, V3 d) const
 		{
 			const bool hitSomething = h.tri != kNoHit;
 			if (finished) status[i] = hitSomething ? 1 : 0;
@@ -289,8 +289,10 @@ namespace spt
 				base = __shfl_sync(0xffffffffu, base, leader);
 				if (slow)
 				{
-					*reinterpret_cast<float4*>(hits + i) = make_float4(h.t, h.u, h.v, __uint_as_float(h.tri));
-					slowList[base + (uint32_t)__popc(m & ((1u << lane) - 1u))] = i;
+					float4* r = reinterpret_cast<float4*>(slowRecs + (base + (uint32_t)__popc(m & ((1u << lane) - 1u))));
+					r[0] = make_float4(h.t, h.u, h.v, __uint_as_float(h.tri));
+					r[1] = make_float4(o.x, o.y, o.z, __uint_as_float(i));
+					r[2] = make_float4(d.x, d.y, d.z, 0.0f);
 				}
 			}
 		}
@@ -311,7 +313,7 @@ namespace spt
 	{
 		__shared__ uint32_t stackMem[kSmemStack * kTraceBlock];
 		{ const uint32_t m = *nPtr; if (m < n) n = m; }
-		QueueSource src{ rays }; WavefrontSink sink{ hits, out.status + *out.auxBase, out.slowList, out.slowCount };
+		QueueSource src{ rays }; WavefrontSink sink{ out.status + *out.auxBase, out.slow, out.slowCount };
 		TraceWarpLoop(bvh, n, counter, stackMem, src, sink);
 	}
 
@@ -411,8 +413,10 @@ namespace spt
 				out.status[*out.auxBase + i] = hitSomething ? 1 : 0;
 				if (hitSomething && !anyHit)
 				{
-					*reinterpret_cast<float4*>(hits + i) = make_float4(hit.t, hit.u, hit.v, __uint_as_float(hit.tri));
-					out.slowList[atomicAdd(out.slowCount, 1u)] = i;
+					float4* r = reinterpret_cast<float4*>(out.slow + atomicAdd(out.slowCount, 1u));
+					r[0] = make_float4(hit.t, hit.u, hit.v, __uint_as_float(hit.tri));
+					r[1] = make_float4(o.x, o.y, o.z, __uint_as_float(i));
+					r[2] = make_float4(d.x, d.y, d.z, 0.0f);
 				}
 			}
 		}
@@ -443,7 +447,7 @@ namespace spt
 	struct PrimarySink
 	{
 		Hit* hits; PrimarySource src;
-		__device__ __forceinline__ void Retire(bool finished, uint32_t i, const Hit& h, bool) const
+		__device__ __forceinline__ void Retire(bool finished, uint32_t i, const Hit& h, bool, V3, V3) const
 		{
 			if (!finished) return;
 			uint32_t x, y; src.Pixel(i, x, y);
@@ -551,7 +555,12 @@ namespace spt
 			if (rays[i].tmax != -1.0f) TraceClosest(bvh, v3(rays[i].ox, rays[i].oy, rays[i].oz), v3(rays[i].dx, rays[i].dy, rays[i].dz), rays[i].ignoreTri, fabsf(rays[i].tmax), st, hits[i]);
 		ctx.kernelLaunches++;
 	}
-	struct WavefrontOut { uint8_t* status; const uint32_t* auxBase; uint32_t* slowList; uint32_t* slowCount; };
+	struct WavefrontOut { uint8_t* status; const uint32_t* auxBase; SlowRec* slow; uint32_t* slowCount; };
+	inline void PushSlow(const WavefrontOut& out, const Hit& h, const RayRec& r, uint32_t i)
+	{
+		SlowRec s; s.t = h.t; s.u = h.u; s.v = h.v; s.tri = h.tri; s.ox = r.ox; s.oy = r.oy; s.oz = r.oz; s.index = i; s.dx = r.dx; s.dy = r.dy; s.dz = r.dz; s.pad = 0;
+		out.slow[(*out.slowCount)++] = s;
+	}
 	inline void LaunchTraceLevel(Ctx& ctx, const BvhView& bvh, const RayRec* rays, Hit* hits, uint32_t cap, uint32_t*, const uint32_t* nPtr, const WavefrontOut& out)
 	{
 		LocalStack st;
@@ -562,7 +571,7 @@ namespace spt
 			Hit h;
 			TraceClosest(bvh, v3(rays[i].ox, rays[i].oy, rays[i].oz), v3(rays[i].dx, rays[i].dy, rays[i].dz), rays[i].ignoreTri, fabsf(rays[i].tmax), st, h);
 			out.status[*out.auxBase + i] = h.tri != kNoHit ? 1 : 0;
-			if (h.tri != kNoHit && !(rays[i].tmax < 0.0f)) { hits[i] = h; out.slowList[(*out.slowCount)++] = i; }
+			if (h.tri != kNoHit && !(rays[i].tmax < 0.0f)) PushSlow(out, h, rays[i], i);
 		}
 		ctx.kernelLaunches++;
 	}

@@ -72,7 +72,7 @@ namespace spt
 		const uint32_t sTri = sNode + (uint32_t)kWideNodeSmem * (kWideBlock * 8u);
 		uint2 ovf[kWideStackDepth - kWideNodeSmem];
 		const uint32_t lane = threadIdx.x & 31;
-		V3 d = v3(0.0f);
+		V3 d = v3(0.0f), o0 = v3(0.0f);      // o0: the ray's origin as queued (the SlowRec of a closest hit carries it to ClassifyKernel)
 		WideRay r; r.o = v3(0.0f); r.idir = v3(0.0f); r.signs = 0; r.octinv = 0;
 		WideBest best; best.Reset();
 		uint32_t ignore = kNoHit, index = 0;
@@ -123,7 +123,7 @@ namespace spt
 							if (!WideSafe(o, rD)) { toReplay = true; replayIndex = i; }
 							else
 							{
-								index = i; active = true; bad = false;
+								index = i; active = true; bad = false; o0 = o;
 								r.Set(o, d, rD, !anyHit);
 								best.Reset();
 								nsp = 0; tsp = 0; tBits = 0;
@@ -234,7 +234,7 @@ namespace spt
 			}
 			SPT_WL_LANES(11, finished);
 			Hit h; h.t = best.t; h.u = best.u; h.v = best.v; h.tri = best.tri;
-			sink.Retire(finished && !toReplay, index, h, anyHit);
+			sink.Retire(finished && !toReplay, index, h, anyHit, o0, d);
 			if (finished) { active = false; gBits = 0; tBits = 0; nsp = 0; tsp = 0; }
 		}
 	}
@@ -252,7 +252,7 @@ namespace spt
 	{
 		__shared__ uint2 stackMem[kWideSmemEntries * kWideBlock];
 		{ const uint32_t m = *nPtr; if (m < n) n = m; }
-		QueueSource src{ rays }; WavefrontSink sink{ hits, out.status + *out.auxBase, out.slowList, out.slowCount };
+		QueueSource src{ rays }; WavefrontSink sink{ out.status + *out.auxBase, out.slow, out.slowCount };
 		TraceWideLoop(w, n, counter, stackMem, replay, src, sink);
 	}
 	inline int WideGridSize()
@@ -324,7 +324,7 @@ namespace spt
 				b.counters[3]++;
 			}
 			out.status[*out.auxBase + i] = h.tri != kNoHit ? 1 : 0;
-			if (h.tri != kNoHit && !(rays[i].tmax < 0.0f)) { hits[i] = h; out.slowList[(*out.slowCount)++] = i; }
+			if (h.tri != kNoHit && !(rays[i].tmax < 0.0f)) PushSlow(out, h, rays[i], i);
 		}
 		ctx.kernelLaunches += 3;
 	}

@@ -29,6 +29,10 @@ namespace spt
 
 	struct BvhView { const TNode* nodes; const TTri* tris; uint32_t rootRef; uint32_t numNodes, numTris; };
 	struct Hit { float t, u, v; uint32_t tri; };
+	// A closest-hit query of a wavefront level that hit something, as ClassifyKernel needs it: the hit, the ray it belongs to and the ray's
+	// level-local index.  Written by the trace kernels at consecutive positions (one warp-aggregated counter), so classify streams 48-byte
+	// records instead of chasing a list of indices into the ray queue and the hit array (two scattered sectors per entry).
+	struct alignas(16) SlowRec { float t, u, v; uint32_t tri; float ox, oy, oz; uint32_t index; float dx, dy, dz; uint32_t pad; };
 
 	// Math::IntersectRayAABB (Bounds.cpp:582-604). _mm_max_ps/_mm_min_ps return the SECOND operand on NaN.
 	SPT_HD float SlabTest(V3 o, V3 rD, float bminx, float bminy, float bminz, float bmaxx, float bmaxy, float bmaxz, float maxLen)
