@@ -367,6 +367,12 @@ namespace spt
 #ifndef SPT_FAST_TRI_REPS
 #define SPT_FAST_TRI_REPS 4
 #endif
+#ifndef SPT_FAST_NODE_UNROLL
+#define SPT_FAST_NODE_UNROLL SPT_FAST_NODE_REPS     // the repetition loops are unrolled: rolled, the loop control and the re-evaluated lane
+#endif                                              // predicates cost 2.6 % of the kernel (profiles/r03q_unroll_variants.txt: 73.9 -> 71.9 ms on C3)
+#ifndef SPT_FAST_TRI_UNROLL
+#define SPT_FAST_TRI_UNROLL SPT_FAST_TRI_REPS
+#endif
 #ifndef SPT_FAST_NODE_BIAS
 #define SPT_FAST_NODE_BIAS 1       // SPT_FAST_IMMEDIATE: a node step runs when (lanes with a node) * bias >= lanes with a triangle
 #endif
@@ -566,7 +572,7 @@ namespace spt
 			if (nodeMask != 0u && __popc(triMask) < SPT_FAST_TRI_VOTE)
 #endif
 			{
-#pragma unroll 1
+SPT_UNROLL(SPT_FAST_NODE_UNROLL)
 				for (int rep = 0; rep < SPT_FAST_NODE_REPS; rep++)
 				{
 					const bool take = SPT_FAST_CAN_NODE;
@@ -613,7 +619,7 @@ namespace spt
 			}
 			else
 			{
-#pragma unroll 1
+SPT_UNROLL(SPT_FAST_TRI_UNROLL)
 				for (int rep = 0; rep < SPT_FAST_TRI_REPS; rep++)
 				{
 					const bool take = active && tcur != kFastNone;

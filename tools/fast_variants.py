@@ -26,6 +26,12 @@ VARIANTS = {
     "cl4": ["SPT_CLASSIFY_MIN_BLOCKS=4"], "cl5": ["SPT_CLASSIFY_MIN_BLOCKS=5"], "cl6": ["SPT_CLASSIFY_MIN_BLOCKS=6"], "g3": ["SPT_GATHER_MIN_BLOCKS=3"], "g4": ["SPT_GATHER_MIN_BLOCKS=4"], "g6": ["SPT_GATHER_MIN_BLOCKS=6"], "g8": ["SPT_GATHER_MIN_BLOCKS=8"],
     "e3": ["SPT_EXPAND_MIN_BLOCKS=3"], "e1": ["SPT_EXPAND_MIN_BLOCKS=1"], "f5": ["SPT_FAN_MIN_BLOCKS=5"], "f3": ["SPT_FAN_MIN_BLOCKS=3"],
     "lazy0": ["SPT_FAST_LAZY_ANY=0"], "lazy1": ["SPT_FAST_LAZY_ANY=1"], "lazy2": ["SPT_FAST_LAZY_ANY=2"], "lazy3": ["SPT_FAST_LAZY_ANY=3"], "lazy1tv12": ["SPT_FAST_LAZY_ANY=1", "SPT_FAST_TRI_VOTE=12"], "lazy2tv14": ["SPT_FAST_LAZY_ANY=2", "SPT_FAST_TRI_VOTE=14"], "lazy1r24": ["SPT_FAST_LAZY_ANY=1", "SPT_FAST_NODE_REPS=2", "SPT_FAST_TRI_REPS=4"],
+    "un22": ["SPT_FAST_NODE_UNROLL=2", "SPT_FAST_TRI_UNROLL=2"], "un44": ["SPT_FAST_NODE_UNROLL=4", "SPT_FAST_TRI_UNROLL=4"], "un21": ["SPT_FAST_NODE_UNROLL=2"], "un12": ["SPT_FAST_TRI_UNROLL=2"],
+    "un64": ["SPT_FAST_NODE_REPS=6", "SPT_FAST_TRI_REPS=4", "SPT_FAST_NODE_UNROLL=6", "SPT_FAST_TRI_UNROLL=4"], "un55": ["SPT_FAST_NODE_REPS=5", "SPT_FAST_TRI_REPS=5", "SPT_FAST_NODE_UNROLL=5", "SPT_FAST_TRI_UNROLL=5"],
+    "un66": ["SPT_FAST_NODE_REPS=6", "SPT_FAST_TRI_REPS=6", "SPT_FAST_NODE_UNROLL=6", "SPT_FAST_TRI_UNROLL=6"], "un46": ["SPT_FAST_NODE_REPS=4", "SPT_FAST_TRI_REPS=6", "SPT_FAST_NODE_UNROLL=4", "SPT_FAST_TRI_UNROLL=6"],
+    "un33": ["SPT_FAST_NODE_REPS=3", "SPT_FAST_TRI_REPS=3", "SPT_FAST_NODE_UNROLL=3", "SPT_FAST_TRI_UNROLL=3"], "un43": ["SPT_FAST_NODE_REPS=4", "SPT_FAST_TRI_REPS=3", "SPT_FAST_NODE_UNROLL=4", "SPT_FAST_TRI_UNROLL=3"],
+    "un84": ["SPT_FAST_NODE_REPS=8", "SPT_FAST_TRI_REPS=4", "SPT_FAST_NODE_UNROLL=8", "SPT_FAST_TRI_UNROLL=4"],
+    "ex2": ["SPT_EXACT_UNROLL=2"], "ex4": ["SPT_EXACT_UNROLL=4"], "ex8": ["SPT_EXACT_UNROLL=8"],
     "mb9": ["SPT_FAST_MIN_BLOCKS=9"], "mb10": ["SPT_FAST_MIN_BLOCKS=10"], "mb12": ["SPT_FAST_MIN_BLOCKS=12"],
     "mb8q4": ["SPT_FAST_MIN_BLOCKS=8", "SPT_FAST_LEAF_QUEUE=4"], "mb10q4": ["SPT_FAST_MIN_BLOCKS=10", "SPT_FAST_LEAF_QUEUE=4", "SPT_FAST_NODE_STACK=10"],
     "mb8r44": ["SPT_FAST_MIN_BLOCKS=8", "SPT_FAST_NODE_REPS=4", "SPT_FAST_TRI_REPS=4"], "b256mb4": ["SPT_FAST_BLOCK=256", "SPT_FAST_MIN_BLOCKS=4"], "b64mb16": ["SPT_FAST_BLOCK=64", "SPT_FAST_MIN_BLOCKS=16"],
