@@ -49,9 +49,9 @@ typedef struct SailorPtParams {
 	const char* output;           /* m_output (PNG); NULL/"" = do not write a file */
 	const char* camera;           /* m_camera; NULL/"" = first camera */
 	uint32_t height;              /* m_height */
-	uint32_t numSamples;          /* m_numSamples        (S: importance samples at the first hit) */
-	uint32_t numAmbientSamples;   /* m_numAmbientSamples (A: hemisphere samples at the first hit) */
-	uint32_t maxBounces;          /* m_maxBounces */
+	uint32_t numSamples;          /* m_numSamples        (S: importance samples at the first hit; <= 65535, else SAILOR_PT_ERR_LIMIT) */
+	uint32_t numAmbientSamples;   /* m_numAmbientSamples (A: hemisphere samples at the first hit; <= 65535) */
+	uint32_t maxBounces;          /* m_maxBounces (<= 64) */
 	uint32_t msaa;                /* m_msaa (primary samples per pixel) */
 	float ambient[3];             /* m_ambient */
 	/* extensions */

@@ -134,6 +134,21 @@ def test_error_paths(emu, tmp_path):
             s.build_bvh()
 
 
+def test_render_limits_are_errors_not_wrong_images(emu, scene_dir):
+    """An activation record keeps the two per-hit sample counts in 16 bits each and the recursion depth in 16 bits (maxBounces <= 64):
+    a request beyond that is refused (SAILOR_PT_ERR_LIMIT) instead of rendered with wrapped counts."""
+    from sailor_b200.capi import ERR_LIMIT, SailorPtError
+    path = _scene(scene_dir, "cube", {})
+    base = dict(height=8, camera="main_cam", msaa=1, ambient=(1, 1, 1), seed=1)
+    with emu.load_scene(path) as s:
+        for kw in (dict(num_samples=70000, num_ambient_samples=1, max_bounces=1), dict(num_samples=1, num_ambient_samples=65536, max_bounces=1),
+                   dict(num_samples=1, num_ambient_samples=1, max_bounces=65)):
+            with pytest.raises(SailorPtError) as e:
+                s.render(Params(**base, **kw))
+            assert e.value.code == ERR_LIMIT
+        s.render(Params(num_samples=1, num_ambient_samples=1, max_bounces=1, **base))          # the scene object is still usable
+
+
 def test_render_is_deterministic_and_partition_invariant(emu, scene_dir):
     """Row shards and primary-sample shards reassemble to the unsharded image (the multi-GPU contract)."""
     path = _scene(scene_dir, "pbr", {})
