@@ -161,19 +161,22 @@ namespace spt
 	// Working-set budget of one batch of first hits: 40 GiB of the B200's 180 GB (a whole C2 frame is then ONE batch: every batch
 	// boundary costs a host round trip, and a descheduled host thread shows up as an idle GPU), never more than a third of what the device
 	// can still give (`held` = bytes the scene's arenas already own, which the batch reuses).  Decided once per frame.
+	inline std::mutex& BudgetCacheMutex() { static std::mutex m; return m; }
+	inline double* BudgetCacheTimes() { static double t[64] = {}; return t; }          // 0 = ask the driver again
 	inline uint64_t BatchBudget(uint64_t held)
 	{
 		uint64_t budget = 40960ull << 20;
-		// cudaMemGetInfo goes through the driver's resource-manager lock and was seen to block for tens of milliseconds on a busy
-		// box (profiles/r01g_SUMMARY.md): ask at most once every few seconds
-		// (one cache entry per device: a multi-device render asks from one host thread per device)
-		static std::mutex m; static uint64_t cachedFreeOf[64] = {}; static double cachedAtOf[64] = {};
+		// cudaMemGetInfo goes through the driver's resource-manager lock: tens of milliseconds on a busy box (profiles/r01g_SUMMARY.md), and
+		// 0.2-0.4 s when two host threads of a multi-device frame ask while both devices are busy (profiles/r03_SUMMARY.md: every frame that
+		// fell on the former 5-second refresh).  Free + held memory of a device only changes when somebody else allocates on it, so it is asked
+		// once, again after five minutes, and after SailorPt_TrimMemory (one cache entry per device).
 		const int dev = DevCurrent() & 63;
 		const double now = HostNow();
 		uint64_t cachedFree;
 		{
-			std::lock_guard<std::mutex> lock(m);
-			if (cachedAtOf[dev] == 0.0 || now - cachedAtOf[dev] > 5.0) { cachedFreeOf[dev] = (uint64_t)DevMemAvailable() + held; cachedAtOf[dev] = now; }
+			std::lock_guard<std::mutex> lock(BudgetCacheMutex());
+			double* cachedAtOf = BudgetCacheTimes(); static uint64_t cachedFreeOf[64] = {};
+			if (cachedAtOf[dev] == 0.0 || now - cachedAtOf[dev] > 300.0) { cachedFreeOf[dev] = (uint64_t)DevMemAvailable() + held; cachedAtOf[dev] = now; }
 			cachedFree = cachedFreeOf[dev];
 		}
 		const uint64_t avail = cachedFree / 3u;
@@ -232,6 +235,7 @@ namespace spt
 		std::lock_guard<std::mutex> frameLock(arenas.frame);
 		ctx.Sync();
 		for (PlainBuf& b : arenas.mem) { if (b.p) DevFreePlain(b.p); b.p = nullptr; b.n = 0; }
+		{ std::lock_guard<std::mutex> lock(BudgetCacheMutex()); BudgetCacheTimes()[DevCurrent() & 63] = 0.0; }
 	}
 
 	inline bool SceneHasThickTransmission(const HostScene& h)
