@@ -77,7 +77,7 @@ def random_rays(n, seed, scale=1.5):
     return o, d
 
 
-def surface_rays(tris, n, seed):
+def surface_rays(tris, n, seed, far_corner=False):
     """Rays as the integrator emits them: origins ON random triangles (offset 1e-6 along the face normal, like
     PathTracer.cpp:667), random directions, the origin's triangle as `ignore`.  tris: (N, 51) flattened triangles."""
     r = np.random.RandomState(seed)
@@ -90,10 +90,15 @@ def surface_rays(tris, n, seed):
     d = r.normal(size=(n, 3))
     d /= np.linalg.norm(d, axis=1, keepdims=True)
     o = p + 1e-6 * fn * np.where(r.uniform(size=(n, 1)) < 0.5, -1.0, 1.0)
+    # rays aimed exactly at the far corner (+M, -M, +M) that stands in for the missing second level of the root's climb nodes
+    # (trace_fast.cuh, FastClimbKernel): an unnormalised (1, -1, 1) "hits" that point box and walks the tree once more from the root
+    if far_corner and n >= 64:
+        d[-16:-8] = (1.0, -1.0, 1.0)
+        d[-8:] = np.array((1.0, -1.0, 1.0)) / np.sqrt(3.0)
     return o.astype(np.float32), d.astype(np.float32), k.astype(np.uint32)
 
 
-def check_random_rays(lib, oracle, path, n=20000, seed=1):
+def check_random_rays(lib, oracle, path, n=20000, seed=1, far_corner=False):
     """BVH::IntersectBVH on random, degenerate and secondary-ray shaped queries: the exact kernel, and the two traversal variants
     the integrator uses for secondary rays (origin-local walk, wide layout) with their exact replay of ambiguous rays -- all bit
     for bit the oracle's closest hit; hit-or-miss queries give the same boolean."""
@@ -102,7 +107,7 @@ def check_random_rays(lib, oracle, path, n=20000, seed=1):
     with lib.load_scene(path) as a, oracle.load_scene(path) as b:
         nt = a.counts()["triangles"]
         ignore = np.random.RandomState(seed + 1).randint(0, nt, n).astype(np.uint32)
-        so, sd, sk = surface_rays(b.triangles()[0], n, seed + 2)
+        so, sd, sk = surface_rays(b.triangles()[0], n, seed + 2, far_corner)
         cases = [("surface", so, sd, sk, b.intersect_rays(so, sd, sk)), ("random", o, d, None, b.intersect_rays(o, d)), ("random+ignore", o, d, ignore, b.intersect_rays(o, d, ignore))]
         for tag, ro, rd, ig, ref in cases:
             assert_hits_equal(a.intersect_rays(ro, rd, ig), ref)

@@ -89,7 +89,7 @@ def test_fast_walks_on_small_scenes(emu, oracle, scene_dir, name, kw, monkeypatc
     """Scenes the shared-memory kernel normally takes, forced through the origin-local walk and the wide layout (+ exact replay)."""
     monkeypatch.setenv("SAILOR_PT_FORCE_WIDE", "1")
     monkeypatch.setenv("SAILOR_PT_FORCE_LOCAL", "1")
-    pc.check_random_rays(emu, oracle, _scene(scene_dir, name, kw), n=6000)
+    pc.check_random_rays(emu, oracle, _scene(scene_dir, name, kw), n=6000, far_corner=True)
 
 
 def test_bvh_of_ragged_scenes(emu, oracle, scene_dir, tmp_path):
