@@ -13,10 +13,11 @@
 //              at once — D shadow rays (:691-705), nA hemisphere rays (:720-737), nS importance rays (:753-784), the
 //              alpha continuation / thick-volume tail ray — into the level's ray queue, with a 32-byte RayAux per
 //              ray that carries what the ray's result will be weighted with (BRDF, term, pdf, ...)
-//   trace    : closest hit for the whole queue (traverse.cuh, persistent threads)
-//   classify : one thread per ray: misses and shadow tests are final and are folded into the RayAux in place; an
-//              importance ray that hit something and passes the throughput cut (:810-811) spawns a child record of
-//              level d+1 that starts from this very hit (the reference re-traces the same ray at :632)
+//   trace    : one launch for the whole queue (trace_kernels.cuh / trace_fast.cuh, persistent threads): a status byte per ray (hit or
+//              miss is all a shadow test, a hemisphere ray or an importance ray below the throughput cut needs), and a SlowRec (hit +
+//              ray + index) per closest-hit query that hit something
+//   classify : one thread per SlowRec: an importance ray that hit something and passes the throughput cut (:810-811) spawns a child
+//              record of level d+1 that starts from this very hit (the reference re-traces the same ray at :632)
 //   sky      : TraceSky continuations through thick transmissive surfaces (:591-616), a small side queue
 //   gather   : bottom-up, one thread per record: replays the accumulation of :690-871 over the record's RayAux
 //              entries IN INDEX ORDER (lights, hemisphere, importance samples) and hands  clamp(term*att*L)  to the

@@ -4,7 +4,7 @@
 //                  shard.  Misses are final (Raytrace returns the ambient colour, :873-876) and are written straight
 //                  to the per-sample buffer; hits are appended to a compact first-hit queue (warp-aggregated atomics).
 //   wavefront      the first hits are processed in batches; a batch evaluates the reference's recursion tree level by
-//                  level (integrator.cuh): [expand, trace, classify, (sky), next-level] per level, then gather bottom-up.
+//                  level (integrator.cuh): [expand (level 0: from the first-hit queue), fan-out, trace, classify, (sky), next-level] per level, then gather bottom-up.
 //                  Level sizes live in device memory, so a whole batch is queued without host synchronisation; the
 //                  host reads one small word (overflow flag + ray count) per batch.
 //   resolve        accumulator = sum over the pixel's primary samples in index order / msaa, row flip (:449,468-469).
@@ -211,8 +211,8 @@ namespace spt
 	}
 
 	// Wavefront working set, shared by every scene object of the process on one device and kept for the life of the process (it
-	// only ever grows): 0 activation records, 1 RayAux arena, 2 rays, 3 hits, 4 per-sample results, 5 primary-hit queue, 6 batch
-	// counters, 7 blue-noise table, 8 fan-out contexts, 9 sky states, 10 sky rays, 11 sky hits, 12 ray status bytes, 13 slow list,
+	// only ever grows): 0 activation records, 1 RayAux arena, 2 rays, 3 (unused), 4 per-sample results, 5 primary-hit queue, 6 batch
+	// counters, 7 blue-noise table, 8 fan-out contexts, 9 sky states, 10 sky rays, 11 sky hits, 12 ray status bytes, 13 SlowRec stream (closest hits for classify),
 	// 14 fan-out slot tables, 15 replay list of the wide traversal.  A host that creates one scene object per frame (the reference's PathTracer object per Run) would
 	// otherwise allocate and free tens of GiB of arenas every frame (~1.5 ms per C2 frame even from the stream-ordered pool); plain
 	// cudaMalloc memory, because a stream-ordered allocation must be freed on a stream that may no longer exist.  One
